@@ -1,0 +1,719 @@
+// C ABI (include/dfr2d.h) of the B200 DFR2D library: problem upload, partition extraction,
+// stage sequencing.  All arithmetic lives in the kernels; this file never touches solution data
+// on the host except to copy it in or out.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "dfr2d_kernels.cuh"
+#include "dfr2d_diss_kernels.cuh"
+
+using namespace dfr2d;
+
+static thread_local std::string g_create_error;
+
+struct dfr2d_handle {
+    int N = 0, device = 0, nParts = 1, part = 0;
+    int64_t Kglobal = 0, k0 = 0, k1 = 0;
+    int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
+    int NpInt = 0, NpEdge = 0, NpFlux = 0;
+    Phys ph{};
+    cudaStream_t stream = 0;
+    std::string err;
+    std::vector<void *> allocs;
+    std::vector<double> opsHost;      // Ops<N> image for constant memory
+    // state
+    double *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // q[4] aliases q[1] (Q1 is dead after stage 1)
+    double *R = nullptr, *qface = nullptr, *eflux = nullptr, *agg = nullptr, *DT = nullptr, *rhsScratch = nullptr;
+    double *Jdet = nullptr, *Jinv = nullptr, *IInII = nullptr;
+    int *etoe = nullptr;
+    // edges
+    int *ekL = nullptr, *ekR = nullptr, *emeta = nullptr;
+    double *enx = nullptr, *eny = nullptr, *eoohk = nullptr, *bpx = nullptr, *bpy = nullptr;
+    // dissipation
+    DissBuffers ds{};
+    // halo
+    std::vector<int64_t> sendCounts, recvCounts;
+    int64_t sendTotal = 0, recvTotal = 0;
+    double *sendBuf = nullptr, *recvBuf = nullptr;
+    int *sendElem = nullptr, *sendRow0 = nullptr, *recvCol = nullptr, *recvRow0 = nullptr;
+    int nSendEdges = 0, nRecvEdges = 0;
+    // time loop
+    DevScalars *sc = nullptr;
+    DevScalars *scHost = nullptr;     // pinned
+    long long stageCounter = 0, stepIndex = 0, launches = 0;
+    bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
+    int edgeBlocks = 0;
+    bool smemAttrSet = false;
+};
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return 2;                                                                                   \
+        }                                                                                               \
+    } while (0)
+
+template <typename T> static int dev_alloc(dfr2d_handle *h, T **p, size_t n) {
+    void *d = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&d, n * sizeof(T));
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return 2;
+    }
+    h->allocs.push_back(d);
+    *p = (T *)d;
+    return 0;
+}
+
+template <typename T> static int dev_upload(dfr2d_handle *h, T **p, const std::vector<T> &v, size_t padTo = 0) {
+    size_t n = std::max(v.size(), padTo);
+    if (int rc = dev_alloc(h, p, n)) return rc;
+    CK(cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    if (!v.empty()) CK(cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static void split1d(int64_t maxIndex, int nparts, int n, int64_t *lo, int64_t *hi) {
+    // utils/parallel_utils.go:172-192
+    int64_t npart = maxIndex / nparts, rem = maxIndex % nparts, startAdd = 0, endAdd = 0;
+    if (rem != 0) {
+        if (n + 1 > rem) { startAdd = rem; endAdd = 0; } else { startAdd = n; endAdd = 1; }
+    }
+    *lo = n * npart + startAdd;
+    *hi = *lo + npart + endAdd;
+}
+
+static int bucket_of(int64_t k, int64_t maxIndex, int nparts) {
+    int b = (int)((double)(nparts * k) / (double)maxIndex);
+    b = std::min(std::max(b, 0), nparts - 1);
+    for (;;) {
+        int64_t lo, hi;
+        split1d(maxIndex, nparts, b, &lo, &hi);
+        if (k < lo) b--; else if (k >= hi) b++; else return b;
+    }
+}
+
+template <int N> static void pack_ops(const dfr2d_problem *p, std::vector<double> &out) {
+    out.assign(kOpsDoubles, 0.0);
+    Ops<N> *o = reinterpret_cast<Ops<N> *>(out.data());
+    constexpr int NI = Dim<N>::NpInt, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
+    auto cp = [](double *dst, const double *src, size_t n) { if (src) memcpy(dst, src, n * sizeof(double)); };
+    cp(&o->FEI[0][0], p->FluxEdgeInterp, (size_t)NF3 * NI);
+    cp(&o->DivInt[0][0], p->DivInt, (size_t)NI * NF);
+    cp(&o->V[0][0], p->V, (size_t)NI * NI);
+    cp(&o->Vinv[0][0], p->Vinv, (size_t)NI * NI);
+    cp(&o->M[0][0], p->MassMatrix, (size_t)NI * NI);
+    cp(&o->D[0][0], p->D, (size_t)NI * NI);
+    cp(&o->P[0][0], p->P, (size_t)NI * NI);
+    cp(&o->mf[0], p->ModeFilter, (size_t)NI);
+    cp(&o->Bary[0][0], p->Bary, (size_t)NF * 3);
+    cp(&o->Div[0][0], p->Div, (size_t)NF * NF);
+}
+
+// One operator set is resident in constant memory at a time; re-upload when another handle's set
+// was active (stream ordered).  Concurrent handles with different operators on different streams
+// are not supported (documented in DESIGN.md).
+static const dfr2d_handle *g_ops_owner = nullptr;
+static int ensure_ops(dfr2d_handle *h) {
+    if (g_ops_owner == h) return 0;
+    CK(cudaMemcpyToSymbolAsync(c_ops_raw, h->opsHost.data(), kOpsDoubles * sizeof(double), 0, cudaMemcpyHostToDevice,
+                               h->stream));
+    g_ops_owner = h;
+    return 0;
+}
+
+extern "C" const char *dfr2d_last_error(const dfr2d_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void dfr2d_destroy(dfr2d_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (void *p : h->allocs) cudaFree(p);
+    if (h->scHost) cudaFreeHost(h->scHost);
+    if (g_ops_owner == h) g_ops_owner = nullptr;
+    delete h;
+}
+
+static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
+    const int N = p->N;
+    h->NpInt = (N + 1) * (N + 2) / 2;
+    h->NpEdge = N + 2;
+    h->NpFlux = (N + 2) * (N + 4);
+    const int NI = h->NpInt, NEd = h->NpEdge;
+    CK(cudaSetDevice(h->device));
+    switch (N) {
+        case 0: pack_ops<0>(p, h->opsHost); break;
+        case 1: pack_ops<1>(p, h->opsHost); break;
+        case 2: pack_ops<2>(p, h->opsHost); break;
+        case 3: pack_ops<3>(p, h->opsHost); break;
+        default: pack_ops<4>(p, h->opsHost); break;
+    }
+    // physics block
+    Phys &ph = h->ph;
+    ph.gamma = p->FSFar.Gamma;
+    ph.CFL = p->CFL;
+    ph.FinalTime = p->FinalTime;
+    ph.fs[0] = p->FSFar; ph.fs[1] = p->FSIn; ph.fs[2] = p->FSOut;
+    ph.vortex = p->vortex;
+    ph.sdKappa = (p->Kappa != 0.0) ? p->Kappa : 5.0;         // dissipation.go:140-147
+    ph.Eps0 = 5.0 / 1.5;                                     // fixed before the kappa override
+    ph.S0 = 4.0 / pow((double)(N + 1), 4.0);                 // dissipation.go:500
+    ph.Cdiff = 1.0 / (double)((N + 1) * (N + 1));            // euler.go:958-960
+    ph.Omega = 1.0 * (double)(N * N);                        // edges.go:218-219
+    ph.fluxType = p->flux_type;
+    ph.localDT = p->local_time_stepping ? 1 : 0;
+    ph.dissipation = p->dissipation ? 1 : 0;
+    ph.N = N;
+    ph.maxIter = p->max_iterations;
+
+    // ---- partition (utils.PartitionMap, parallelism.go:179-190) ------------------------------
+    h->Kglobal = p->K;
+    split1d(p->K, h->nParts, h->part, &h->k0, &h->k1);
+    const int64_t k0 = h->k0, k1 = h->k1;
+    h->K = (int)(k1 - k0);
+    auto mine = [&](int64_t k) { return k >= k0 && k < k1; };
+
+    // local edges = every edge touching an owned element; remote sides become ghost columns
+    struct LE { int64_t ge; int l, r; };
+    std::vector<LE> led;
+    led.reserve((size_t)(h->nParts == 1 ? p->NE : 2 * (p->NE / h->nParts) + 1024));
+    std::unordered_map<int64_t, int> ghostOf;
+    std::vector<int64_t> ghostGlobal;
+    auto local_col = [&](int64_t kg) -> int {
+        if (mine(kg)) return (int)(kg - k0);
+        auto it = ghostOf.find(kg);
+        if (it != ghostOf.end()) return h->K + it->second;
+        int g = (int)ghostGlobal.size();
+        ghostOf.emplace(kg, g);
+        ghostGlobal.push_back(kg);
+        return h->K + g;
+    };
+    for (int64_t e = 0; e < p->NE; e++) {
+        const int64_t kl = p->edge_kL[e], kr = (p->edge_nconn[e] == 2) ? p->edge_kR[e] : -1;
+        if (!(mine(kl) || (kr >= 0 && mine(kr)))) continue;
+        led.push_back({e, 0, 0});
+    }
+    // ghosts are numbered in global-edge order so that both sides of a cut agree on the message order
+    for (auto &le : led) {
+        const int64_t e = le.ge;
+        le.l = local_col(p->edge_kL[e]);
+        le.r = (p->edge_nconn[e] == 2) ? local_col(p->edge_kR[e]) : -1;
+    }
+    h->G = (int)ghostGlobal.size();
+    h->Kp = ((h->K + h->G + 31) / 32) * 32;
+    // sort by the owner-side column so that owner-side loads of neighbouring threads coalesce
+    std::stable_sort(led.begin(), led.end(), [](const LE &a, const LE &b) { return a.l < b.l; });
+    h->NE = (int)led.size();
+    h->NEp = ((h->NE + 31) / 32) * 32;
+    h->NV = (int)p->NV;
+    const int Kp = h->Kp, K = h->K;
+
+    std::unordered_map<int64_t, int> slotOfGlobalEdge;
+    if (h->nParts > 1) slotOfGlobalEdge.reserve(led.size() * 2);
+    std::vector<int> slotOfEdgeDense;
+    if (h->nParts == 1) slotOfEdgeDense.assign((size_t)p->NE, -1);
+    std::vector<int> ekL(h->NE), ekR(h->NE), emeta(h->NE);
+    std::vector<double> enx(h->NE), eny(h->NE), eoohk(h->NE), eooLen(h->NE);
+    std::unordered_map<int64_t, int64_t> bpOfEdge;
+    for (int64_t b = 0; b < p->NBP; b++) bpOfEdge.emplace(p->bp_edge[b], b);
+    std::vector<double> bpx, bpy;
+    int nbp = 0;
+    const double np12 = (double)((N + 1) * (N + 1));
+    for (int s = 0; s < h->NE; s++) {
+        const int64_t e = led[s].ge;
+        if (h->nParts == 1) slotOfEdgeDense[e] = s; else slotOfGlobalEdge.emplace(e, s);
+        const int64_t kl = p->edge_kL[e];
+        const int numL = p->edge_numL[e], numR = p->edge_numR[e];
+        ekL[s] = led[s].l;
+        emeta[s] = (numL & 3) | ((numR & 3) << 2) | ((p->edge_bc[e] & 15) << 4);
+        enx[s] = p->FaceNormX[kl + p->K * numL];
+        eny[s] = p->FaceNormY[kl + p->K * numL];
+        const double hK = p->EdgeLenMax[kl] / np12;          // DFR.GetHk (dfr_startup.go:89-98)
+        eoohk[s] = 1.0 / hK;
+        eooLen[s] = 1.0 / p->edge_len[e];
+        if (led[s].r >= 0) {
+            ekR[s] = led[s].r;
+        } else {
+            auto it = bpOfEdge.find(e);
+            if (it == bpOfEdge.end()) {
+                h->err = "boundary edge without edge-point coordinates (bp_edge)";
+                return 3;
+            }
+            ekR[s] = -1 - nbp;
+            for (int i = 0; i < NEd; i++) {
+                bpx.push_back(p->bp_x[it->second * NEd + i]);
+                bpy.push_back(p->bp_y[it->second * NEd + i]);
+            }
+            nbp++;
+        }
+    }
+    h->NBP = nbp;
+    auto slot_of = [&](int64_t e) -> int {
+        return h->nParts == 1 ? slotOfEdgeDense[e] : slotOfGlobalEdge.at(e);
+    };
+
+    // element arrays (SoA, stride Kp)
+    std::vector<double> Jdet((size_t)Kp, 1.0), Jinv((size_t)4 * Kp, 0.0), IInII((size_t)3 * Kp, 0.0);
+    std::vector<int> etoe((size_t)3 * Kp, 0);
+    for (int k = 0; k < K; k++) {
+        const int64_t kg = k0 + k;
+        Jdet[k] = p->Jdet[kg];
+        for (int c = 0; c < 4; c++) Jinv[(size_t)c * Kp + k] = p->Jinv[kg * 4 + c];
+        for (int le = 0; le < 3; le++) {
+            IInII[(size_t)le * Kp + k] = p->IInII[kg + p->K * le];
+            const int64_t e = p->EtoEdge[kg * 3 + le];
+            const int s = slot_of(e);
+            etoe[(size_t)le * Kp + k] = (p->edge_kL[e] == kg) ? s : -1 - s;
+        }
+    }
+
+    // ---- halo lists: for every cut edge the 4 x NpEdge Q_Face values of each side cross once per stage
+    h->sendCounts.assign(h->nParts, 0);
+    h->recvCounts.assign(h->nParts, 0);
+    std::vector<int> sendElem, sendRow0, recvCol, recvRow0;
+    if (h->nParts > 1) {
+        struct Cut { int peer; int64_t ge; int myCol, myNum, ghCol, ghNum; };
+        std::vector<Cut> cuts;
+        for (int s = 0; s < h->NE; s++) {
+            const int64_t e = led[s].ge;
+            if (p->edge_nconn[e] != 2) continue;
+            const int64_t kl = p->edge_kL[e], kr = p->edge_kR[e];
+            if (mine(kl) && mine(kr)) continue;
+            const bool lMine = mine(kl);
+            const int64_t remote = lMine ? kr : kl;
+            Cut c;
+            c.peer = bucket_of(remote, p->K, h->nParts);
+            c.ge = e;
+            c.myCol = lMine ? led[s].l : led[s].r;
+            c.myNum = lMine ? p->edge_numL[e] : p->edge_numR[e];
+            c.ghCol = lMine ? led[s].r : led[s].l;
+            c.ghNum = lMine ? p->edge_numR[e] : p->edge_numL[e];
+            cuts.push_back(c);
+        }
+        std::stable_sort(cuts.begin(), cuts.end(), [](const Cut &a, const Cut &b) {
+            return a.peer != b.peer ? a.peer < b.peer : a.ge < b.ge;
+        });
+        const int64_t per = 4 * NEd;
+        for (auto &c : cuts) {
+            h->sendCounts[c.peer] += per;
+            h->recvCounts[c.peer] += per;
+            sendElem.push_back(c.myCol);
+            sendRow0.push_back(c.myNum * NEd);
+            recvCol.push_back(c.ghCol);
+            recvRow0.push_back(c.ghNum * NEd);
+        }
+        h->nSendEdges = h->nRecvEdges = (int)cuts.size();
+        h->sendTotal = h->recvTotal = per * (int64_t)cuts.size();
+    }
+
+    // ---- device memory -------------------------------------------------------------------------
+    const size_t reg = (size_t)4 * NI * Kp;
+    for (int r = 0; r < 4; r++) {
+        if (int rc = dev_alloc(h, &h->q[r], reg)) return rc;
+        CK(cudaMemset(h->q[r], 0, reg * sizeof(double)));
+    }
+    h->q[4] = h->q[1];
+    if (int rc = dev_alloc(h, &h->R, reg)) return rc;
+    CK(cudaMemset(h->R, 0, reg * sizeof(double)));
+    if (int rc = dev_alloc(h, &h->qface, (size_t)4 * 3 * NEd * Kp)) return rc;
+    CK(cudaMemset(h->qface, 0, (size_t)4 * 3 * NEd * Kp * sizeof(double)));
+    if (int rc = dev_alloc(h, &h->eflux, (size_t)4 * NEd * h->NEp)) return rc;
+    CK(cudaMemset(h->eflux, 0, (size_t)4 * NEd * h->NEp * sizeof(double)));
+    if (int rc = dev_alloc(h, &h->agg, (size_t)h->NEp)) return rc;
+    CK(cudaMemset(h->agg, 0, (size_t)h->NEp * sizeof(double)));
+    if (int rc = dev_alloc(h, &h->DT, (size_t)Kp)) return rc;
+    CK(cudaMemset(h->DT, 0, (size_t)Kp * sizeof(double)));
+    if (int rc = dev_upload(h, &h->Jdet, Jdet)) return rc;
+    if (int rc = dev_upload(h, &h->Jinv, Jinv)) return rc;
+    if (int rc = dev_upload(h, &h->IInII, IInII)) return rc;
+    if (int rc = dev_upload(h, &h->etoe, etoe)) return rc;
+    if (int rc = dev_upload(h, &h->ekL, ekL, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->ekR, ekR, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->emeta, emeta, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->enx, enx, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->eny, eny, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->eoohk, eoohk, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->bpx, bpx)) return rc;
+    if (int rc = dev_upload(h, &h->bpy, bpy)) return rc;
+    if (h->nParts > 1) {
+        if (int rc = dev_alloc(h, &h->sendBuf, (size_t)h->sendTotal)) return rc;
+        if (int rc = dev_alloc(h, &h->recvBuf, (size_t)h->recvTotal)) return rc;
+        if (int rc = dev_upload(h, &h->sendElem, sendElem)) return rc;
+        if (int rc = dev_upload(h, &h->sendRow0, sendRow0)) return rc;
+        if (int rc = dev_upload(h, &h->recvCol, recvCol)) return rc;
+        if (int rc = dev_upload(h, &h->recvRow0, recvRow0)) return rc;
+    }
+    if (ph.dissipation) {
+        // vertices: keep global numbering (vertex arrays are small next to the element arrays)
+        std::vector<int> etov((size_t)3 * Kp, 0);
+        std::vector<double> hk((size_t)Kp, 1.0);
+        for (int k = 0; k < K; k++) {
+            const int64_t kg = k0 + k;
+            for (int v = 0; v < 3; v++) etov[(size_t)v * Kp + k] = p->EToV[kg * 3 + v];
+            hk[k] = p->EdgeLenMax[kg] / np12;
+        }
+        std::vector<double> nxk((size_t)3 * Kp, 0.0), nyk((size_t)3 * Kp, 0.0);
+        for (int k = 0; k < K; k++)
+            for (int le = 0; le < 3; le++) {
+                nxk[(size_t)le * Kp + k] = p->FaceNormX[(k0 + k) + p->K * le];
+                nyk[(size_t)le * Kp + k] = p->FaceNormY[(k0 + k) + p->K * le];
+            }
+        DissBuffers &d = h->ds;
+        if (int rc = dev_upload(h, &d.etov, etov)) return rc;
+        if (int rc = dev_upload(h, &d.hk, hk)) return rc;
+        if (int rc = dev_upload(h, &d.nxk, nxk)) return rc;
+        if (int rc = dev_upload(h, &d.nyk, nyk)) return rc;
+        if (int rc = dev_upload(h, &d.eooLen, eooLen, h->NEp)) return rc;
+        if (int rc = dev_alloc(h, &d.sigma, (size_t)Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.epsk, (size_t)Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.se, (size_t)Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.sigmaV, (size_t)h->NV)) return rc;
+        if (int rc = dev_alloc(h, &d.epsV, (size_t)h->NV)) return rc;
+        if (int rc = dev_alloc(h, &d.dissX, (size_t)4 * h->NpFlux * Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * h->NpFlux * Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.vflux, (size_t)4 * NEd * h->NEp)) return rc;
+        if (int rc = dev_alloc(h, &d.aggv, (size_t)h->NEp)) return rc;
+        if (int rc = dev_alloc(h, &d.DTVisc, (size_t)Kp)) return rc;
+        CK(cudaMemset(d.sigma, 0, (size_t)Kp * sizeof(double)));
+        CK(cudaMemset(d.epsk, 0, (size_t)Kp * sizeof(double)));
+        CK(cudaMemset(d.se, 0, (size_t)Kp * sizeof(double)));
+        CK(cudaMemset(d.sigmaV, 0, (size_t)std::max(h->NV, 1) * sizeof(double)));
+        CK(cudaMemset(d.epsV, 0, (size_t)std::max(h->NV, 1) * sizeof(double)));
+        CK(cudaMemset(d.dissX, 0, (size_t)4 * h->NpFlux * Kp * sizeof(double)));
+        CK(cudaMemset(d.dissY, 0, (size_t)4 * h->NpFlux * Kp * sizeof(double)));
+        CK(cudaMemset(d.vflux, 0, (size_t)4 * NEd * h->NEp * sizeof(double)));
+        CK(cudaMemset(d.aggv, 0, (size_t)h->NEp * sizeof(double)));
+        CK(cudaMemset(d.DTVisc, 0, (size_t)Kp * sizeof(double)));
+    }
+    if (int rc = dev_alloc(h, &h->sc, 1)) return rc;
+    CK(cudaMemset(h->sc, 0, sizeof(DevScalars)));
+    CK(cudaMallocHost(&h->scHost, sizeof(DevScalars)));
+    memset(h->scHost, 0, sizeof(DevScalars));
+
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    h->edgeBlocks = sms * 8;
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+extern "C" int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int device, dfr2d_handle **out) {
+    if (!p || !out) { g_create_error = "null argument"; return 1; }
+    if (p->N < 0 || p->N > DFR2D_MAX_ORDER) { g_create_error = "polynomial order out of range 0..4"; return 1; }
+    if (n_parts < 1 || part < 0 || part >= n_parts || p->K < n_parts) { g_create_error = "bad partition request"; return 1; }
+    if (p->dissipation && n_parts > 1) { g_create_error = "artificial dissipation is single-partition only in this build"; return 1; }
+    dfr2d_handle *h = new dfr2d_handle();
+    h->N = p->N; h->device = device; h->nParts = n_parts; h->part = part;
+    int rc = create_impl(h, p);
+    if (rc) {
+        g_create_error = h->err;
+        dfr2d_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+// ---- state I/O -------------------------------------------------------------------------------------
+static int copy_in(dfr2d_handle *h, double *dst, const double *Q) {
+    CK(cudaSetDevice(h->device));
+    const size_t rows = (size_t)4 * h->NpInt;
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->Kp * sizeof(double), Q + h->k0, (size_t)h->Kglobal * sizeof(double),
+                         (size_t)h->K * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+static int copy_out(dfr2d_handle *h, const double *src, double *Q) {
+    CK(cudaSetDevice(h->device));
+    const size_t rows = (size_t)4 * h->NpInt;
+    CK(cudaMemcpy2DAsync(Q + h->k0, (size_t)h->Kglobal * sizeof(double), src, (size_t)h->Kp * sizeof(double),
+                         (size_t)h->K * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dfr2d_set_state(dfr2d_handle *h, const double *Q) {
+    if (!h || !Q) return 1;
+    h->qfaceValid = false;
+    return copy_in(h, h->q[0], Q);
+}
+extern "C" int dfr2d_get_state(dfr2d_handle *h, double *Q) {
+    if (!h || !Q) return 1;
+    return copy_out(h, h->q[0], Q);
+}
+extern "C" int dfr2d_set_register(dfr2d_handle *h, int reg, const double *Q) {
+    if (!h || !Q || reg < 0 || reg > 4) return 1;
+    h->qfaceValid = false;
+    return copy_in(h, h->q[reg], Q);
+}
+extern "C" int dfr2d_get_register(dfr2d_handle *h, int reg, double *Q) {
+    if (!h || !Q || reg < 0 || reg > 5) return 1;
+    return copy_out(h, reg == 5 ? h->R : h->q[reg], Q);
+}
+
+// ---- launches ---------------------------------------------------------------------------------------
+#define DISPATCH_N(N_, ...)                              \
+    switch (N_) {                                            \
+        case 0: { constexpr int NN = 0; __VA_ARGS__; } break; \
+        case 1: { constexpr int NN = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int NN = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int NN = 3; __VA_ARGS__; } break; \
+        default: { constexpr int NN = 4; __VA_ARGS__; } break; \
+    }
+
+static int launch_check(dfr2d_handle *h, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        h->err = std::string(what) + ": " + cudaGetErrorString(e);
+        return 2;
+    }
+    h->launches++;
+    return 0;
+}
+
+static int run_interp(dfr2d_handle *h, const double *reg) {
+    const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    DISPATCH_N(h->N, (k_interp<NN><<<blocks, kElemThreads, 0, h->stream>>>(h->K, h->Kp, reg, h->qface)));
+    return launch_check(h, "k_interp");
+}
+
+static int run_pack(dfr2d_handle *h) {
+    if (h->nSendEdges == 0) return 0;
+    const int per = 4 * h->NpEdge;
+    const int total = h->nSendEdges * per;
+    k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->NpEdge, h->Kp, h->qface, h->sendElem, h->sendRow0,
+                                                            h->sendBuf);
+    return launch_check(h, "k_halo_pack");
+}
+
+static int run_unpack(dfr2d_handle *h) {
+    if (h->nRecvEdges == 0) return 0;
+    const int per = 4 * h->NpEdge;
+    const int total = h->nRecvEdges * per;
+    k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->NpEdge, h->Kp, h->qface, h->recvCol, h->recvRow0,
+                                                              h->recvBuf);
+    return launch_check(h, "k_halo_unpack");
+}
+
+static int run_edges(dfr2d_handle *h, int rk) {
+    EdgeArgs a{};
+    a.ne = h->NE; a.NEp = h->NEp; a.Kp = h->Kp;
+    a.kL = h->ekL; a.kR = h->ekR; a.meta = h->emeta;
+    a.nx = h->enx; a.ny = h->eny; a.oohk = h->eoohk;
+    a.bpx = h->bpx; a.bpy = h->bpy;
+    a.qface = h->qface; a.eflux = h->eflux; a.agg = h->agg;
+    a.sc = h->sc;
+    a.slot = (int)(h->stageCounter & 1);
+    a.par = (int)(h->stepIndex & 1);
+    a.stepIndex = h->stepIndex;
+    a.ph = h->ph;
+    const int blocks = std::max(1, std::min(h->edgeBlocks, (h->NE + 255) / 256));
+    DISPATCH_N(h->N, (k_edge<NN><<<blocks, 256, 0, h->stream>>>(a)));
+    (void)rk;
+    return launch_check(h, "k_edge");
+}
+
+template <int N> static size_t elem_smem() { return (size_t)12 * Dim<N>::NpInt * kElemsPerBlock * sizeof(double); }
+
+static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
+    ElemArgs a{};
+    a.K = h->K; a.Kp = h->Kp; a.NEp = h->NEp;
+    a.qs = h->q[rk];
+    a.q0 = h->q[0]; a.q1 = h->q[1]; a.q2 = h->q[2]; a.q3 = h->q[3]; a.q4 = h->q[4]; a.R = h->R;
+    a.qface = fuseInterp ? h->qface : nullptr;
+    a.eflux = h->eflux; a.vflux = h->ds.vflux;
+    a.agg = h->agg; a.aggv = h->ds.aggv;
+    a.DT = h->DT; a.DTVisc = h->ds.DTVisc;
+    a.Jdet = h->Jdet; a.Jinv = h->Jinv; a.IInII = h->IInII;
+    a.etoe = h->etoe;
+    a.dissX = h->ds.dissX; a.dissY = h->ds.dissY; a.sigma = h->ds.sigma;
+    a.rhsOut = rhsOut;
+    a.sc = h->sc;
+    a.rk = rk;
+    a.slot = (int)(h->stageCounter & 1);
+    a.par = (int)(h->stepIndex & 1);
+    a.stepIndex = h->stepIndex;
+    a.ph = h->ph;
+    const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->ph.dissipation) {
+        DISPATCH_N(h->N, {
+            const size_t sm = elem_smem_diss<NN>();
+            if (!h->smemAttrSet) cudaFuncSetAttribute(k_elem<NN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_elem<NN, true><<<blocks, kElemThreads, sm, h->stream>>>(a);
+        });
+    } else {
+        DISPATCH_N(h->N, {
+            const size_t sm = elem_smem<NN>();
+            if (!h->smemAttrSet) cudaFuncSetAttribute(k_elem<NN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            k_elem<NN, false><<<blocks, kElemThreads, sm, h->stream>>>(a);
+        });
+    }
+    h->smemAttrSet = true;
+    return launch_check(h, "k_elem");
+}
+
+static int run_diss_prepare(dfr2d_handle *h, int rk) { (void)rk; h->err = "dissipation path not built yet"; return 9; }
+static int run_diss_edges(dfr2d_handle *h, int rk) { (void)rk; h->err = "dissipation path not built yet"; return 9; }
+
+// ---- stage phases (also the multi-process API) ---------------------------------------------------------
+static int stage_prepare(dfr2d_handle *h, int rk) {
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
+    if (h->ph.dissipation) {
+        if (int rc = run_diss_prepare(h, rk)) return rc;     // sensor, vertex merge, limiter, interpolation
+    } else if (!h->qfaceValid) {
+        if (int rc = run_interp(h, h->q[rk])) return rc;
+    }
+    h->qfaceValid = false;
+    return run_pack(h);
+}
+
+static int stage_edges(dfr2d_handle *h, int rk) {
+    CK(cudaSetDevice(h->device));
+    if (int rc = run_unpack(h)) return rc;
+    if (int rc = run_edges(h, rk)) return rc;
+    if (h->ph.dissipation) return run_diss_edges(h, rk);     // gradient + viscous edge flux
+    return 0;
+}
+
+static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
+    CK(cudaSetDevice(h->device));
+    const bool fuse = (rhsOut == nullptr) && !h->ph.dissipation;
+    if (int rc = run_elem(h, rk, rhsOut, fuse)) return rc;
+    if (rhsOut == nullptr) {
+        h->qfaceValid = fuse;
+        h->stageCounter++;
+        if (rk == 4) h->stepIndex++;
+    }
+    return 0;
+}
+
+extern "C" int dfr2d_stage_prepare(dfr2d_handle *h, int rk) { return h ? stage_prepare(h, rk) : 1; }
+extern "C" int dfr2d_stage_edges(dfr2d_handle *h, int rk) { return h ? stage_edges(h, rk) : 1; }
+extern "C" int dfr2d_stage_update(dfr2d_handle *h, int rk) { return h ? stage_update(h, rk, nullptr) : 1; }
+
+extern "C" int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info) {
+    if (!h) return 1;
+    if (!info) return 0;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->scHost, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    info->time = h->scHost->timeOut;
+    info->dt = h->scHost->globalDT;
+    info->steps = h->scHost->steps;
+    info->finished = h->scHost->finished;
+    info->nan_found = h->scHost->nanFlag;
+    if (h->scHost->nanFlag) {
+        h->err = "NAN found";
+        return DFR2D_ERR_NAN;
+    }
+    return 0;
+}
+
+extern "C" int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info) {
+    if (!h) return 1;
+    if (h->nParts > 1) {
+        h->err = "dfr2d_step drives a single partition; multi-partition hosts use the stage calls with their own exchange";
+        return 1;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        if (h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) break;   // host-visible half of CheckIfFinished
+        for (int rk = 0; rk < 5; rk++) {
+            if (int rc = stage_prepare(h, rk)) return rc;
+            if (int rc = stage_edges(h, rk)) return rc;
+            if (int rc = stage_update(h, rk, nullptr)) return rc;
+        }
+    }
+    int rc = dfr2d_step_finish(h, info);
+    if (info && h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) info->finished = 1;
+    return rc;
+}
+
+extern "C" int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out) {
+    if (!h || !RHS_out || rk < 0 || rk > 4) return 1;
+    if (h->nParts > 1) { h->err = "dfr2d_rhs is a single-partition test hook"; return 1; }
+    CK(cudaSetDevice(h->device));
+    if (!h->rhsScratch) {
+        if (int rc = dev_alloc(h, &h->rhsScratch, (size_t)4 * h->NpInt * h->Kp)) return rc;
+    }
+    h->qfaceValid = false;
+    if (int rc = stage_prepare(h, rk)) return rc;
+    if (int rc = stage_edges(h, rk)) return rc;
+    if (int rc = stage_update(h, rk, h->rhsScratch)) return rc;
+    h->qfaceValid = false;
+    return copy_out(h, h->rhsScratch, RHS_out);
+}
+
+extern "C" int dfr2d_residual(dfr2d_handle *h, double maxR[4]) {
+    if (!h || !maxR) return 1;
+    CK(cudaSetDevice(h->device));
+    double *tmp = nullptr;
+    CK(cudaMalloc(&tmp, 4 * sizeof(double)));
+    k_signed_max<<<4, 1024, 0, h->stream>>>(h->R, h->NpInt, h->K, h->Kp, tmp);
+    int rc = launch_check(h, "k_signed_max");
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(maxR, tmp, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
+    }
+    cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int dfr2d_get_field(dfr2d_handle *h, int which, double *out) {
+    if (!h || !out) return 1;
+    CK(cudaSetDevice(h->device));
+    const double *src = nullptr;
+    switch (which) {
+        case DFR2D_FIELD_DT: src = h->DT; break;
+        case DFR2D_FIELD_SigmaScalar: src = h->ds.sigma; break;
+        case DFR2D_FIELD_EpsilonScalar: src = h->ds.epsk; break;
+        case DFR2D_FIELD_Se: src = h->ds.se; break;
+        default: break;
+    }
+    if (!src) { h->err = "field not available for this configuration"; return 1; }
+    CK(cudaMemcpyAsync(out + h->k0, src, (size_t)h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dfr2d_set_stream(dfr2d_handle *h, void *s) {
+    if (!h) return 1;
+    h->stream = (cudaStream_t)s;
+    if (g_ops_owner == h) g_ops_owner = nullptr;     // re-upload on the new stream's order
+    return 0;
+}
+extern "C" int dfr2d_partition_range(const dfr2d_handle *h, int64_t *b, int64_t *e) {
+    if (!h) return 1;
+    if (b) *b = h->k0;
+    if (e) *e = h->k1;
+    return 0;
+}
+extern "C" int dfr2d_halo_counts(const dfr2d_handle *h, int64_t *s, int64_t *r) {
+    if (!h) return 1;
+    for (int i = 0; i < h->nParts; i++) {
+        if (s) s[i] = h->sendCounts[i];
+        if (r) r[i] = h->recvCounts[i];
+    }
+    return 0;
+}
+extern "C" int dfr2d_halo_buffers(dfr2d_handle *h, void **s, void **r) {
+    if (!h) return 1;
+    if (s) *s = h->sendBuf;
+    if (r) *r = h->recvBuf;
+    return 0;
+}
+extern "C" int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **p) {
+    if (!h || !p) return 1;
+    *p = (void *)&h->sc->wave[h->stageCounter & 1][0];
+    return 0;
+}
+extern "C" int64_t dfr2d_launch_count(const dfr2d_handle *h) { return h ? h->launches : 0; }

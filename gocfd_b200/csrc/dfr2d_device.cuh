@@ -1,0 +1,298 @@
+// Device-side building blocks of the 2D Euler DFR stage: gas functions, numerical fluxes,
+// boundary states.  Each function restates the arithmetic of the reference function it names
+// (same operation order; the compiler may still contract a*b+c into an FMA, which moves results
+// by <= 1 ulp per operation -- far inside the 1e-11 relative-L2 parity bar).
+//
+// Reference files are under model_problems/Euler2D/ unless noted.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dfr2d.h"
+
+namespace dfr2d {
+
+template <int N> struct Dim {
+    static constexpr int NpInt = (N + 1) * (N + 2) / 2;
+    static constexpr int NpEdge = N + 2;
+    static constexpr int NpFlux = (N + 2) * (N + 4);
+    static constexpr int NF3 = 3 * NpEdge;
+};
+
+// Reference-element operators of one polynomial order, resident in constant memory so that the
+// fully unrolled contractions use them as immediate c[bank][offset] operands of DFMA.
+template <int N> struct Ops {
+    double FEI[Dim<N>::NF3][Dim<N>::NpInt];          // FluxEdgeInterp
+    double DivInt[Dim<N>::NpInt][Dim<N>::NpFlux];
+    double V[Dim<N>::NpInt][Dim<N>::NpInt];
+    double Vinv[Dim<N>::NpInt][Dim<N>::NpInt];
+    double M[Dim<N>::NpInt][Dim<N>::NpInt];
+    double D[Dim<N>::NpInt][Dim<N>::NpInt];
+    double P[Dim<N>::NpInt][Dim<N>::NpInt];
+    double mf[Dim<N>::NpInt];
+    double Bary[Dim<N>::NpFlux][3];
+    double Div[Dim<N>::NpFlux][Dim<N>::NpFlux];
+};
+
+constexpr int kOpsDoubles = sizeof(Ops<DFR2D_MAX_ORDER>) / sizeof(double);
+__constant__ double c_ops_raw[kOpsDoubles];
+
+template <int N> __device__ __forceinline__ const Ops<N> &ops() {
+    return *reinterpret_cast<const Ops<N> *>(c_ops_raw);
+}
+
+struct Phys {
+    double gamma, CFL, FinalTime;
+    dfr2d_freestream fs[3];   // far, in, out
+    dfr2d_vortex vortex;
+    double sdKappa, Eps0, S0, Cdiff, Omega;
+    int fluxType, localDT, dissipation, N, maxIter;
+};
+
+// Device-resident scalars of the time loop; nothing here is read by the host inside a step.
+struct DevScalars {
+    unsigned long long wave[2][2];   // [slot][0 = max wave speed, 1 = max viscous wave speed], double bits
+    double time[2];                  // rk.Time by step parity
+    double globalDT;                 // rk.GlobalDT of the last stage
+    double timeOut;                  // rk.Time after the last finished step
+    long long steps;                 // rk.StepCount
+    int finished;
+    int nanFlag;
+};
+
+// ---- fluids.go:289-336 GetFlowFunctionBase ---------------------------------------------------
+__device__ __forceinline__ double static_pressure(double gamma, double rho, double rhoU, double rhoV, double E) {
+    double oorho = 1.0 / rho;
+    double u = rhoU * oorho, v = rhoV * oorho;
+    double U2 = u * u + v * v;
+    double q = 0.5 * rho * U2;
+    return (gamma - 1.0) * (E - q);
+}
+
+// (|u| + c) of a conserved state: Velocity + SoundSpeed, both as GetFlowFunctionBase computes them
+__device__ __forceinline__ double speed_plus_sound(double gamma, double rho, double rhoU, double rhoV, double E) {
+    double oorho = 1.0 / rho;
+    double u = rhoU * oorho, v = rhoV * oorho;
+    double U2 = u * u + v * v;
+    double q = 0.5 * rho * U2;
+    double p = (gamma - 1.0) * (E - q);
+    double C = sqrt(fabs(gamma * p * oorho));
+    return sqrt(U2) + C;
+}
+
+// ---- fluxes.go:76-87 FluxCalcBase --------------------------------------------------------------
+__device__ __forceinline__ void flux_calc(double gamma, const double Q[4], double Fx[4], double Fy[4]) {
+    double rho = Q[0], rhoU = Q[1], rhoV = Q[2], E = Q[3];
+    double oorho = 1.0 / rho;
+    double u = rhoU * oorho;
+    double v = rhoV * oorho;
+    double p = static_pressure(gamma, rho, rhoU, rhoV, E);
+    Fx[0] = rhoU; Fx[1] = rhoU * u + p; Fx[2] = rhoU * v; Fx[3] = u * (E + p);
+    Fy[0] = rhoV; Fy[1] = rhoV * u; Fy[2] = rhoV * v + p; Fy[3] = v * (E + p);
+}
+
+// ---- fluxes.go:284-413 RoeFlux -----------------------------------------------------------------
+__device__ __forceinline__ void roe_flux(double gamma, const double QL[4], const double QR[4], double nx, double ny,
+                                         double F[4]) {
+    const double GM1 = gamma - 1.0;
+    double rhoULr = QL[1] * nx + QL[2] * ny;
+    double rhoVLr = QL[1] * (-ny) + QL[2] * nx;
+    double rhoURr = QR[1] * nx + QR[2] * ny;
+    double rhoVRr = QR[1] * (-ny) + QR[2] * nx;
+    double rhoL = QL[0], uL = rhoULr / QL[0], vL = rhoVLr / QL[0];
+    double rhoR = QR[0], uR = rhoURr / QR[0], vR = rhoVRr / QR[0];
+    double pL = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
+    double pR = static_pressure(gamma, QR[0], QR[1], QR[2], QR[3]);
+    double hL = (QL[3] + pL) / rhoL, hR = (QR[3] + pR) / rhoR;
+    double rhoLs = sqrt(rhoL), rhoRs = sqrt(rhoR);
+    double rhoLsRs = rhoLs + rhoRs;
+    double rho = rhoLs * rhoRs;
+    double u = (rhoLs * uL + rhoRs * uR) / rhoLsRs;
+    double v = (rhoLs * vL + rhoRs * vR) / rhoLsRs;
+    double h = (rhoLs * hL + rhoRs * hR) / rhoLsRs;
+    double c2 = GM1 * (h - 0.5 * (u * u + v * v));
+    double C = sqrt(c2);
+    double dW1 = -0.5 * (rho * (uR - uL)) / C + 0.5 * (pR - pL) / c2;
+    double dW2 = (rhoR - rhoL) - (pR - pL) / c2;
+    double dW3 = rho * (vR - vL);
+    double dW4 = 0.5 * (rho * (uR - uL)) / C + 0.5 * (pR - pL) / c2;
+    dW1 = fabs(u - C) * dW1;
+    dW2 = fabs(u) * dW2;
+    dW3 = fabs(u) * dW3;
+    dW4 = fabs(u + C) * dW4;
+    double f0 = 0.5 * (rhoULr + rhoURr);
+    double f1 = 0.5 * (rhoULr * uL + rhoURr * uR + pL + pR);
+    double f2 = 0.5 * (rhoVLr * uL + rhoVRr * uR);
+    double f3 = 0.5 * ((pL + QL[3]) * uL + (pR + QR[3]) * uR);
+    f0 -= 0.5 * (dW1 + dW2 + dW4);
+    f1 -= 0.5 * (dW1 * (u - C) + dW2 * u + dW4 * (u + C));
+    f2 -= 0.5 * (dW1 * v + dW2 * v + dW3 + dW4 * v);
+    f3 -= 0.5 * (dW1 * (h - u * C) + 0.5 * dW2 * (u * u + v * v) + dW3 * v + dW4 * (h + u * C));
+    F[0] = f0;
+    F[1] = nx * f1 - ny * f2;     // rotate back to Cartesian
+    F[2] = ny * f1 + nx * f2;
+    F[3] = f3;
+}
+
+// ---- fluxes.go:161-190 LaxFlux -----------------------------------------------------------------
+__device__ __forceinline__ void lax_flux(double gamma, const double QL[4], const double QR[4], double nx, double ny,
+                                         double F[4]) {
+    double rhoL = QL[0], rhoR = QR[0];
+    double rhoUL = QL[1], rhoVL = QL[2], rhoUR = QR[1], rhoVR = QR[2];
+    double EL = QL[3], ER = QR[3];
+    double uL = rhoUL / rhoL, vL = rhoVL / rhoL;
+    double uR = rhoUR / rhoR, vR = rhoVR / rhoR;
+    double pL = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
+    double pR = static_pressure(gamma, QR[0], QR[1], QR[2], QR[3]);
+    double CL = sqrt(fabs(gamma * pL * (1.0 / rhoL)));
+    double CR = sqrt(fabs(gamma * pR * (1.0 / rhoR)));
+    double maxV = fmax(sqrt(uL * uL + vL * vL) + CL, sqrt(uR * uR + vR * vR) + CR);
+    F[0] = 0.5 * (nx * (rhoUL + rhoUR) + ny * (rhoVL + rhoVR));
+    F[1] = 0.5 * (nx * (rhoUL * uL + rhoUR * uR + pL + pR) + ny * (rhoUL * vL + rhoUR * vR));
+    F[2] = 0.5 * (nx * (rhoVL * uL + rhoVR * uR) + ny * (rhoVL * vL + rhoVR * vR + pL + pR));
+    F[3] = 0.5 * (nx * ((pL + EL) * uL + (pR + ER) * uR) + ny * ((pL + EL) * vL + (pR + ER) * vR));
+#pragma unroll
+    for (int n = 0; n < 4; n++) F[n] += 0.5 * maxV * (QL[n] - QR[n]);
+}
+
+// ---- fluxes.go:135-159 AvgFlux -----------------------------------------------------------------
+__device__ __forceinline__ void avg_flux(double gamma, const double QL[4], const double QR[4], double nx, double ny,
+                                         double F[4]) {
+    double FxL[4], FyL[4], FxR[4], FyR[4];
+    flux_calc(gamma, QL, FxL, FyL);
+    flux_calc(gamma, QR, FxR, FyR);
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        double fx = 0.5 * (FxL[n] + FxR[n]);
+        double fy = 0.5 * (FyL[n] + FyR[n]);
+        F[n] = nx * fx + ny * fy;
+    }
+}
+
+// ---- fluxes.go:415-503 RoeERFlux (as written, including (dPu+dPp)*ny in the energy row) -----------
+__device__ __forceinline__ void roe_er_flux(double gamma, const double QL[4], const double QR[4], double nx, double ny,
+                                            double F[4]) {
+    const double GM1 = gamma - 1.0;
+    double rhoL = QL[0], rhoR = QR[0];
+    double ooRhoL = 1.0 / rhoL, ooRhoR = 1.0 / rhoR;
+    double rhoLs = sqrt(rhoL), rhoRs = sqrt(rhoR);
+    double uL = QL[1] * ooRhoL, vL = QL[2] * ooRhoL;
+    double uR = QR[1] * ooRhoR, vR = QR[2] * ooRhoR;
+    double EL = QL[3], ER = QR[3];
+    double UL = nx * uL + ny * vL, UR = nx * uR + ny * vR;
+    double pL = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
+    double pR = static_pressure(gamma, QR[0], QR[1], QR[2], QR[3]);
+    double HL = EL + pL, HR = ER + pR;
+    double ooRs = 1.0 / (rhoLs + rhoRs);
+    double u = (rhoLs * uL + rhoRs * uR) * ooRs, v = (rhoLs * vL + rhoRs * vR) * ooRs, h = (HL + HR) * ooRs;
+    double rho = rhoLs * rhoRs;
+    double H = h * rho;
+    double U = nx * u + ny * v;
+    double C2 = GM1 * (h - 0.5 * (u * u + v * v));
+    double C = sqrt(C2);
+    double ooC = 1.0 / C;
+    double Uabs = fabs(U);
+    F[0] = 0.5 * (UL * rhoL + UR * rhoR);
+    F[1] = 0.5 * (UL * rhoL * uL + pL * nx + UR * rhoR * uR + pR * nx);
+    F[2] = 0.5 * (UL * rhoL * vL + pL * ny + UR * rhoR * vR + pR * ny);
+    F[3] = 0.5 * (UL * HL + UR * HR);
+    double Uef = 0.05 * C;
+    double du = (uR - uL), dv = (vR - vL);
+    double deltaV2 = du * du + dv * dv;
+    double ooVmag = 1.0 / sqrt(u * u + v * v);
+    double n1x, n1y;
+    if (deltaV2 < 0.01 * C2) { n1x = nx; n1y = ny; } else { n1x = ooVmag * du; n1y = ooVmag * dv; }
+    double n2x = n1y * (nx * n1y - n1x * ny), n2y = -n1x * (nx * n1y - n1x * ny);
+    double alp1 = nx * n1x + ny * n1y, alp2 = nx * n2x + ny * n2y;
+    double U1x = n1x * u, U1y = n1y * v;
+    double U2x = n2x * u, U2y = n2y * v;
+    double Urot = sqrt(alp1 * alp1 * (U1x * U1x + U1y * U1y)) + sqrt(alp2 * alp2 * (U2x * U2x + U2y * U2y));
+    double sigma = fmax(Uabs, fmin(Uef, Urot));
+    // math.Copysign(x, 1) == |x|
+    double UabsPrime = Uabs - 0.25 * fmax(0.0, UR - UL) * (fabs(U + C) - fabs(U - C));
+    double dU = UR - UL, dP = pR - pL, dRho = rhoR - rhoL;
+    double dRhoU = rhoR * uR - rhoL * uL, dRhoV = rhoR * vR - rhoL * vL, dE = ER - EL;
+    double dPu = rho * dU * fmax(0.0, C - UabsPrime);
+    double swt = fabs(U) * fmin(UabsPrime, C);
+    double dPp = swt * dP * ooC;
+    double dUu = swt * dU * ooC;
+    F[0] -= 0.5 * (sigma * dRho + (dPu + dPp) * 0 + dUu * rho);
+    F[1] -= 0.5 * (sigma * dRhoU + (dPu + dPp) * nx + dUu * rho * u);
+    F[2] -= 0.5 * (sigma * dRhoV + (dPu + dPp) * ny + dUu * rho * v);
+    F[3] -= 0.5 * (sigma * dE + (dPu + dPp) * ny + dUu * H);
+}
+
+// ---- bcs.go:70-133 RiemannBC -------------------------------------------------------------------
+__device__ __forceinline__ void riemann_bc(const dfr2d_freestream &FS, const double QQ[4], const double QInf[4], double nx,
+                                           double ny, double Q[4]) {
+    double rhoInt = QQ[0], uInt = QQ[1] / QQ[0], vInt = QQ[2] / QQ[0];
+    double Gamma = FS.Gamma;
+    double pInt = static_pressure(Gamma, QQ[0], QQ[1], QQ[2], QQ[3]);
+    double CInt = sqrt(fabs(Gamma * pInt * (1.0 / QQ[0])));
+    double pInf = FS.Pinf, CInf = FS.Cinf;
+    double GM1 = Gamma - 1.0;
+    double OOGM1 = 1.0 / GM1;
+    double rhoInf = QInf[0], uInf = QInf[1] / QInf[0], vInf = QInf[2] / QInf[0];
+    double tx = -ny, ty = nx;
+    double VnormInt = nx * uInt + ny * vInt;
+    if (FS.Minf <= 1.0) {
+        double VnormInf = nx * uInf + ny * vInf;
+        double Rinf = VnormInf - 2.0 * CInf * OOGM1;
+        double Rint = VnormInt + 2.0 * CInt * OOGM1;
+        double Vnorm = 0.5 * (Rint + Rinf);
+        double C = 0.25 * GM1 * (Rint - Rinf);
+        double Vtang = 0.0, Beta = 0.0;
+        if (VnormInt < 0) {                 // inflow: entropy and tangent velocity from Qinf
+            Vtang = tx * uInf + ty * vInf;
+            Beta = pInf / pow(rhoInf, Gamma);
+        } else if (VnormInt >= 0) {         // outflow: from the interior
+            Vtang = tx * uInt + ty * vInt;
+            Beta = pInt / pow(rhoInt, Gamma);
+        }
+        double u = Vnorm * nx + Vtang * tx;
+        double v = Vnorm * ny + Vtang * ty;
+        double rho = pow(C * C / (Gamma * Beta), OOGM1);
+        double p = Beta * pow(rho, Gamma);
+        Q[0] = rho;
+        Q[1] = rho * u;
+        Q[2] = rho * v;
+        Q[3] = p * OOGM1 + 0.5 * rho * (u * u + v * v);
+    } else {                                // supersonic far field
+        if (VnormInt < 0) { Q[0] = QInf[0]; Q[1] = QInf[1]; Q[2] = QInf[2]; Q[3] = QInf[3]; }
+        else { Q[0] = QQ[0]; Q[1] = QQ[1]; Q[2] = QQ[2]; Q[3] = QQ[3]; }
+    }
+}
+
+// ---- isentropic_vortex/analytic_vortex.go:31-82 GetStateC --------------------------------------
+__device__ __forceinline__ void ivortex_state(const dfr2d_vortex &iv, double t, double x, double y, double Q[4]) {
+    const double pi = 3.14159265358979323846;
+    double oo2pi = 0.5 * (1.0 / pi);
+    double Gamma = iv.Gamma, GM1 = Gamma - 1.0, OOGM1 = 1.0 / GM1;
+    double pi2 = pi * pi;
+    double beta = iv.Beta, beta2 = beta * beta;
+    double fac = 16 * Gamma * pi2;
+    double u = iv.Ufs, v = 0.0;
+    double xmut = x - u * t, ymvt = y - v * t;
+    double r2 = (xmut - iv.X0) * (xmut - iv.X0) + (ymvt - iv.Y0) * (ymvt - iv.Y0);
+    double ex1r = exp(1 - r2);
+    double tv1 = 1.0 - (GM1 * beta2 * exp(2.0 * (1.0 - r2)) / fac);
+    u -= beta * ex1r * (ymvt - iv.Y0) * oo2pi;
+    v += beta * ex1r * (xmut - iv.X0) * oo2pi;
+    double rho = pow(tv1, OOGM1);
+    double p = pow(rho, Gamma);
+    double ooGM1 = 1.0 / (iv.Gamma - 1.0);
+    double q = 0.5 * rho * (u * u + v * v);
+    Q[0] = rho; Q[1] = rho * u; Q[2] = rho * v; Q[3] = p * ooGM1 + q;
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(unsigned long long *addr, double v) {
+    // for doubles >= 0 the IEEE bit pattern is monotone in the value
+    atomicMax(addr, (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace dfr2d

@@ -1,0 +1,383 @@
+// Kernels of the inviscid stage.  Two launches per RK stage:
+//   k_edge : numerical normal flux on every edge (+BCs) and wave-speed maxima      (edges.go:246-452)
+//   k_elem : interior flux -> RT DOFs -> DivInt contraction -> dt -> SSP-RK update,
+//            fused with the NEXT stage's solution-to-edge interpolation            (euler.go:460-566,
+//            :665-726; edges.go:454-491)
+// Layout: every element-indexed array is [row][Kp] with the element index fastest (the
+// reference's own utils.Matrix layout), Kp = padded (own + ghost) element count.  Edge arrays are
+// [var][point][NEp], edge index fastest.
+#pragma once
+#include "dfr2d_device.cuh"
+
+namespace dfr2d {
+
+constexpr int kElemsPerBlock = 32;              // E: elements per CTA of k_elem / k_interp
+constexpr int kElemThreads = 4 * kElemsPerBlock; // one thread per (element, conserved variable)
+
+struct EdgeArgs {
+    int ne, NEp, Kp;
+    const int *kL, *kR, *meta;          // kR < 0: boundary edge, boundary-point slot = -1 - kR
+    const double *nx, *ny, *oohk;
+    const double *bpx, *bpy;            // [NBPloc][NpEdge]
+    const double *qface;                // [4][3NpEdge][Kp]
+    double *eflux;                      // [4][NpEdge][NEp]
+    double *agg;                        // [NEp] edge max wave speed
+    DevScalars *sc;
+    int slot, par;
+    long long stepIndex;
+    Phys ph;
+};
+
+// The reference's loop is `for !finished { Step; Time += GlobalDT; steps++; finished = Time >= FinalTime ||
+// steps >= MaxIterations }` (euler.go:175-182): step 0 always runs, step t >= 1 runs iff the time at its start is
+// below FinalTime and t < MaxIterations.  time[par] is stable for the whole step, so every thread of every launch of
+// a step evaluates the same predicate without any host round trip.
+__device__ __forceinline__ bool step_is_noop(const DevScalars *sc, const Phys &ph, int par, long long stepIndex) {
+    return stepIndex >= 1 && (sc->time[par] >= ph.FinalTime || stepIndex >= (long long)ph.maxIter);
+}
+
+// SSP54 coefficients (euler.go:511-563)
+#define RK0_A 0.391752226571890
+#define RK1_A 0.444370493651235
+#define RK1_B 0.555629506348765
+#define RK1_C 0.368410593050371
+#define RK2_A 0.620101851488403
+#define RK2_B 0.379898148511597
+#define RK2_C 0.251891774271694
+#define RK3_A 0.178079954393132
+#define RK3_B 0.821920045606868
+#define RK3_C 0.544974750228521
+#define RK4_A 0.517231671970585
+#define RK4_B 0.096059710526146
+#define RK4_C 0.386708617503269
+#define RK4_D 0.063692468666290
+#define RK4_E 0.226007483236906
+
+// ------------------------------------------------------------------------------------------------
+// Edge kernel: one thread per edge, grid-stride.  CalculateEdgeEulerFlux + StoreEdgeAggregates.
+// The BC routines overwrite Q_Face in place in the reference; the only later reader of the
+// overwritten rows is StoreEdgeAggregates, so the post-BC state stays in registers here.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(256) k_edge(EdgeArgs a) {
+    constexpr int NE_ = Dim<N>::NpEdge;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    const double gamma = a.ph.gamma;
+    const size_t qplane = (size_t)Dim<N>::NF3 * a.Kp;
+    const size_t fplane = (size_t)NE_ * a.NEp;
+    double blockmax = 0.0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.ne; e += gridDim.x * blockDim.x) {
+        const int kL = a.kL[e], kR = a.kR[e], meta = a.meta[e];
+        const int numL = meta & 3, numR = (meta >> 2) & 3, bc = (meta >> 4) & 15;
+        const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
+        double wmax = -1.7976931348623157e308;
+#pragma unroll
+        for (int i = 0; i < NE_; i++) {
+            double QL[4], F[4];
+            const size_t offL = (size_t)(numL * NE_ + i) * a.Kp + kL;
+#pragma unroll
+            for (int n = 0; n < 4; n++) QL[n] = a.qface[n * qplane + offL];
+            if (kR >= 0) {
+                double QR[4];
+                const size_t offR = (size_t)(numR * NE_ + (NE_ - 1 - i)) * a.Kp + kR;
+#pragma unroll
+                for (int n = 0; n < 4; n++) QR[n] = a.qface[n * qplane + offR];
+                switch (a.ph.fluxType) {
+                    case DFR2D_FLUX_Average: avg_flux(gamma, QL, QR, nx, ny, F); break;
+                    case DFR2D_FLUX_LaxFriedrichs: lax_flux(gamma, QL, QR, nx, ny, F); break;
+                    case DFR2D_FLUX_Roe: roe_flux(gamma, QL, QR, nx, ny, F); break;
+                    default: roe_er_flux(gamma, QL, QR, nx, ny, F); break;
+                }
+            } else {
+                // calculateNonSharedEdgeFlux (edges.go:413-452)
+                bool normalFlux = true;
+                if (bc == DFR2D_BC_Far || bc == DFR2D_BC_In || bc == DFR2D_BC_Out) {
+                    const dfr2d_freestream &FS = a.ph.fs[bc == DFR2D_BC_Far ? 0 : (bc == DFR2D_BC_In ? 1 : 2)];
+                    double QB[4];
+                    riemann_bc(FS, QL, FS.Qinf, nx, ny, QB);
+#pragma unroll
+                    for (int n = 0; n < 4; n++) QL[n] = QB[n];
+                } else if (bc == DFR2D_BC_IVortex) {
+                    const int b = -1 - kR;
+                    double QX[4], QB[4];
+                    ivortex_state(a.ph.vortex, a.sc->time[a.par], a.bpx[(size_t)b * NE_ + i], a.bpy[(size_t)b * NE_ + i], QX);
+                    riemann_bc(a.ph.fs[0], QL, QX, nx, ny, QB);
+#pragma unroll
+                    for (int n = 0; n < 4; n++) QL[n] = QB[n];
+                } else if (bc == DFR2D_BC_Wall || bc == DFR2D_BC_Cyl) {
+                    normalFlux = false;
+                    double p = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
+                    F[0] = 0; F[1] = nx * p; F[2] = ny * p; F[3] = 0;
+                } else if (bc == DFR2D_BC_Periodic || bc == DFR2D_BC_PeriodicReversed) {
+                    normalFlux = false;
+                    F[0] = F[1] = F[2] = F[3] = 0;
+                }
+                if (normalFlux) {
+                    double Fx[4], Fy[4];
+                    flux_calc(gamma, QL, Fx, Fy);
+#pragma unroll
+                    for (int n = 0; n < 4; n++) F[n] = nx * Fx[n] + ny * Fy[n];
+                }
+            }
+#pragma unroll
+            for (int n = 0; n < 4; n++) a.eflux[n * fplane + (size_t)i * a.NEp + e] = F[n];
+            // StoreEdgeAggregates: owner side, post-BC state (edges.go:260-273)
+            double w = oohk * speed_plus_sound(gamma, QL[0], QL[1], QL[2], QL[3]);
+            if (w > wmax) wmax = w;
+        }
+        a.agg[e] = wmax;
+        blockmax = fmax(blockmax, wmax);
+    }
+    __shared__ double smax[8];
+    blockmax = warp_max(blockmax);
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
+        v = warp_max(v);
+        if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][0], v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q_Face[n][m][k] = sum_i FluxEdgeInterp[m][i] * q[i]   (edges.go:485-491), thread = (element, n)
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void interp_store(const double (&q)[Dim<N>::NpInt], double *qface_n, int Kp, int k) {
+    const Ops<N> &op = ops<N>();
+#pragma unroll
+    for (int m = 0; m < Dim<N>::NF3; m++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < Dim<N>::NpInt; i++) s = fma(op.FEI[m][i], q[i], s);
+        qface_n[(size_t)m * Kp + k] = s;
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kElemThreads) k_interp(int K, int Kp, const double *q, double *qface) {
+    const int e = threadIdx.x % kElemsPerBlock, n = threadIdx.x / kElemsPerBlock;
+    const int k = blockIdx.x * kElemsPerBlock + e;
+    if (k >= K) return;
+    double qs[Dim<N>::NpInt];
+#pragma unroll
+    for (int i = 0; i < Dim<N>::NpInt; i++) qs[i] = q[((size_t)n * Dim<N>::NpInt + i) * Kp + k];
+    interp_store<N>(qs, qface + (size_t)n * Dim<N>::NF3 * Kp, Kp, k);
+}
+
+struct ElemArgs {
+    int K, Kp, NEp;
+    const double *qs;                       // stage input register [4][NpInt][Kp]
+    double *q0, *q1, *q2, *q3, *q4, *R;     // c.Q, Q1..Q4, Residual
+    double *qface;                          // [4][3NpEdge][Kp], written for the next stage when non-null
+    const double *eflux;                    // [4][NpEdge][NEp] numerical normal flux
+    const double *vflux;                    // [4][NpEdge][NEp] viscous normal flux (dissipation)
+    const double *agg, *aggv;               // [NEp]
+    double *DT, *DTVisc;                    // [Kp] (local time stepping)
+    const double *Jdet, *Jinv, *IInII;      // [Kp], [4][Kp], [3][Kp]
+    const int *etoe;                        // [3][Kp]: edge slot, or -1 - slot when the neighbour owns it
+    const double *dissX, *dissY;            // [4][NpFlux][Kp] (dissipation)
+    const double *sigma;                    // [Kp] vertex-averaged sigma (dissipation)
+    double *rhsOut;                         // test hook: RHSQ only, no update
+    DevScalars *sc;
+    int rk, slot, par;
+    long long stepIndex;
+    Phys ph;
+};
+
+// Element kernel.  CTA = 32 elements x 4 conserved variables.
+//   phase 1  thread (e,n) loads its solution row into registers and shared memory, and gathers
+//            the numerical flux of its three edges (sign / reversal / IInII applied)
+//   phase 2  per-point physical flux -> (Fr, Fs) RT DOFs into shared memory (euler.go:701-726)
+//   phase 3  DivInt contraction from shared memory with the operator as constant-bank operands,
+//            -1/Jdet, dt, SSP-RK update, NaN flag, next stage's edge interpolation
+template <int N, bool DISS>
+__global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
+    constexpr int E = kElemsPerBlock;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) {
+        if (a.rk == 4 && a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.sc->time[a.par ^ 1] = a.sc->time[a.par];     // keep both parities at the final time
+            a.sc->finished = 1;
+        }
+        return;
+    }
+    extern __shared__ double smem[];
+    double *sQ = smem;                    // [4][NI][E]
+    double *sF = smem + 4 * NI * E;       // [4][2NI][E]
+    const Ops<N> &op = ops<N>();
+    const int e = threadIdx.x % E, n = threadIdx.x / E;
+    const int k = blockIdx.x * E + e;
+    const bool valid = k < a.K;
+    const int kc = valid ? k : a.K - 1;   // clamp: out-of-range lanes compute on a valid element, store nothing
+    const size_t Kp = a.Kp;
+
+    double qs[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        qs[i] = a.qs[((size_t)n * NI + i) * Kp + kc];
+        sQ[(n * NI + i) * E + e] = qs[i];
+    }
+    const double jdet = a.Jdet[kc];
+    // edge rows of F_RT_DOF for variable n (SetRTFluxOnEdges, edges.go:454-483)
+    double fe[NF3];
+    double dtk = 0.0, dtv = 0.0;
+    {
+        double wmaxk = -1.7976931348623157e308, vmaxk = -1.7976931348623157e308;
+#pragma unroll
+        for (int le = 0; le < 3; le++) {
+            const int s = a.etoe[(size_t)le * Kp + kc];
+            const bool owner = s >= 0;
+            const int slot = owner ? s : -1 - s;
+            const double iin = a.IInII[(size_t)le * Kp + kc];
+            const double *f = a.eflux + ((size_t)n * NEd) * a.NEp + slot;
+#pragma unroll
+            for (int i = 0; i < NEd; i++) {
+                const double v = f[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
+                fe[le * NEd + i] = owner ? v * iin : -v * iin;
+            }
+            if (a.ph.localDT) {
+                wmaxk = fmax(wmaxk, a.agg[slot]);
+                if (DISS) vmaxk = fmax(vmaxk, a.aggv[slot]);
+            }
+        }
+        if (a.ph.localDT) {
+            // InitializeDT at stage 0, then DT = max(DT, edge aggregates) (euler.go:637-643, edges.go:291-323)
+            double d = (a.rk == 0) ? -100.0 : a.DT[kc];
+            dtk = a.ph.CFL / fmax(d, wmaxk);                       // CalculateLocalDT (euler.go:985-988)
+            if (DISS) {
+                dtv = fmax(a.DTVisc[kc], vmaxk);
+                if (dtv > 1.e-9) { dtv = a.ph.Cdiff / dtv; dtk = fmin(dtk, dtv); }
+            }
+        } else {
+            // calculateGlobalDT (euler.go:945-971); every thread derives the same scalar
+            const double gw = __longlong_as_double((long long)a.sc->wave[a.slot][0]);
+            dtk = a.ph.CFL / gw;
+            if (DISS) {
+                const double gv = __longlong_as_double((long long)a.sc->wave[a.slot][1]);
+                dtk = fmin(dtk, a.ph.Cdiff / gv);
+            }
+            const double t = a.sc->time[a.par];
+            if (t + dtk > a.ph.FinalTime) dtk = a.ph.FinalTime - t;
+        }
+    }
+    __syncthreads();
+
+    // phase 2: SetRTFluxInternal for points j = n, n+4, ...
+    {
+        const double j0 = a.Jinv[0 * Kp + kc], j1 = a.Jinv[1 * Kp + kc], j2 = a.Jinv[2 * Kp + kc], j3 = a.Jinv[3 * Kp + kc];
+#pragma unroll
+        for (int j = n; j < NI; j += 4) {
+            double Q[4], Fx[4], Fy[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) Q[m] = sQ[(m * NI + j) * E + e];
+            flux_calc(a.ph.gamma, Q, Fx, Fy);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                sF[(m * 2 * NI + j) * E + e] = jdet * (j0 * Fx[m] + j1 * Fy[m]);
+                sF[(m * 2 * NI + j + NI) * E + e] = jdet * (j2 * Fx[m] + j3 * Fy[m]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase 3: RHSInternalPoints (euler.go:665-699)
+    double acc[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) acc[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 2 * NI; j++) {
+        const double f = sF[(n * 2 * NI + j) * E + e];
+#pragma unroll
+        for (int i = 0; i < NI; i++) acc[i] = fma(op.DivInt[i][j], f, acc[i]);
+    }
+#pragma unroll
+    for (int j = 0; j < NF3; j++) {
+#pragma unroll
+        for (int i = 0; i < NI; i++) acc[i] = fma(op.DivInt[i][2 * NI + j], fe[j], acc[i]);
+    }
+    const double moojd = -(1.0 / jdet);
+#pragma unroll
+    for (int i = 0; i < NI; i++) acc[i] *= moojd;
+
+    if (a.rhsOut != nullptr) {
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < NI; i++) a.rhsOut[((size_t)n * NI + i) * Kp + k] = acc[i];
+        }
+        return;
+    }
+
+    // SSP-RK(5,4) combination (euler.go:502-565); qs is the stage input register
+    const size_t base = (size_t)n * NI * Kp + kc;
+    double qn[NI];
+    bool bad = false;
+    double *dst;
+    switch (a.rk) {
+        case 0:
+            dst = a.q1;
+#pragma unroll
+            for (int i = 0; i < NI; i++) qn[i] = qs[i] + RK0_A * (dtk * acc[i]);
+            break;
+        case 1:
+            dst = a.q2;
+#pragma unroll
+            for (int i = 0; i < NI; i++)
+                qn[i] = RK1_A * a.q0[base + i * Kp] + RK1_B * qs[i] + RK1_C * (dtk * acc[i]);
+            break;
+        case 2:
+            dst = a.q3;
+#pragma unroll
+            for (int i = 0; i < NI; i++)
+                qn[i] = RK2_A * a.q0[base + i * Kp] + RK2_B * qs[i] + RK2_C * (dtk * acc[i]);
+            break;
+        case 3:
+            dst = a.q4;
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                qn[i] = RK3_A * a.q0[base + i * Kp] + RK3_B * qs[i] + RK3_C * (dtk * acc[i]);
+                if (valid) a.R[base + i * Kp] = acc[i];      // keep RHS(q3) for the last stage
+            }
+            break;
+        default:
+            dst = a.q0;
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const double q0 = a.q0[base + i * Kp];
+                const double dtR3 = dtk * a.R[base + i * Kp];
+                const double r = -q0 + RK4_A * a.q2[base + i * Kp] + RK4_B * a.q3[base + i * Kp] + RK4_C * qs[i] +
+                                 RK4_D * dtR3 + RK4_E * (dtk * acc[i]);
+                if (valid) a.R[base + i * Kp] = r;
+                qn[i] = q0 + r;
+            }
+            break;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        bad |= (qn[i] != qn[i]);
+        if (valid) dst[base + i * Kp] = qn[i];
+    }
+    if (bad && valid) a.sc->nanFlag = 1;     // utils.IsNanPanic (euler.go:471-486)
+    if (a.ph.localDT && valid && n == 0) {
+        a.DT[k] = dtk;
+        if (DISS) a.DTVisc[k] = dtv;
+    }
+    if (a.qface != nullptr && valid) interp_store<N>(qn, a.qface + (size_t)n * NF3 * Kp, a.Kp, k);
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // controller bookkeeping (euler.go:177-182, :796-801), one thread per launch
+        a.sc->wave[a.slot ^ 1][0] = 0ull;
+        a.sc->wave[a.slot ^ 1][1] = 0ull;
+        if (!a.ph.localDT) a.sc->globalDT = dtk;
+        if (a.rk == 4) {
+            const double tnew = a.sc->time[a.par] + (a.ph.localDT ? a.sc->globalDT : dtk);
+            a.sc->time[a.par ^ 1] = tnew;
+            a.sc->timeOut = tnew;
+            const long long st = a.sc->steps + 1;
+            a.sc->steps = st;
+            if (tnew >= a.ph.FinalTime || st >= (long long)a.ph.maxIter) a.sc->finished = 1;   // CheckIfFinished
+        }
+    }
+}
+
+}  // namespace dfr2d

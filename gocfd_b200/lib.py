@@ -1,0 +1,254 @@
+"""ctypes binding of the C ABI in include/dfr2d.h (the same entry points the cgo shim binds).
+
+There is no fallback: if the CUDA library is missing or a call fails, this raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libdfr2d.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class Freestream(C.Structure):
+    _fields_ = [("Gamma", C.c_double), ("Qinf", C.c_double * 4), ("Pinf", C.c_double), ("QQinf", C.c_double),
+                ("Cinf", C.c_double), ("Alpha", C.c_double), ("Minf", C.c_double)]
+
+
+class Vortex(C.Structure):
+    _fields_ = [("Beta", C.c_double), ("X0", C.c_double), ("Y0", C.c_double), ("Gamma", C.c_double),
+                ("Ufs", C.c_double)]
+
+
+class ProblemStruct(C.Structure):
+    _fields_ = [
+        ("N", C.c_int32), ("flux_type", C.c_int32), ("init_case", C.c_int32), ("local_time_stepping", C.c_int32),
+        ("max_iterations", C.c_int32), ("dissipation", C.c_int32),
+        ("K", C.c_int64), ("NV", C.c_int64), ("NE", C.c_int64), ("NBP", C.c_int64),
+        ("CFL", C.c_double), ("FinalTime", C.c_double), ("Kappa", C.c_double),
+        ("FSFar", Freestream), ("FSIn", Freestream), ("FSOut", Freestream), ("vortex", Vortex),
+        ("FluxEdgeInterp", _dp), ("DivInt", _dp), ("Div", _dp), ("V", _dp), ("Vinv", _dp),
+        ("MassMatrix", _dp), ("D", _dp), ("P", _dp), ("ModeFilter", _dp), ("Bary", _dp),
+        ("Jdet", _dp), ("Jinv", _dp), ("FaceNormX", _dp), ("FaceNormY", _dp), ("IInII", _dp), ("EdgeLenMax", _dp),
+        ("EToV", _ip), ("edge_kL", _ip), ("edge_kR", _ip), ("edge_numL", _ip), ("edge_numR", _ip),
+        ("edge_nconn", _ip), ("edge_bc", _ip), ("edge_len", _dp), ("EtoEdge", _ip),
+        ("bp_edge", _ip), ("bp_x", _dp), ("bp_y", _dp),
+    ]
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("time", C.c_double), ("dt", C.c_double), ("steps", C.c_int64), ("finished", C.c_int32),
+                ("nan_found", C.c_int32)]
+
+
+EXPORTS = [
+    "dfr2d_create", "dfr2d_destroy", "dfr2d_last_error", "dfr2d_set_state", "dfr2d_get_state", "dfr2d_step",
+    "dfr2d_residual", "dfr2d_rhs", "dfr2d_set_register", "dfr2d_get_register", "dfr2d_get_field",
+    "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
+    "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
+    "dfr2d_step_finish", "dfr2d_launch_count",
+]
+
+_lib = None
+
+
+def load():
+    """Load libdfr2d.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("CUDA library %s is missing: build it with __graft_entry__.build(); "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    lib.dfr2d_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.dfr2d_destroy.argtypes = [H]
+    lib.dfr2d_destroy.restype = None
+    lib.dfr2d_last_error.argtypes = [H]
+    lib.dfr2d_last_error.restype = C.c_char_p
+    for name in ("dfr2d_set_state", "dfr2d_get_state"):
+        getattr(lib, name).argtypes = [H, _dp]
+    lib.dfr2d_step.argtypes = [H, C.c_int, C.POINTER(StepInfo)]
+    lib.dfr2d_residual.argtypes = [H, _dp]
+    lib.dfr2d_rhs.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_set_register.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_get_register.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_get_field.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_set_stream.argtypes = [H, C.c_void_p]
+    lib.dfr2d_partition_range.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.dfr2d_halo_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.dfr2d_halo_buffers.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.dfr2d_wavespeed_buffer.argtypes = [H, C.POINTER(C.c_void_p)]
+    for name in ("dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update"):
+        getattr(lib, name).argtypes = [H, C.c_int]
+    lib.dfr2d_step_finish.argtypes = [H, C.POINTER(StepInfo)]
+    lib.dfr2d_launch_count.argtypes = [H]
+    lib.dfr2d_launch_count.restype = C.c_int64
+    _lib = lib
+    return lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _fs(fs):
+    a = fs.as_array()
+    return Freestream(a[0], (C.c_double * 4)(*a[1:5]), a[5], a[6], a[7], a[8], a[9])
+
+
+def problem_struct(p):
+    """Flatten a host-side Problem into the C struct.  Returns (struct, keepalive list)."""
+    keep = []
+
+    def dd(x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        keep.append(x)
+        return _d(x)
+
+    def ii(x):
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        keep.append(x)
+        return _i(x)
+
+    v = p.Vortex.as_array()
+    s = ProblemStruct(
+        N=p.N, flux_type=p.FluxType, init_case=p.Case, local_time_stepping=int(p.LocalTimeStepping),
+        max_iterations=p.MaxIterations, dissipation=int(p.Dissipation),
+        K=p.K, NV=p.NV, NE=p.NE, NBP=p.NBP, CFL=p.CFL, FinalTime=p.FinalTime, Kappa=p.Kappa,
+        FSFar=_fs(p.FSFar), FSIn=_fs(p.FSIn), FSOut=_fs(p.FSOut), vortex=Vortex(*v),
+        FluxEdgeInterp=dd(p.FluxEdgeInterp), DivInt=dd(p.DivInt), Div=dd(p.Div), V=dd(p.V), Vinv=dd(p.Vinv),
+        MassMatrix=dd(p.MassMatrix), D=dd(p.D), P=dd(p.P), ModeFilter=dd(p.ModeFilter), Bary=dd(p.Bary),
+        Jdet=dd(p.Jdet), Jinv=dd(p.Jinv), FaceNormX=dd(p.FaceNormX), FaceNormY=dd(p.FaceNormY),
+        IInII=dd(p.IInII), EdgeLenMax=dd(p.EdgeLenMax),
+        EToV=ii(p.EToV), edge_kL=ii(p.edge_kL), edge_kR=ii(p.edge_kR), edge_numL=ii(p.edge_numL),
+        edge_numR=ii(p.edge_numR), edge_nconn=ii(p.edge_nconn), edge_bc=ii(p.edge_bc),
+        edge_len=dd(p.edge_len), EtoEdge=ii(p.EtoEdge),
+        bp_edge=ii(p.bp_edge), bp_x=dd(p.bp_x), bp_y=dd(p.bp_y),
+    )
+    return s, keep
+
+
+class Dfr2dError(RuntimeError):
+    pass
+
+
+class Dfr2d:
+    """One partition of the device solver.  Same surface as the oracle's OracleSolver."""
+
+    def __init__(self, problem, n_parts=1, part=0, device=0):
+        self.lib = load()
+        self.p = problem
+        self.shape = (4, problem.NpInt, problem.K)
+        s, keep = problem_struct(problem)
+        self.h = C.c_void_p()
+        rc = self.lib.dfr2d_create(C.byref(s), n_parts, part, device, C.byref(self.h))
+        del keep
+        if rc != 0:
+            raise Dfr2dError("dfr2d_create failed (%d): %s" % (rc, self.lib.dfr2d_last_error(None).decode()))
+        self.n_parts, self.part = n_parts, part
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise Dfr2dError("dfr2d call failed (%d): %s" % (rc, self.lib.dfr2d_last_error(self.h).decode()))
+
+    def close(self):
+        if self.h:
+            self.lib.dfr2d_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == self.shape
+        self._ck(self.lib.dfr2d_set_state(self.h, _d(q)))
+
+    def get_state(self, out=None):
+        q = np.zeros(self.shape) if out is None else out
+        self._ck(self.lib.dfr2d_get_state(self.h, _d(q)))
+        return q
+
+    def set_register(self, reg, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        self._ck(self.lib.dfr2d_set_register(self.h, reg, _d(q)))
+
+    def get_register(self, reg):
+        q = np.zeros(self.shape)
+        self._ck(self.lib.dfr2d_get_register(self.h, reg, _d(q)))
+        return q
+
+    def step(self, nsteps=1, sync=True):
+        info = StepInfo()
+        self._ck(self.lib.dfr2d_step(self.h, nsteps, C.byref(info) if sync else None))
+        return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
+
+    def rhs(self, rk=0):
+        out = np.zeros(self.shape)
+        self._ck(self.lib.dfr2d_rhs(self.h, rk, _d(out)))
+        return out
+
+    def residual(self):
+        r = np.zeros(4)
+        self._ck(self.lib.dfr2d_residual(self.h, _d(r)))
+        return list(r)
+
+    def get_field(self, which):
+        out = np.zeros(self.p.K)
+        self._ck(self.lib.dfr2d_get_field(self.h, which, _d(out)))
+        return out
+
+    # ---- multi-partition plumbing -------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._ck(self.lib.dfr2d_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def partition_range(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.dfr2d_partition_range(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def halo_counts(self):
+        s = (C.c_int64 * self.n_parts)()
+        r = (C.c_int64 * self.n_parts)()
+        self._ck(self.lib.dfr2d_halo_counts(self.h, s, r))
+        return list(s), list(r)
+
+    def halo_buffers(self):
+        s, r = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.dfr2d_halo_buffers(self.h, C.byref(s), C.byref(r)))
+        return s.value, r.value
+
+    def wavespeed_buffer(self):
+        p = C.c_void_p()
+        self._ck(self.lib.dfr2d_wavespeed_buffer(self.h, C.byref(p)))
+        return p.value
+
+    def stage_prepare(self, rk):
+        self._ck(self.lib.dfr2d_stage_prepare(self.h, rk))
+
+    def stage_edges(self, rk):
+        self._ck(self.lib.dfr2d_stage_edges(self.h, rk))
+
+    def stage_update(self, rk):
+        self._ck(self.lib.dfr2d_stage_update(self.h, rk))
+
+    def step_finish(self, sync=True):
+        info = StepInfo()
+        self._ck(self.lib.dfr2d_step_finish(self.h, C.byref(info) if sync else None))
+        return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
+
+    def launch_count(self):
+        return int(self.lib.dfr2d_launch_count(self.h))

@@ -1,0 +1,168 @@
+/*
+ * dfr2d.h -- C ABI of the B200 device library for gocfd's 2D Euler DFR right-hand side and
+ * SSP-RK(5,4) time step (float64, sm_100a CUDA, no CPU fallback).
+ *
+ * The Go host (cmd/2D.go -> Euler2D.NewEuler -> Euler.Solve) keeps mesh input, YAML input and
+ * all DG2D operator construction.  It hands the flattened problem to dfr2d_create() once and
+ * then replaces `c.RK.Step(c)` (model_problems/Euler2D/euler.go:177) with dfr2d_step().
+ * Citations below are file:line in the gocfd reference tree.
+ *
+ * Conventions
+ *   - every matrix is row-major; field arrays are [node rows][element columns] exactly like
+ *     utils.Matrix (utils/matrix_extended.go:33-55): index = k + i*K.
+ *   - all pointers in dfr2d_problem are host memory owned by the caller and only read during
+ *     dfr2d_create(); the library copies what it needs (cgo pointer rules are respected).
+ *   - every entry point returns 0 on success, non-zero on failure; dfr2d_last_error() gives the
+ *     message.  The Go shim panics on non-zero, matching the reference's panic-on-error style
+ *     (euler.go:149, utils/system.go:22 "NAN found").
+ *   - a handle is not re-entrant: one caller at a time (the reference's single controller
+ *     goroutine, euler.go:408-418).
+ */
+#ifndef DFR2D_H
+#define DFR2D_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* types/cfd.go:13-26 -- BC flag numbering is part of the ABI */
+enum {
+    DFR2D_BC_None = 0, DFR2D_BC_In = 1, DFR2D_BC_Dirichlet = 2, DFR2D_BC_Slip = 3, DFR2D_BC_Far = 4,
+    DFR2D_BC_Wall = 5, DFR2D_BC_Cyl = 6, DFR2D_BC_Neuman = 7, DFR2D_BC_Out = 8, DFR2D_BC_IVortex = 9,
+    DFR2D_BC_Periodic = 10, DFR2D_BC_PeriodicReversed = 11
+};
+/* fluxes.go:18-23 */
+enum { DFR2D_FLUX_Average = 0, DFR2D_FLUX_LaxFriedrichs = 1, DFR2D_FLUX_Roe = 2, DFR2D_FLUX_RoeER = 3 };
+/* initialization.go:17-23 */
+enum { DFR2D_CASE_Freestream = 0, DFR2D_CASE_IVortex = 1, DFR2D_CASE_ShockTube = 2 };
+/* dfr2d_get_field selectors */
+enum { DFR2D_FIELD_DT = 0, DFR2D_FIELD_SigmaScalar = 1, DFR2D_FIELD_EpsilonScalar = 2, DFR2D_FIELD_Se = 3 };
+
+#define DFR2D_MAX_ORDER 4
+#define DFR2D_ERR_NAN 7
+
+/* fluids.go:237-243 FreeStream */
+typedef struct dfr2d_freestream {
+    double Gamma;
+    double Qinf[4];
+    double Pinf, QQinf, Cinf;
+    double Alpha, Minf;
+} dfr2d_freestream;
+
+/* isentropic_vortex/analytic_vortex.go:9-12 */
+typedef struct dfr2d_vortex {
+    double Beta, X0, Y0, Gamma, Ufs;
+} dfr2d_vortex;
+
+/*
+ * Everything NewEuler + NewRungeKuttaSSP leave in place for the time loop (euler.go:98-117,
+ * :343-406), flattened.  Np* follow from N: NpInt=(N+1)(N+2)/2, NpEdge=N+2,
+ * NpFlux=(N+2)(N+4) (raviart_thomas_element.go:199-203 with RT order N+1).
+ */
+typedef struct dfr2d_problem {
+    int32_t N;                    /* PolynomialOrder, 0..DFR2D_MAX_ORDER */
+    int32_t flux_type;            /* c.FluxCalcAlgo */
+    int32_t init_case;            /* c.Case (informational) */
+    int32_t local_time_stepping;  /* c.LocalTimeStepping */
+    int32_t max_iterations;       /* c.MaxIterations */
+    int32_t dissipation;          /* c.Dissipation != nil: PerssonC0 limiter requested and N != 0 (euler.go:110) */
+    int64_t K, NV, NE;            /* elements, vertices, edges */
+    int64_t NBP;                  /* boundary edges for which edge-point coordinates are given */
+    double CFL, FinalTime;
+    double Kappa;                 /* ip.Kappa as given (0 -> the dissipation default 5, dissipation.go:140-147) */
+    dfr2d_freestream FSFar, FSIn, FSOut;
+    dfr2d_vortex vortex;          /* analytic state of BC_IVortex edges */
+
+    /* reference-element operators */
+    const double *FluxEdgeInterp; /* [3NpEdge x NpInt]  DFR.FluxEdgeInterp          dfr_startup.go:64   */
+    const double *DivInt;         /* [NpInt x NpFlux]   DFR.FluxElement.DivInt      raviart_thomas_element.go:243-247 */
+    const double *Div;            /* [NpFlux x NpFlux]  DFR.FluxElement.Div         (dissipation only) */
+    const double *V, *Vinv;       /* [NpInt x NpInt]    SolutionElement.JB2D        basis_polynomials.go:41-43 */
+    const double *MassMatrix, *D, *P; /* [NpInt x NpInt] ModeAliasShockFinder       dfr_shock_capturing.go:84-105 */
+    const double *ModeFilter;     /* [NpInt]                                        dfr_shock_capturing.go:43-69 */
+    const double *Bary;           /* [NpFlux x 3]       Dissipation.BaryCentricCoords dissipation.go:414-449 */
+
+    /* geometry, global (un-sharded) */
+    const double *Jdet;           /* [K]        dfr_startup.go:256-287 */
+    const double *Jinv;           /* [K x 4]    element-major {rx,ry,sx,sy} */
+    const double *FaceNormX, *FaceNormY; /* [3 x K]   DFR.FaceNorm[0|1], index k + K*edge, dfr_startup.go:289-310 */
+    const double *IInII;          /* [3 x K]    dfr_startup.go:301 */
+    const double *EdgeLenMax;     /* [K]        dfr_startup.go:125-147 (hK = EdgeLenMax/(N+1)^2) */
+
+    /* topology */
+    const int32_t *EToV;          /* [K x 3]    Tris.EToV */
+    const int32_t *edge_kL, *edge_kR;       /* [NE] Edge.ConnectedTris[0|1]; kR = -1 when NumConnectedTris == 1 */
+    const int32_t *edge_numL, *edge_numR;   /* [NE] Edge.ConnectedTriEdgeNumber[0|1] */
+    const int32_t *edge_nconn;    /* [NE]       Edge.NumConnectedTris */
+    const int32_t *edge_bc;       /* [NE]       Edge.BCType (after the IVORTEX wall->ivortex rewrite, euler.go:781-787) */
+    const double *edge_len;       /* [NE]       Edge.GetEdgeLength() triangulation.go:189-198 */
+    const int32_t *EtoEdge;       /* [K x 3]    position in this table of DFR.EdgeNumber[k + K*e] */
+
+    /* DFR.FluxX/FluxY rows 2NpInt.. of boundary elements only (bcs.go:33-37) */
+    const int32_t *bp_edge;       /* [NBP]          edge index */
+    const double *bp_x, *bp_y;    /* [NBP x NpEdge] in the owner's edge-point order */
+} dfr2d_problem;
+
+typedef struct dfr2d_step_info {
+    double time;        /* rk.Time */
+    double dt;          /* rk.GlobalDT of the last stage (0 with local time stepping) */
+    int64_t steps;      /* rk.StepCount */
+    int32_t finished;   /* CheckIfFinished euler.go:796-801 */
+    int32_t nan_found;  /* utils.IsNanPanic would have fired */
+} dfr2d_step_info;
+
+typedef struct dfr2d_handle dfr2d_handle;
+
+/*
+ * Build one partition of the solver on CUDA device `device`.  n_parts/part select the
+ * contiguous element range of utils.PartitionMap.Split1D (utils/parallel_utils.go:172-192);
+ * n_parts = 1 is the whole mesh on one GPU.  Mirrors the tail of NewEuler + NewRungeKuttaSSP.
+ */
+int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int device, dfr2d_handle **out);
+void dfr2d_destroy(dfr2d_handle *h);
+const char *dfr2d_last_error(const dfr2d_handle *h); /* h may be NULL: error of the last failed create on this thread */
+
+/* c.Q shards <-> global [4][NpInt x K] (parallelism.go:61-98).  get_state writes only this partition's columns. */
+int dfr2d_set_state(dfr2d_handle *h, const double *Q);
+int dfr2d_get_state(dfr2d_handle *h, double *Q);
+
+/* nsteps x { RK.Step; Time += GlobalDT; StepCount++ } (euler.go:177-182); stops early when finished.
+ * info may be NULL (no host synchronisation at all). */
+int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info);
+
+/* Signed max of the Residual arrays per variable, as PrintUpdate reports it (euler.go:821-835). */
+int dfr2d_residual(dfr2d_handle *h, double maxR[4]);
+
+/* Test hooks: RHSQ of stage rk evaluated on register `rk` ({c.Q,Q1..Q4}[rk], euler.go:422) without
+ * advancing; register access; per-element fields. Global layouts, own columns only. */
+int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out);
+int dfr2d_set_register(dfr2d_handle *h, int reg, const double *Q);
+int dfr2d_get_register(dfr2d_handle *h, int reg, double *Q);
+int dfr2d_get_field(dfr2d_handle *h, int which, double *out /* [K] */);
+
+/* ---- plumbing for one-process-per-GPU hosts (torch.distributed / NCCL) ---------------------
+ * The library never calls a collective itself: per stage the host moves the halo bytes and
+ * max-reduces two doubles, between the three phases below.  Single-partition users only need
+ * dfr2d_step().  All work is enqueued on the stream given to dfr2d_set_stream (default 0). */
+int dfr2d_set_stream(dfr2d_handle *h, void *cuda_stream);
+int dfr2d_partition_range(const dfr2d_handle *h, int64_t *k_begin, int64_t *k_end);
+/* doubles sent to / received from every partition each stage (arrays of n_parts) */
+int dfr2d_halo_counts(const dfr2d_handle *h, int64_t *send_counts, int64_t *recv_counts);
+/* device buffers, contiguous, ordered by peer partition */
+int dfr2d_halo_buffers(dfr2d_handle *h, void **send_dev, void **recv_dev);
+/* device address of {max wave speed, max viscous wave speed} of the stage in flight: MAX-allreduce in place */
+int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **dev_two_doubles);
+int dfr2d_stage_prepare(dfr2d_handle *h, int rk); /* edge interpolation if stale + pack the halo send buffer */
+int dfr2d_stage_edges(dfr2d_handle *h, int rk);   /* unpack halo + numerical edge fluxes + wave-speed maxima */
+int dfr2d_stage_update(dfr2d_handle *h, int rk);  /* divergence, dt, SSP-RK update (+ next stage's interpolation) */
+int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info); /* after stage 4: read back time/steps (info may be NULL) */
+
+/* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
+int64_t dfr2d_launch_count(const dfr2d_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFR2D_H */

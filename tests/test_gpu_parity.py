@@ -1,0 +1,149 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Needs a GPU.
+
+Bar (BASELINE.json north_star): per-RHS-evaluation and after-N-steps fields within 1e-11
+relative L2 of the reference restatement on the same mesh, order and inputs.
+"""
+import numpy as np
+import pytest
+
+from conftest import mesh_path
+from gocfd_b200.host.euler2d import Euler
+from gocfd_b200.host.input_parameters import InputParameters2D
+from gocfd_b200.host.meshgen import structured_tri_mesh
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def rel_l2(a, b):
+    den = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (den if den > 0 else 1.0)
+
+
+def make(ip_kw, mesh):
+    base = dict(CFL=1.0, FluxType="Roe", InitType="Freestream", Minf=0.8, Gamma=1.4, Alpha=1.25,
+                FinalTime=100.0, MaxIterations=1000)
+    base.update(ip_kw)
+    return Euler(InputParameters2D(**base), mesh)
+
+
+def pair(c):
+    from gocfd_b200 import lib
+    from oracle.euler2d_oracle import OracleSolver
+    dev = lib.Dfr2d(c.problem)
+    ora = OracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    return dev, ora
+
+
+def perturbed(c, seed=0, amp=0.02):
+    rng = np.random.default_rng(seed)
+    return c.Q * (1.0 + amp * rng.standard_normal(c.Q.shape))
+
+
+@pytest.mark.parametrize("n", range(5))
+@pytest.mark.parametrize("flux", ["average", "lax", "roe", "roe-er"])
+def test_rhs_parity_far_field(n, flux):
+    """One RHS evaluation on the shipped vortex mesh (all-far boundaries), perturbed freestream."""
+    c = make(dict(PolynomialOrder=n, FluxType=flux, Minf=0.5), mesh_path("vortex-new.su2"))
+    c.Q = perturbed(c, seed=n)
+    dev, ora = pair(c)
+    assert rel_l2(dev.rhs(0), ora.rhs(0)) < TOL
+    dev.close()
+
+
+@pytest.mark.parametrize("n", [0, 2, 4])
+def test_freestream_rhs_is_zero_on_device(n):
+    """TestEuler part 3 (euler_test.go:176-225) through the device path: no-BC mesh, M=2."""
+    c = make(dict(PolynomialOrder=n, FluxType="average", Minf=2.0, Alpha=0.0), mesh_path("test_tris_6_nowall.neu"))
+    dev, _ = pair(c)
+    assert np.abs(dev.rhs(0)).max() < 1e-10
+    dev.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4])
+def test_vortex_steps_global_dt(n):
+    """Isentropic vortex with analytic IVortex+Riemann boundaries, global dt, 5 steps."""
+    c = make(dict(PolynomialOrder=n, InitType="IVortex", CFL=1.0, FinalTime=50.0), structured_tri_mesh(16, 12))
+    dev, ora = pair(c)
+    a, b = dev.step(5), ora.step(5)
+    assert a["steps"] == b["steps"] == 5 and a["finished"] == b["finished"]
+    assert abs(a["time"] - b["time"]) <= 1e-13 * abs(b["time"])
+    assert abs(a["dt"] - b["dt"]) <= 1e-12 * abs(b["dt"])
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    ra, rb = dev.residual(), ora.residual()
+    np.testing.assert_allclose(ra, rb, rtol=1e-9, atol=1e-13)
+    dev.close()
+
+
+def test_naca_local_dt_p0():
+    """Config C1: NACA0012 SU2 mesh, N=0, Roe, local time stepping, CFL 2 (wall + far BCs)."""
+    c = make(dict(PolynomialOrder=0, CFL=2.0, LocalTimeStepping=True, MaxIterations=40, Limiter="PerssonC0",
+                  Kappa=4.5, FinalTime=20.0), mesh_path("mesh_NACA0012_inv.su2"))
+    assert not c.problem.Dissipation            # N == 0 disables the limiter (euler.go:110)
+    dev, ora = pair(c)
+    a, b = dev.step(40), ora.step(40)
+    assert a["finished"] and b["finished"] and a["steps"] == b["steps"] == 40
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    np.testing.assert_allclose(dev.residual(), ora.residual(), rtol=1e-8, atol=1e-13)
+    np.testing.assert_allclose(dev.get_field(0), ora.DT, rtol=1e-12)
+    dev.close()
+
+
+def test_naca_local_dt_p2():
+    c = make(dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=10, Minf=0.3, Alpha=0.0),
+             mesh_path("mesh_NACA0012_inv.su2"))
+    dev, ora = pair(c)
+    dev.step(10), ora.step(10)
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    dev.close()
+
+
+def test_final_time_clip_and_finish():
+    """Global dt is clipped to land exactly on FinalTime and later steps are no-ops (euler.go:968-970, :796-801)."""
+    c = make(dict(PolynomialOrder=1, InitType="IVortex", CFL=1.0, FinalTime=0.05), structured_tri_mesh(8, 8))
+    dev, ora = pair(c)
+    a = dev.step(50)
+    b = ora.step(50)
+    assert a["finished"] and b["finished"]
+    assert a["steps"] == b["steps"]
+    assert a["time"] == pytest.approx(0.05, abs=1e-15) and b["time"] == pytest.approx(0.05, abs=1e-15)
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    dev.close()
+
+
+def test_shocktube_inviscid_bcs():
+    """In/Out/Wall boundary types on the shipped Sod mesh, N=0 (dissipation off), 10 steps."""
+    c = make(dict(PolynomialOrder=0, InitType="shocktube", CFL=0.5, FinalTime=0.2), mesh_path("sod-aligned-100pts.su2"))
+    dev, ora = pair(c)
+    dev.step(10), ora.step(10)
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    dev.close()
+
+
+def test_step_is_deterministic_and_state_roundtrip():
+    c = make(dict(PolynomialOrder=2, InitType="IVortex"), structured_tri_mesh(10, 10))
+    from gocfd_b200 import lib
+    d1, d2 = lib.Dfr2d(c.problem), lib.Dfr2d(c.problem)
+    d1.set_state(c.Q), d2.set_state(c.Q)
+    assert np.array_equal(d1.get_state(), c.Q)
+    d1.step(3)
+    d2.step(1), d2.step(2)
+    assert np.array_equal(d1.get_state(), d2.get_state())
+    d1.close(), d2.close()
+
+
+def test_large_mesh_properties():
+    """Full-size property checks (no oracle): C2-sized vortex mesh, N=2 -- freestream stays
+    freestream to round-off and mass is conserved to round-off away from the boundary fluxes."""
+    c = make(dict(PolynomialOrder=2, InitType="Freestream", Minf=0.5, Alpha=30.0, CFL=1.0),
+             structured_tri_mesh(316, 316, tag="far"))
+    from gocfd_b200 import lib
+    dev = lib.Dfr2d(c.problem)
+    dev.set_state(c.Q)
+    dev.step(5)
+    q = dev.get_state()
+    assert rel_l2(q, c.Q) < 1e-12
+    dev.close()
