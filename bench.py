@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the 2D Euler DFR stage on B200 (contract: see the task's bench.py section).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA through the C ABI)
+  python bench.py --impl reference ...                      CPU arm: the oracle port on the host cores
+
+A "step" is one SSP-RK(5,4) time step = 5 passes of the hot path (stages) over the whole mesh.
+Metric: DOF-stage-updates/s = 4 * NpInt * K * 5 * steps / elapsed  (BASELINE.md section 2).
+Default workload: config C5 of BASELINE.json -- synthetic 2000x2000x2 = 8M-triangle isentropic
+vortex, N=4, Roe flux, global dt, analytic IVortex/Riemann boundaries -- element-partitioned over
+the N GPUs with the reference's PartitionMap ranges (strong scaling: the mesh is fixed).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, N)
+    "c5": (2000, 2000, 4),      # 8,000,000 triangles, P=4 (north-star target config)
+    "c2": (316, 316, 2),        # 199,712 triangles, P=2
+}
+
+
+def algorithmic_bytes(n):
+    """Bytes per element per stage of a maximally fused inviscid stage, and the
+    share of the two kernels (DESIGN.md 'Kernels')."""
+    np_int, np_edge = (n + 1) * (n + 2) // 2, n + 2
+    total = 8.0 * (15.2 * np_int + 42 * np_edge + 15)
+    elem = 8.0 * (15.2 * np_int + 24 * np_edge + 7.5)
+    edge = 8.0 * (18 * np_edge + 7.5)
+    return total, elem, edge
+
+
+def build_case(nx, ny, n, max_iter=10 ** 9):
+    from gocfd_b200.host.euler2d import Euler
+    from gocfd_b200.host.input_parameters import InputParameters2D
+    from gocfd_b200.host.meshgen import structured_tri_mesh
+    ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n,
+                           FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.1)
+    return Euler(ip, structured_tri_mesh(nx, ny, tag="wall"))
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through the CUDA array interface."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def cpu_baseline(n, seconds_target=12.0, nx=120):
+    """Oracle port timed on the host cores on a bounded sample of the same workload: same vortex
+    set-up and order on an nx x nx x 2 mesh, whole RK steps until ~seconds_target has elapsed."""
+    from oracle.euler2d_oracle import OracleSolver
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        cores = os.cpu_count() or 1
+    c = build_case(nx, nx, n)
+    o = OracleSolver(c.problem)
+    o.set_state(c.Q)
+    o.step(1)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 2 or time.perf_counter() - t0 < seconds_target:
+        o.step(1)
+        steps += 1
+        if steps >= 200:
+            break
+    el = time.perf_counter() - t0
+    dof = 4 * c.problem.NpInt * c.problem.K * 5 * steps
+    return {"value": dof / el, "unit": "DOF-stage-updates/s", "cores": cores, "kind": "port",
+            "sample": "numpy restatement of the Go stage (oracle/), %dx%dx2=%d triangles, N=%d, %d RK steps in %.1f s; "
+                      "BLAS matmuls threaded, element loops vectorised single-thread; not the Go solver"
+                      % (nx, nx, c.problem.K, n, steps, el)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    nx, ny, n = WORKLOADS[args.workload]
+    t_all = time.perf_counter()
+    base = cpu_baseline(n, seconds_target=max(4.0, 3.0 * args.steps))
+    line = {
+        "impl": "reference", "metric": "DOF-stage-updates/s", "value": base["value"], "unit": "DOF-stage-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "%s: isentropic vortex, %dx%dx2 triangles, N=%d, Roe, global dt (CPU arm runs a bounded "
+                               "sample of it)" % (args.workload, nx, ny, n)},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "DOF-stage-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=0, help="override the mesh size (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from gocfd_b200 import lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    nx, ny, n = WORKLOADS[args.workload]
+    if args.nx:
+        nx = ny = args.nx
+    t_setup = time.perf_counter()
+    c = build_case(nx, ny, n)
+    p = c.problem
+    dev = lib.Dfr2d(p, n_parts=world, part=rank, device=local_rank)
+    stream = torch.cuda.current_stream()
+    dev.set_stream(stream.cuda_stream)
+    k0, k1 = dev.partition_range()
+    setup_s = time.perf_counter() - t_setup
+
+    # state lives in pinned host memory (the Go side would pin c.Q the same way)
+    q_host_t = torch.empty((4, p.NpInt, p.K), dtype=torch.float64, pin_memory=True)
+    q_host = q_host_t.numpy()
+    q_host[...] = c.Q
+    dev.set_state(q_host)
+
+    if world > 1:
+        sc, rc = dev.halo_counts()
+        sp, rp = dev.halo_buffers()
+        send_t = torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda")[:sum(sc)]
+        recv_t = torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda")[:sum(rc)]
+        wave_t = [None, None]
+
+        def one_step():
+            for rk in range(5):
+                dev.stage_prepare(rk)
+                dist.all_to_all_single(recv_t, send_t, rc, sc)
+                dev.stage_edges(rk)
+                wp = dev.wavespeed_buffer()
+                w = torch.as_tensor(_DevArray(wp, 2), device="cuda")
+                dist.all_reduce(w, op=dist.ReduceOp.MAX)
+                dev.stage_update(rk)
+
+        def run_steps(k):
+            for _ in range(k):
+                one_step()
+    else:
+        def run_steps(k):
+            dev.step(k, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_steps(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = dev.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    run_steps(args.steps)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = dev.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    dof_per_step = 4 * p.NpInt * p.K * 5
+    value = dof_per_step * args.steps / (ms * 1e-3)
+
+    # ---- per-kernel timing of the dominant kernel (k_elem) with CUDA events on the launch stream
+    b_total, b_elem, b_edge = algorithmic_bytes(n)
+    k_local = k1 - k0
+    t_elem, t_edge = [], []
+    if world == 1:
+        evs = []
+        for _ in range(2):
+            for rk in range(5):
+                a, b, cc = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                dev.stage_prepare(rk)
+                a.record(stream)
+                dev.stage_edges(rk)
+                b.record(stream)
+                dev.stage_update(rk)
+                cc.record(stream)
+                evs.append((a, b, cc))
+        torch.cuda.synchronize()
+        t_edge = [a.elapsed_time(b) for a, b, _ in evs]
+        t_elem = [b.elapsed_time(cc) for _, b, cc in evs]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roofline = None
+    if t_elem:
+        te = statistics.mean(t_elem) * 1e-3
+        ach = b_elem * k_local / te / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_elem<N=%d>" % n, "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": b_elem * k_local, "avg_launch_ms": te * 1e3,
+                    "edge_kernel": {"achieved": b_edge * k_local / (statistics.mean(t_edge) * 1e-3) / 1e9,
+                                    "avg_launch_ms": statistics.mean(t_edge)},
+                    "whole_stage": {"bytes_per_element": b_total,
+                                    "achieved": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9,
+                                    "frac": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9 / peak / world}}
+        prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(prof):
+            try:
+                roofline["traffic"] = json.load(open(prof)).get("k_elem_N%d" % n)
+            except Exception:
+                pass
+
+    # ---- end to end through the C ABI with host buffers: upload state, K steps each returning
+    # step info to the host (as Solve does for its progress line), download state.
+    e2e = None
+    if world == 1:
+        q_host[...] = c.Q
+        k_e2e = args.steps
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev.set_state(q_host)
+        for _ in range(k_e2e):
+            info = dev.step(1, sync=True)
+        dev.get_state(q_host)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        qb = q_host.nbytes
+        e2e = {"value": dof_per_step * k_e2e / el, "unit": "DOF-stage-updates/s",
+               "h2d_bytes_per_step": qb / k_e2e, "d2h_bytes_per_step": qb / k_e2e + 40,
+               "what": "dfr2d_set_state(pinned host Q) + %d x dfr2d_step(1, info) + dfr2d_get_state" % k_e2e}
+    else:
+        # every rank uploads its columns, steps with the NCCL exchange, downloads its columns
+        q_host[...] = c.Q
+        barrier()
+        t0 = time.perf_counter()
+        dev.set_state(q_host)
+        for _ in range(args.steps):
+            one_step()
+            dev.step_finish(sync=True)
+        dev.get_state(q_host)
+        barrier()
+        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        qb = 4 * p.NpInt * (k1 - k0) * 8
+        e2e = {"value": dof_per_step * args.steps / float(el.item()), "unit": "DOF-stage-updates/s",
+               "h2d_bytes_per_step": qb / args.steps, "d2h_bytes_per_step": qb / args.steps + 40,
+               "what": "per rank: set_state(own columns) + steps with NCCL halo exchange + step info + get_state"}
+
+    if rank == 0:
+        line = {
+            "metric": "DOF-stage-updates/s", "value": value, "unit": "DOF-stage-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: isentropic vortex, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, "
+                                   "IVortex+Riemann boundaries" % (args.workload, nx, ny, p.K, n, p.NpInt),
+                       "partition": "PartitionMap.Split1D element ranges over %d GPU(s)" % world,
+                       "l2": "no flush needed: per-GPU working set %.1f GB >> 126 MB L2"
+                             % ((5 * 4 * p.NpInt + 12 * p.NpEdge + 6 * p.NpEdge) * 8 * k_local / 1e9),
+                       "setup_s": setup_s},
+            "element_stages_per_s": p.K * 5 * args.steps / (ms * 1e-3),
+            "us_per_element_iteration": ms * 1e3 / args.steps / p.K,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(n)
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
