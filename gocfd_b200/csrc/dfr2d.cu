@@ -560,8 +560,59 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     return launch_check(h, "k_elem");
 }
 
-static int run_diss_prepare(dfr2d_handle *h, int rk) { (void)rk; h->err = "dissipation path not built yet"; return 9; }
-static int run_diss_edges(dfr2d_handle *h, int rk) { (void)rk; h->err = "dissipation path not built yet"; return 9; }
+// sensor + vertex merge + (rk == 2) limiter + edge interpolation: phases P1-P3 of StepWorker (euler.go:574-616)
+static int run_diss_prepare(dfr2d_handle *h, int rk) {
+    DissBuffers &d = h->ds;
+    CK(cudaMemsetAsync(d.sigmaV, 0, (size_t)h->NV * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(d.epsV, 0, (size_t)h->NV * sizeof(double), h->stream));
+    SensorArgs sa{};
+    sa.K = h->K; sa.Kp = h->Kp;
+    sa.rho = h->q[rk];
+    sa.etov = d.etov; sa.hk = d.hk;
+    sa.se = d.se; sa.sigma = d.sigma; sa.epsk = d.epsk;
+    sa.sigmaV = (unsigned long long *)d.sigmaV; sa.epsV = (unsigned long long *)d.epsV;
+    sa.sc = h->sc; sa.par = (int)(h->stepIndex & 1); sa.stepIndex = h->stepIndex; sa.ph = h->ph;
+    DISPATCH_N(h->N, (k_sensor<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(sa)));
+    if (int rc = launch_check(h, "k_sensor")) return rc;
+    PrepArgs pa{};
+    pa.K = h->K; pa.Kp = h->Kp;
+    pa.q = h->q[rk]; pa.qface = h->qface;
+    pa.etov = d.etov; pa.sigmaV = d.sigmaV; pa.sigma = d.sigma;
+    pa.sc = h->sc; pa.rk = rk; pa.par = sa.par; pa.stepIndex = h->stepIndex; pa.ph = h->ph;
+    const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    DISPATCH_N(h->N, (k_diss_prepare<NN><<<blocks, kElemThreads, 0, h->stream>>>(pa)));
+    return launch_check(h, "k_diss_prepare");
+}
+
+// RT gradient x epsilon, then the viscous edge flux: phases P5-P6 (euler.go:624-635)
+static int run_diss_edges(dfr2d_handle *h, int rk) {
+    DissBuffers &d = h->ds;
+    GradArgs ga{};
+    ga.K = h->K; ga.Kp = h->Kp;
+    ga.q = h->q[rk]; ga.qface = h->qface;
+    ga.etoe = h->etoe; ga.ekL = h->ekL; ga.ekR = h->ekR; ga.emeta = h->emeta;
+    ga.Jdet = h->Jdet; ga.Jinv = h->Jinv; ga.IInII = h->IInII; ga.nxk = d.nxk; ga.nyk = d.nyk;
+    ga.etov = d.etov; ga.epsV = d.epsV;
+    ga.dissX = d.dissX; ga.dissY = d.dissY;
+    ga.sc = h->sc; ga.par = (int)(h->stepIndex & 1); ga.stepIndex = h->stepIndex; ga.ph = h->ph;
+    const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    DISPATCH_N(h->N, {
+        const size_t sm = (size_t)4 * (Dim<NN>::NpInt + Dim<NN>::NF3) * kElemsPerBlock * sizeof(double);
+        k_grad<NN><<<blocks, kElemThreads, sm, h->stream>>>(ga);
+    });
+    if (int rc = launch_check(h, "k_grad")) return rc;
+    ViscEdgeArgs va{};
+    va.ne = h->NE; va.NEp = h->NEp; va.Kp = h->Kp;
+    va.kL = h->ekL; va.kR = h->ekR; va.meta = h->emeta;
+    va.nx = h->enx; va.ny = h->eny; va.oohk = h->eoohk; va.ooLen = d.eooLen;
+    va.qface = h->qface; va.dissX = d.dissX; va.dissY = d.dissY;
+    va.etov = d.etov; va.epsV = d.epsV;
+    va.vflux = d.vflux; va.aggv = d.aggv;
+    va.sc = h->sc; va.slot = (int)(h->stageCounter & 1); va.par = ga.par; va.stepIndex = h->stepIndex; va.ph = h->ph;
+    const int eb = std::max(1, std::min(h->edgeBlocks, (h->NE + 255) / 256));
+    DISPATCH_N(h->N, (k_visc_edge<NN><<<eb, 256, 0, h->stream>>>(va)));
+    return launch_check(h, "k_visc_edge");
+}
 
 // ---- stage phases (also the multi-process API) ---------------------------------------------------------
 static int stage_prepare(dfr2d_handle *h, int rk) {

@@ -55,6 +55,319 @@ __global__ void __launch_bounds__(1024) k_signed_max(const double *R, int npInt,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Phase P1: Persson modal sensor on the density of the stage input, sigma, element viscosity, and
+// the element -> vertex max merge.  One thread per element.
+//   UpdateSeMoment (DG2D/dfr_shock_capturing.go:142-166), UpdateShockFinderSigma
+//   (dissipation.go:491-518), CalculateElementViscosity (:397-412),
+//   MergeElementScalarToVertices with max (euler.go:1048-1065): every incident element contributes,
+//   values are >= 0, so zero + atomicMax on the bit pattern gives the same vertex value.
+// ------------------------------------------------------------------------------------------------
+struct SensorArgs {
+    int K, Kp;
+    const double *rho;                 // [NpInt][Kp] density rows of the stage input
+    const int *etov;                   // [3][Kp]
+    const double *hk;
+    double *se, *sigma, *epsk;
+    unsigned long long *sigmaV, *epsV; // [NV] double bits
+    DevScalars *sc;
+    int par;
+    long long stepIndex;
+    Phys ph;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) k_sensor(SensorArgs a) {
+    constexpr int NI = Dim<N>::NpInt;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const Ops<N> &op = ops<N>();
+    double rho[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) rho[i] = a.rho[(size_t)i * a.Kp + k];
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        double x = 0.0, y = 0.0, dq = 0.0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) {
+            x = fma(op.P[i][j], rho[j], x);
+            y = fma(op.M[i][j], rho[j], y);
+            dq = fma(op.D[i][j], rho[j], dq);
+        }
+        num += dq * x;
+        den += rho[i] * y;
+    }
+    const double se = log10(num / den);
+    const double kappa = a.ph.sdKappa, S0 = a.ph.S0;
+    const double left = S0 - kappa, right = S0 + kappa, ookappa = 0.5 / kappa;
+    double sigma = 0.0;                 // (a NaN Se matches no case in the reference; unreachable for rho > 0)
+    if (se < left) sigma = 0.0;
+    else if (se >= left && se <= right) sigma = 0.5 * (1.0 + sin(3.14159265358979323846 * ookappa * (se - S0)));
+    else if (se > right) sigma = 1.0;
+    const double eps = a.ph.Eps0 * a.hk[k] * sigma;
+    a.se[k] = se;
+    a.sigma[k] = sigma;
+    a.epsk[k] = eps;
+#pragma unroll
+    for (int v = 0; v < 3; v++) {
+        const int vid = a.etov[(size_t)v * a.Kp + k];
+        if (sigma > 0.0) atomic_max_nonneg(&a.sigmaV[vid], sigma);
+        if (eps > 0.0) atomic_max_nonneg(&a.epsV[vid], eps);
+    }
+}
+
+// limitAndFilterSolution (dissipation.go:606-622) on one (element, variable) row held in registers
+template <int N>
+__device__ __forceinline__ void limit_filter_row(double (&u)[Dim<N>::NpInt], double sigmaK) {
+    constexpr int NI = Dim<N>::NpInt;
+    const Ops<N> &op = ops<N>();
+    const double alpha = sin(0.5 * 3.14159265358979323846 * sigmaK);
+    double uh[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) s = fma(op.Vinv[i][j], u[j], s);
+        uh[i] = (i >= 1) ? s * (op.mf[i] * (1.0 - alpha)) : s;
+    }
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) s = fma(op.V[i][j], uh[j], s);
+        u[i] = s;
+    }
+}
+
+// Phase P3: sigma_k = mean of its three vertex values (euler.go:1067-1086); at rk == 2 the stage
+// input is limited/filtered in place (euler.go:605-609); then the edge interpolation.
+struct PrepArgs {
+    int K, Kp;
+    double *q;                         // stage input register (modified in place at rk == 2)
+    double *qface;
+    const int *etov;
+    const double *sigmaV;
+    double *sigma;
+    DevScalars *sc;
+    int rk, par;
+    long long stepIndex;
+    Phys ph;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kElemThreads) k_diss_prepare(PrepArgs a) {
+    constexpr int NI = Dim<N>::NpInt;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    const int e = threadIdx.x % kElemsPerBlock, n = threadIdx.x / kElemsPerBlock;
+    const int k = blockIdx.x * kElemsPerBlock + e;
+    if (k >= a.K) return;
+    double acc = 0.0;
+#pragma unroll
+    for (int v = 0; v < 3; v++) acc = acc + a.sigmaV[a.etov[(size_t)v * a.Kp + k]];
+    const double sig = acc / 3.;
+    if (n == 0) a.sigma[k] = sig;
+    double qs[NI];
+#pragma unroll
+    for (int i = 0; i < NI; i++) qs[i] = a.q[((size_t)n * NI + i) * a.Kp + k];
+    if (a.rk == 2) {
+        limit_filter_row<N>(qs, sig);
+#pragma unroll
+        for (int i = 0; i < NI; i++) a.q[((size_t)n * NI + i) * a.Kp + k] = qs[i];
+    }
+    interp_store<N>(qs, a.qface + (size_t)n * Dim<N>::NF3 * a.Kp, a.Kp, k);
+}
+
+// Epsilon at RT row r of an element from its three vertex values (InterpolateEpsilonSigma,
+// dissipation.go:219-242): Bary[NpFlux x 3] . vertexVals[3]
+template <int N>
+__device__ __forceinline__ double eps_row(int r, double e0, double e1, double e2) {
+    const Ops<N> &op = ops<N>();
+    return op.Bary[r][0] * e0 + op.Bary[r][1] * e1 + op.Bary[r][2] * e2;
+}
+
+// Phase P5: RT-element gradient of every conserved variable, times Epsilon
+//   GetSolutionGradientUsingRTElement (euler.go:864-918) + CalculateEpsilonGradient C0 branch
+//   (dissipation.go:244-272).  Only the rows later consumed are produced: [0, NpInt) (AddDissipation)
+//   and the 3*NpEdge edge rows (StoreEdgeViscousFlux); the duplicate interior rows are never read.
+struct GradArgs {
+    int K, Kp;
+    const double *q;                   // stage input (after the rk == 2 limiter)
+    const double *qface;               // Q_Face incl. neighbours (pre-BC = EdgeQValues of the owner)
+    const int *etoe;                   // [3][Kp] edge slot (or -1-slot when not the owner)
+    const int *ekL, *ekR, *emeta;      // edge table
+    const double *Jdet, *Jinv, *IInII, *nxk, *nyk;
+    const int *etov;
+    const double *epsV;
+    double *dissX, *dissY;             // [4][NpFlux][Kp]
+    DevScalars *sc;
+    int par;
+    long long stepIndex;
+    Phys ph;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kElemThreads) k_grad(GradArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
+    constexpr int E = kElemsPerBlock;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    extern __shared__ double smem[];
+    double *sU = smem;                 // [4][NI + NF3][E]: distinct solution values of the RT points
+    const Ops<N> &op = ops<N>();
+    const int e = threadIdx.x % E, n = threadIdx.x / E;
+    const int k = blockIdx.x * E + e;
+    const bool valid = k < a.K;
+    const int kc = valid ? k : a.K - 1;
+    const size_t Kp = a.Kp;
+    constexpr int NU = NI + NF3;
+    double *u = sU + (size_t)n * NU * E + e;          // u[j * E]
+#pragma unroll
+    for (int i = 0; i < NI; i++) u[i * E] = a.q[((size_t)n * NI + i) * Kp + kc];
+    const size_t qplane = (size_t)NF3 * Kp;
+#pragma unroll
+    for (int le = 0; le < 3; le++) {
+        const int s = a.etoe[(size_t)le * Kp + kc];
+        if (s >= 0) {                   // owner: own edge values
+#pragma unroll
+            for (int i = 0; i < NEd; i++) u[(NI + le * NEd + i) * E] = a.qface[n * qplane + (size_t)(le * NEd + i) * Kp + kc];
+        } else {                        // neighbour: the owner's values in reversed order (euler.go:896-912)
+            const int slot = -1 - s;
+            const int kO = a.ekL[slot];
+            const int numO = a.emeta[slot] & 3;
+#pragma unroll
+            for (int i = 0; i < NEd; i++)
+                u[(NI + le * NEd + i) * E] = a.qface[n * qplane + (size_t)(numO * NEd + (NEd - 1 - i)) * Kp + kO];
+        }
+    }
+    // per-element metric scalars (CalculateRTBasedDerivativeMetrics, DG2D/dfr_startup.go:213-254)
+    const double j0 = a.Jinv[0 * Kp + kc], j1 = a.Jinv[1 * Kp + kc], j2 = a.Jinv[2 * Kp + kc], j3 = a.Jinv[3 * Kp + kc];
+    const double oojd = 1.0 / a.Jdet[kc];
+    double mx[3], my[3];
+#pragma unroll
+    for (int le = 0; le < 3; le++) {
+        const double iin = a.IInII[(size_t)le * Kp + kc];
+        mx[le] = oojd * a.nxk[(size_t)le * Kp + kc] * iin;
+        my[le] = oojd * a.nyk[(size_t)le * Kp + kc] * iin;
+    }
+    const double ev0 = a.epsV[a.etov[0 * Kp + kc]], ev1 = a.epsV[a.etov[1 * Kp + kc]], ev2 = a.epsV[a.etov[2 * Kp + kc]];
+    __syncthreads();   // (each thread only reads what it wrote; the barrier keeps the phases aligned across warps)
+
+    // output rows in chunks; DOF_j = metric_j * U_j is formed on the fly
+    constexpr int NOUT = NI + NF3;                 // rows [0,NI) and [2NI, NF)
+    constexpr int CH = (NOUT % 11 == 0) ? 11 : ((NOUT % 9 == 0) ? 9 : ((NOUT % 7 == 0) ? 7 : ((NOUT % 5 == 0) ? 5 : 3)));
+    static_assert(NOUT % CH == 0, "chunking");
+#pragma unroll
+    for (int c0 = 0; c0 < NOUT; c0 += CH) {
+        double gx[CH], gy[CH];
+#pragma unroll
+        for (int r = 0; r < CH; r++) { gx[r] = 0.0; gy[r] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < NF; j++) {
+            // value and metric of RT point j
+            const int ju = (j < NI) ? j : ((j < 2 * NI) ? j - NI : j - NI);
+            const double uj = u[ju * E];
+            double dx, dy;
+            if (j < NI) { dx = j0 * uj; dy = j1 * uj; }
+            else if (j < 2 * NI) { dx = j2 * uj; dy = j3 * uj; }
+            else { const int le = (j - 2 * NI) / NEd; dx = mx[le] * uj; dy = my[le] * uj; }
+#pragma unroll
+            for (int r = 0; r < CH; r++) {
+                const int row = (c0 + r < NI) ? (c0 + r) : (c0 + r + NI);
+                const double d = op.Div[row][j];
+                gx[r] = fma(d, dx, gx[r]);
+                gy[r] = fma(d, dy, gy[r]);
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < CH; r++) {
+                const int row = (c0 + r < NI) ? (c0 + r) : (c0 + r + NI);
+                const double eps = op.Bary[row][0] * ev0 + op.Bary[row][1] * ev1 + op.Bary[row][2] * ev2;
+                a.dissX[((size_t)n * NF + row) * Kp + k] = gx[r] * eps;
+                a.dissY[((size_t)n * NF + row) * Kp + k] = gy[r] * eps;
+            }
+        }
+    }
+}
+
+// Phase P6: StoreEdgeViscousFlux (edges.go:151-244) + the viscous half of StoreEdgeAggregates
+// (edges.go:274-286).  One thread per edge, grid-stride.
+struct ViscEdgeArgs {
+    int ne, NEp, Kp;
+    const int *kL, *kR, *meta;
+    const double *nx, *ny, *oohk, *ooLen;
+    const double *qface, *dissX, *dissY;
+    const int *etov;
+    const double *epsV;
+    double *vflux, *aggv;
+    DevScalars *sc;
+    int slot, par;
+    long long stepIndex;
+    Phys ph;
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    const size_t Kp = a.Kp;
+    const size_t dplane = (size_t)NF * Kp, qplane = (size_t)NF3 * Kp, fplane = (size_t)NEd * a.NEp;
+    double blockmax = 0.0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.ne; e += gridDim.x * blockDim.x) {
+        const int kL = a.kL[e], kRraw = a.kR[e], meta = a.meta[e];
+        const bool shared = kRraw >= 0;
+        const int kR = shared ? kRraw : 0;
+        const int numL = meta & 3, numR = (meta >> 2) & 3;
+        const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
+        const double eL0 = a.epsV[a.etov[0 * Kp + kL]], eL1 = a.epsV[a.etov[1 * Kp + kL]], eL2 = a.epsV[a.etov[2 * Kp + kL]];
+        double eR0 = 0, eR1 = 0, eR2 = 0;
+        if (shared) { eR0 = a.epsV[a.etov[0 * Kp + kR]]; eR1 = a.epsV[a.etov[1 * Kp + kR]]; eR2 = a.epsV[a.etov[2 * Kp + kR]]; }
+        const double ooLen = a.ooLen[e];
+        double vmax = -1.7976931348623157e308;
+#pragma unroll
+        for (int i = 0; i < NEd; i++) {
+            const int rowL = 2 * NI + numL * NEd + i;
+            const int rowR = 2 * NI + numR * NEd + (NEd - 1 - i);
+            const Ops<N> &op = ops<N>();
+            const double epsL = op.Bary[rowL][0] * eL0 + op.Bary[rowL][1] * eL1 + op.Bary[rowL][2] * eL2;
+            vmax = fmax(oohk * oohk * epsL, vmax);
+            double lam = 0.0;
+            if (shared) {
+                const double epsR = op.Bary[rowR][0] * eR0 + op.Bary[rowR][1] * eR1 + op.Bary[rowR][2] * eR2;
+                lam = 0.5 * (epsL + epsR);
+            }
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+                const double vFL = nx * a.dissX[n * dplane + (size_t)rowL * Kp + kL] + ny * a.dissY[n * dplane + (size_t)rowL * Kp + kL];
+                double vf = vFL;
+                if (shared) {
+                    // normalR := normalL in the reference (edges.go:175)
+                    const double vFR = nx * a.dissX[n * dplane + (size_t)rowR * Kp + kR] + ny * a.dissY[n * dplane + (size_t)rowR * Kp + kR];
+                    vf = 0.5 * (vFL + vFR);
+                    // both "sides" of the jump resolve to the owner's stored edge values (edges.go:225-236)
+                    const double qa = a.qface[n * qplane + (size_t)(numL * NEd + i) * Kp + kL];
+                    const double qb = a.qface[n * qplane + (size_t)(numL * NEd + (NEd - 1 - i)) * Kp + kL];
+                    vf -= (a.ph.Omega * lam * ooLen) * (qa - qb);
+                }
+                a.vflux[n * fplane + (size_t)i * a.NEp + e] = vf;
+            }
+        }
+        a.aggv[e] = vmax;
+        blockmax = fmax(blockmax, vmax);
+    }
+    __shared__ double smax[8];
+    blockmax = warp_max(blockmax);
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
+        v = warp_max(v);
+        if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][1], v);
+    }
+}
+
 template <int N> static size_t elem_smem_diss() { return (size_t)12 * Dim<N>::NpInt * kElemsPerBlock * sizeof(double); }
 
 }  // namespace dfr2d

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kElemThreads) k_interp(int K, int Kp, const do
     interp_store<N>(qs, qface + (size_t)n * Dim<N>::NF3 * Kp, Kp, k);
 }
 
+template <int N> __device__ __forceinline__ void limit_filter_row(double (&u)[Dim<N>::NpInt], double sigmaK);
+
 struct ElemArgs {
     int K, Kp, NEp;
     const double *qs;                       // stage input register [4][NpInt][Kp]
@@ -236,6 +238,16 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
                 const double v = f[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
                 fe[le * NEd + i] = owner ? v * iin : -v * iin;
             }
+            if (DISS) {
+                // AddDissipation edge DOFs (dissipation.go:316-333): edgeFlux[ii] * IInII * sign; folded into the
+                // same contraction with the opposite sign (RHS = -(1/J) DivInt (F - F_visc))
+                const double *fv = a.vflux + ((size_t)n * NEd) * a.NEp + slot;
+#pragma unroll
+                for (int i = 0; i < NEd; i++) {
+                    const double v = fv[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
+                    fe[le * NEd + i] -= owner ? v * iin : v * iin * -1.0;
+                }
+            }
             if (a.ph.localDT) {
                 wmaxk = fmax(wmaxk, a.agg[slot]);
                 if (DISS) vmaxk = fmax(vmaxk, a.aggv[slot]);
@@ -274,8 +286,16 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
             flux_calc(a.ph.gamma, Q, Fx, Fy);
 #pragma unroll
             for (int m = 0; m < 4; m++) {
-                sF[(m * 2 * NI + j) * E + e] = jdet * (j0 * Fx[m] + j1 * Fy[m]);
-                sF[(m * 2 * NI + j + NI) * E + e] = jdet * (j2 * Fx[m] + j3 * Fy[m]);
+                double fr = jdet * (j0 * Fx[m] + j1 * Fy[m]);
+                double fs = jdet * (j2 * Fx[m] + j3 * Fy[m]);
+                if (DISS) {   // interior dissipation DOFs (dissipation.go:310-315)
+                    const double dix = a.dissX[((size_t)m * Dim<N>::NpFlux + j) * Kp + kc];
+                    const double diy = a.dissY[((size_t)m * Dim<N>::NpFlux + j) * Kp + kc];
+                    fr -= jdet * (j0 * dix + j1 * diy);
+                    fs -= jdet * (j2 * dix + j3 * diy);
+                }
+                sF[(m * 2 * NI + j) * E + e] = fr;
+                sF[(m * 2 * NI + j + NI) * E + e] = fs;
             }
         }
     }
@@ -299,6 +319,7 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
     const double moojd = -(1.0 / jdet);
 #pragma unroll
     for (int i = 0; i < NI; i++) acc[i] *= moojd;
+    if (DISS) limit_filter_row<N>(acc, a.sigma[kc]);     // LimitFilterSolution(RHSQ) (euler.go:499)
 
     if (a.rhsOut != nullptr) {
         if (valid) {

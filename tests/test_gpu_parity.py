@@ -147,3 +147,66 @@ def test_large_mesh_properties():
     q = dev.get_state()
     assert rel_l2(q, c.Q) < 1e-12
     dev.close()
+
+
+# ---- artificial dissipation path (Persson C0): SURVEY.md 8(a) rows a15-a21 ---------------------------
+
+def _sod(n, **kw):
+    base = dict(PolynomialOrder=n, InitType="shocktube", CFL=1.0, FinalTime=0.2, Limiter="persson c0", Kappa=5.0)
+    base.update(kw)
+    return make(base, mesh_path("sod-aligned-100pts.su2"))
+
+
+def _smeared_sod_state(c, width=0.004):
+    """A state with an under-resolved front inside elements so that the sensor fires."""
+    x, _ = c.DFR.solution_xy()
+    w = 0.5 * (1.0 - np.tanh((x - 0.503) / width))
+    q = np.empty_like(c.Q)
+    for n in range(4):
+        q[n] = c.FSOut.Qinf[n] + (c.FSIn.Qinf[n] - c.FSOut.Qinf[n]) * w
+    return q
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+@pytest.mark.parametrize("rk", [0, 2])
+def test_dissipation_rhs_parity(n, rk):
+    """RHSQ with sensor, vertex merge, RT gradient, viscous edge flux, AddDissipation and the RHS
+    limiter; rk=2 also exercises the in-place limiting of the stage input (euler.go:605-609)."""
+    c = _sod(n)
+    assert c.problem.Dissipation
+    q = _smeared_sod_state(c, 0.004 if n == 1 else 0.002)
+    dev, ora = pair(c)
+    dev.set_register(rk, q)
+    ora.Q[rk][...] = q
+    a, b = dev.rhs(rk), ora.rhs(rk)
+    assert ora.SigmaScalar.max() > 0.05, "test state must trigger the sensor"
+    assert rel_l2(a, b) < TOL
+    np.testing.assert_allclose(dev.get_field(3)[np.isfinite(ora.Se)], ora.Se[np.isfinite(ora.Se)], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(dev.get_field(1), ora.SigmaScalar, rtol=1e-9, atol=1e-12)
+    dev.close()
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_sod_steps_with_dissipation(n):
+    """Config C3: Sod tube, PerssonC0, global dt (incl. the viscous dt limit), 10 steps from a smeared front."""
+    c = _sod(n, CFL=2.0)
+    c.Q = _smeared_sod_state(c)
+    dev, ora = pair(c)
+    a, b = dev.step(10), ora.step(10)
+    assert a["steps"] == b["steps"]
+    assert abs(a["time"] - b["time"]) <= 1e-12 * abs(b["time"])
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    dev.close()
+
+
+def test_naca_transonic_local_dt_with_dissipation():
+    """Config C4 flavour: NACA0012 M=0.8 alpha=2, N=2, PerssonC0 Kappa 4.5, local time stepping
+    (exercises DTVisc carry-over, euler.go:989-999)."""
+    c = make(dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=12, Minf=0.8, Alpha=2.0,
+                  Limiter="PerssonC0", Kappa=4.5), mesh_path("mesh_NACA0012_inv.su2"))
+    assert c.problem.Dissipation
+    dev, ora = pair(c)
+    dev.step(12), ora.step(12)
+    assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    np.testing.assert_allclose(dev.get_field(0), ora.DT, rtol=1e-10)
+    dev.close()
