@@ -142,6 +142,173 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
     delete h;
 }
 
+// Host-only partition plan: which elements/edges/ghost columns a partition holds and what crosses the
+// cut each stage.  Pure integer/geometry bookkeeping, no CUDA -- also exported (dfr2d_plan_*) so the
+// multi-partition logic can be tested on a CPU-only machine.
+struct dfr2d_plan {
+    int N = 0, nParts = 1, part = 0;
+    int64_t Kglobal = 0, k0 = 0, k1 = 0;
+    int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
+    std::vector<int> ekL, ekR, emeta, etoe, sendElem, sendRow0, recvCol, recvRow0;
+    std::vector<double> enx, eny, eoohk, eooLen, bpx, bpy, Jdet, Jinv, IInII;
+    std::vector<int64_t> ghostGlobal, edgeGlobal, sendCounts, recvCounts;
+    int nSendEdges = 0, nRecvEdges = 0;
+    int64_t sendTotal = 0, recvTotal = 0;
+    std::string err;
+};
+
+static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
+    const int N = p->N;
+    pl.N = N;
+    const int NEd = N + 2;
+    // ---- partition (utils.PartitionMap, parallelism.go:179-190) ------------------------------
+    pl.Kglobal = p->K;
+    split1d(p->K, pl.nParts, pl.part, &pl.k0, &pl.k1);
+    const int64_t k0 = pl.k0, k1 = pl.k1;
+    pl.K = (int)(k1 - k0);
+    auto mine = [&](int64_t k) { return k >= k0 && k < k1; };
+
+    // local edges = every edge touching an owned element; remote sides become ghost columns
+    struct LE { int64_t ge; int l, r; };
+    std::vector<LE> led;
+    led.reserve((size_t)(pl.nParts == 1 ? p->NE : 2 * (p->NE / pl.nParts) + 1024));
+    std::unordered_map<int64_t, int> ghostOf;
+    auto &ghostGlobal = pl.ghostGlobal;
+    auto local_col = [&](int64_t kg) -> int {
+        if (mine(kg)) return (int)(kg - k0);
+        auto it = ghostOf.find(kg);
+        if (it != ghostOf.end()) return pl.K + it->second;
+        int g = (int)ghostGlobal.size();
+        ghostOf.emplace(kg, g);
+        ghostGlobal.push_back(kg);
+        return pl.K + g;
+    };
+    for (int64_t e = 0; e < p->NE; e++) {
+        const int64_t kl = p->edge_kL[e], kr = (p->edge_nconn[e] == 2) ? p->edge_kR[e] : -1;
+        if (!(mine(kl) || (kr >= 0 && mine(kr)))) continue;
+        led.push_back({e, 0, 0});
+    }
+    // ghosts are numbered in global-edge order so that both sides of a cut agree on the message order
+    for (auto &le : led) {
+        const int64_t e = le.ge;
+        le.l = local_col(p->edge_kL[e]);
+        le.r = (p->edge_nconn[e] == 2) ? local_col(p->edge_kR[e]) : -1;
+    }
+    pl.G = (int)ghostGlobal.size();
+    pl.Kp = ((pl.K + pl.G + 31) / 32) * 32;
+    // sort by the owner-side column so that owner-side loads of neighbouring threads coalesce
+    std::stable_sort(led.begin(), led.end(), [](const LE &a, const LE &b) { return a.l < b.l; });
+    pl.NE = (int)led.size();
+    pl.NEp = ((pl.NE + 31) / 32) * 32;
+    pl.NV = (int)p->NV;
+    const int Kp = pl.Kp, K = pl.K;
+
+    std::unordered_map<int64_t, int> slotOfGlobalEdge;
+    if (pl.nParts > 1) slotOfGlobalEdge.reserve(led.size() * 2);
+    std::vector<int> slotOfEdgeDense;
+    if (pl.nParts == 1) slotOfEdgeDense.assign((size_t)p->NE, -1);
+    auto &ekL = pl.ekL; auto &ekR = pl.ekR; auto &emeta = pl.emeta;
+    auto &enx = pl.enx; auto &eny = pl.eny; auto &eoohk = pl.eoohk; auto &eooLen = pl.eooLen;
+    ekL.assign(pl.NE, 0); ekR.assign(pl.NE, 0); emeta.assign(pl.NE, 0);
+    enx.assign(pl.NE, 0.0); eny.assign(pl.NE, 0.0); eoohk.assign(pl.NE, 0.0); eooLen.assign(pl.NE, 0.0);
+    pl.edgeGlobal.assign(pl.NE, 0);
+    std::unordered_map<int64_t, int64_t> bpOfEdge;
+    for (int64_t b = 0; b < p->NBP; b++) bpOfEdge.emplace(p->bp_edge[b], b);
+    auto &bpx = pl.bpx; auto &bpy = pl.bpy;
+    int nbp = 0;
+    const double np12 = (double)((N + 1) * (N + 1));
+    for (int s = 0; s < pl.NE; s++) {
+        const int64_t e = led[s].ge;
+        pl.edgeGlobal[s] = e;
+        if (pl.nParts == 1) slotOfEdgeDense[e] = s; else slotOfGlobalEdge.emplace(e, s);
+        const int64_t kl = p->edge_kL[e];
+        const int numL = p->edge_numL[e], numR = p->edge_numR[e];
+        ekL[s] = led[s].l;
+        emeta[s] = (numL & 3) | ((numR & 3) << 2) | ((p->edge_bc[e] & 15) << 4);
+        enx[s] = p->FaceNormX[kl + p->K * numL];
+        eny[s] = p->FaceNormY[kl + p->K * numL];
+        const double hK = p->EdgeLenMax[kl] / np12;          // DFR.GetHk (dfr_startup.go:89-98)
+        eoohk[s] = 1.0 / hK;
+        eooLen[s] = 1.0 / p->edge_len[e];
+        if (led[s].r >= 0) {
+            ekR[s] = led[s].r;
+        } else {
+            auto it = bpOfEdge.find(e);
+            if (it == bpOfEdge.end()) {
+                pl.err = "boundary edge without edge-point coordinates (bp_edge)";
+                return 3;
+            }
+            ekR[s] = -1 - nbp;
+            for (int i = 0; i < NEd; i++) {
+                bpx.push_back(p->bp_x[it->second * NEd + i]);
+                bpy.push_back(p->bp_y[it->second * NEd + i]);
+            }
+            nbp++;
+        }
+    }
+    pl.NBP = nbp;
+    auto slot_of = [&](int64_t e) -> int {
+        return pl.nParts == 1 ? slotOfEdgeDense[e] : slotOfGlobalEdge.at(e);
+    };
+
+    // element arrays (SoA, stride Kp)
+    auto &Jdet = pl.Jdet; auto &Jinv = pl.Jinv; auto &IInII = pl.IInII; auto &etoe = pl.etoe;
+    Jdet.assign((size_t)Kp, 1.0); Jinv.assign((size_t)4 * Kp, 0.0); IInII.assign((size_t)3 * Kp, 0.0);
+    etoe.assign((size_t)3 * Kp, 0);
+    for (int k = 0; k < K; k++) {
+        const int64_t kg = k0 + k;
+        Jdet[k] = p->Jdet[kg];
+        for (int c = 0; c < 4; c++) Jinv[(size_t)c * Kp + k] = p->Jinv[kg * 4 + c];
+        for (int le = 0; le < 3; le++) {
+            IInII[(size_t)le * Kp + k] = p->IInII[kg + p->K * le];
+            const int64_t e = p->EtoEdge[kg * 3 + le];
+            const int s = slot_of(e);
+            etoe[(size_t)le * Kp + k] = (p->edge_kL[e] == kg) ? s : -1 - s;
+        }
+    }
+
+    // ---- halo lists: for every cut edge the 4 x NpEdge Q_Face values of each side cross once per stage
+    pl.sendCounts.assign(pl.nParts, 0);
+    pl.recvCounts.assign(pl.nParts, 0);
+    auto &sendElem = pl.sendElem; auto &sendRow0 = pl.sendRow0; auto &recvCol = pl.recvCol; auto &recvRow0 = pl.recvRow0;
+    if (pl.nParts > 1) {
+        struct Cut { int peer; int64_t ge; int myCol, myNum, ghCol, ghNum; };
+        std::vector<Cut> cuts;
+        for (int s = 0; s < pl.NE; s++) {
+            const int64_t e = led[s].ge;
+            if (p->edge_nconn[e] != 2) continue;
+            const int64_t kl = p->edge_kL[e], kr = p->edge_kR[e];
+            if (mine(kl) && mine(kr)) continue;
+            const bool lMine = mine(kl);
+            const int64_t remote = lMine ? kr : kl;
+            Cut c;
+            c.peer = bucket_of(remote, p->K, pl.nParts);
+            c.ge = e;
+            c.myCol = lMine ? led[s].l : led[s].r;
+            c.myNum = lMine ? p->edge_numL[e] : p->edge_numR[e];
+            c.ghCol = lMine ? led[s].r : led[s].l;
+            c.ghNum = lMine ? p->edge_numR[e] : p->edge_numL[e];
+            cuts.push_back(c);
+        }
+        std::stable_sort(cuts.begin(), cuts.end(), [](const Cut &a, const Cut &b) {
+            return a.peer != b.peer ? a.peer < b.peer : a.ge < b.ge;
+        });
+        const int64_t per = 4 * NEd;
+        for (auto &c : cuts) {
+            pl.sendCounts[c.peer] += per;
+            pl.recvCounts[c.peer] += per;
+            sendElem.push_back(c.myCol);
+            sendRow0.push_back(c.myNum * NEd);
+            recvCol.push_back(c.ghCol);
+            recvRow0.push_back(c.ghNum * NEd);
+        }
+        pl.nSendEdges = pl.nRecvEdges = (int)cuts.size();
+        pl.sendTotal = pl.recvTotal = per * (int64_t)cuts.size();
+    }
+
+    return 0;
+}
+
 static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     const int N = p->N;
     h->NpInt = (N + 1) * (N + 2) / 2;
@@ -174,145 +341,21 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     ph.N = N;
     ph.maxIter = p->max_iterations;
 
-    // ---- partition (utils.PartitionMap, parallelism.go:179-190) ------------------------------
-    h->Kglobal = p->K;
-    split1d(p->K, h->nParts, h->part, &h->k0, &h->k1);
-    const int64_t k0 = h->k0, k1 = h->k1;
-    h->K = (int)(k1 - k0);
-    auto mine = [&](int64_t k) { return k >= k0 && k < k1; };
-
-    // local edges = every edge touching an owned element; remote sides become ghost columns
-    struct LE { int64_t ge; int l, r; };
-    std::vector<LE> led;
-    led.reserve((size_t)(h->nParts == 1 ? p->NE : 2 * (p->NE / h->nParts) + 1024));
-    std::unordered_map<int64_t, int> ghostOf;
-    std::vector<int64_t> ghostGlobal;
-    auto local_col = [&](int64_t kg) -> int {
-        if (mine(kg)) return (int)(kg - k0);
-        auto it = ghostOf.find(kg);
-        if (it != ghostOf.end()) return h->K + it->second;
-        int g = (int)ghostGlobal.size();
-        ghostOf.emplace(kg, g);
-        ghostGlobal.push_back(kg);
-        return h->K + g;
-    };
-    for (int64_t e = 0; e < p->NE; e++) {
-        const int64_t kl = p->edge_kL[e], kr = (p->edge_nconn[e] == 2) ? p->edge_kR[e] : -1;
-        if (!(mine(kl) || (kr >= 0 && mine(kr)))) continue;
-        led.push_back({e, 0, 0});
-    }
-    // ghosts are numbered in global-edge order so that both sides of a cut agree on the message order
-    for (auto &le : led) {
-        const int64_t e = le.ge;
-        le.l = local_col(p->edge_kL[e]);
-        le.r = (p->edge_nconn[e] == 2) ? local_col(p->edge_kR[e]) : -1;
-    }
-    h->G = (int)ghostGlobal.size();
-    h->Kp = ((h->K + h->G + 31) / 32) * 32;
-    // sort by the owner-side column so that owner-side loads of neighbouring threads coalesce
-    std::stable_sort(led.begin(), led.end(), [](const LE &a, const LE &b) { return a.l < b.l; });
-    h->NE = (int)led.size();
-    h->NEp = ((h->NE + 31) / 32) * 32;
-    h->NV = (int)p->NV;
+    // ---- partition plan (host only) -------------------------------------------------------------
+    dfr2d_plan pl;
+    pl.nParts = h->nParts; pl.part = h->part;
+    if (int rc = build_plan(p, pl)) { h->err = pl.err; return rc; }
+    h->Kglobal = pl.Kglobal; h->k0 = pl.k0; h->k1 = pl.k1;
+    h->K = pl.K; h->G = pl.G; h->Kp = pl.Kp; h->NE = pl.NE; h->NEp = pl.NEp; h->NV = pl.NV; h->NBP = pl.NBP;
+    h->sendCounts = pl.sendCounts; h->recvCounts = pl.recvCounts;
+    h->nSendEdges = pl.nSendEdges; h->nRecvEdges = pl.nRecvEdges; h->sendTotal = pl.sendTotal; h->recvTotal = pl.recvTotal;
     const int Kp = h->Kp, K = h->K;
-
-    std::unordered_map<int64_t, int> slotOfGlobalEdge;
-    if (h->nParts > 1) slotOfGlobalEdge.reserve(led.size() * 2);
-    std::vector<int> slotOfEdgeDense;
-    if (h->nParts == 1) slotOfEdgeDense.assign((size_t)p->NE, -1);
-    std::vector<int> ekL(h->NE), ekR(h->NE), emeta(h->NE);
-    std::vector<double> enx(h->NE), eny(h->NE), eoohk(h->NE), eooLen(h->NE);
-    std::unordered_map<int64_t, int64_t> bpOfEdge;
-    for (int64_t b = 0; b < p->NBP; b++) bpOfEdge.emplace(p->bp_edge[b], b);
-    std::vector<double> bpx, bpy;
-    int nbp = 0;
+    const int64_t k0 = h->k0;
     const double np12 = (double)((N + 1) * (N + 1));
-    for (int s = 0; s < h->NE; s++) {
-        const int64_t e = led[s].ge;
-        if (h->nParts == 1) slotOfEdgeDense[e] = s; else slotOfGlobalEdge.emplace(e, s);
-        const int64_t kl = p->edge_kL[e];
-        const int numL = p->edge_numL[e], numR = p->edge_numR[e];
-        ekL[s] = led[s].l;
-        emeta[s] = (numL & 3) | ((numR & 3) << 2) | ((p->edge_bc[e] & 15) << 4);
-        enx[s] = p->FaceNormX[kl + p->K * numL];
-        eny[s] = p->FaceNormY[kl + p->K * numL];
-        const double hK = p->EdgeLenMax[kl] / np12;          // DFR.GetHk (dfr_startup.go:89-98)
-        eoohk[s] = 1.0 / hK;
-        eooLen[s] = 1.0 / p->edge_len[e];
-        if (led[s].r >= 0) {
-            ekR[s] = led[s].r;
-        } else {
-            auto it = bpOfEdge.find(e);
-            if (it == bpOfEdge.end()) {
-                h->err = "boundary edge without edge-point coordinates (bp_edge)";
-                return 3;
-            }
-            ekR[s] = -1 - nbp;
-            for (int i = 0; i < NEd; i++) {
-                bpx.push_back(p->bp_x[it->second * NEd + i]);
-                bpy.push_back(p->bp_y[it->second * NEd + i]);
-            }
-            nbp++;
-        }
-    }
-    h->NBP = nbp;
-    auto slot_of = [&](int64_t e) -> int {
-        return h->nParts == 1 ? slotOfEdgeDense[e] : slotOfGlobalEdge.at(e);
-    };
-
-    // element arrays (SoA, stride Kp)
-    std::vector<double> Jdet((size_t)Kp, 1.0), Jinv((size_t)4 * Kp, 0.0), IInII((size_t)3 * Kp, 0.0);
-    std::vector<int> etoe((size_t)3 * Kp, 0);
-    for (int k = 0; k < K; k++) {
-        const int64_t kg = k0 + k;
-        Jdet[k] = p->Jdet[kg];
-        for (int c = 0; c < 4; c++) Jinv[(size_t)c * Kp + k] = p->Jinv[kg * 4 + c];
-        for (int le = 0; le < 3; le++) {
-            IInII[(size_t)le * Kp + k] = p->IInII[kg + p->K * le];
-            const int64_t e = p->EtoEdge[kg * 3 + le];
-            const int s = slot_of(e);
-            etoe[(size_t)le * Kp + k] = (p->edge_kL[e] == kg) ? s : -1 - s;
-        }
-    }
-
-    // ---- halo lists: for every cut edge the 4 x NpEdge Q_Face values of each side cross once per stage
-    h->sendCounts.assign(h->nParts, 0);
-    h->recvCounts.assign(h->nParts, 0);
-    std::vector<int> sendElem, sendRow0, recvCol, recvRow0;
-    if (h->nParts > 1) {
-        struct Cut { int peer; int64_t ge; int myCol, myNum, ghCol, ghNum; };
-        std::vector<Cut> cuts;
-        for (int s = 0; s < h->NE; s++) {
-            const int64_t e = led[s].ge;
-            if (p->edge_nconn[e] != 2) continue;
-            const int64_t kl = p->edge_kL[e], kr = p->edge_kR[e];
-            if (mine(kl) && mine(kr)) continue;
-            const bool lMine = mine(kl);
-            const int64_t remote = lMine ? kr : kl;
-            Cut c;
-            c.peer = bucket_of(remote, p->K, h->nParts);
-            c.ge = e;
-            c.myCol = lMine ? led[s].l : led[s].r;
-            c.myNum = lMine ? p->edge_numL[e] : p->edge_numR[e];
-            c.ghCol = lMine ? led[s].r : led[s].l;
-            c.ghNum = lMine ? p->edge_numR[e] : p->edge_numL[e];
-            cuts.push_back(c);
-        }
-        std::stable_sort(cuts.begin(), cuts.end(), [](const Cut &a, const Cut &b) {
-            return a.peer != b.peer ? a.peer < b.peer : a.ge < b.ge;
-        });
-        const int64_t per = 4 * NEd;
-        for (auto &c : cuts) {
-            h->sendCounts[c.peer] += per;
-            h->recvCounts[c.peer] += per;
-            sendElem.push_back(c.myCol);
-            sendRow0.push_back(c.myNum * NEd);
-            recvCol.push_back(c.ghCol);
-            recvRow0.push_back(c.ghNum * NEd);
-        }
-        h->nSendEdges = h->nRecvEdges = (int)cuts.size();
-        h->sendTotal = h->recvTotal = per * (int64_t)cuts.size();
-    }
+    auto &ekL = pl.ekL; auto &ekR = pl.ekR; auto &emeta = pl.emeta; auto &etoe = pl.etoe;
+    auto &enx = pl.enx; auto &eny = pl.eny; auto &eoohk = pl.eoohk; auto &eooLen = pl.eooLen;
+    auto &bpx = pl.bpx; auto &bpy = pl.bpy; auto &Jdet = pl.Jdet; auto &Jinv = pl.Jinv; auto &IInII = pl.IInII;
+    auto &sendElem = pl.sendElem; auto &sendRow0 = pl.sendRow0; auto &recvCol = pl.recvCol; auto &recvRow0 = pl.recvRow0;
 
     // ---- device memory -------------------------------------------------------------------------
     const size_t reg = (size_t)4 * NI * Kp;
@@ -768,3 +811,48 @@ extern "C" int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **p) {
     return 0;
 }
 extern "C" int64_t dfr2d_launch_count(const dfr2d_handle *h) { return h ? h->launches : 0; }
+
+// ---- host-only plan API (CPU tests of the multi-partition bookkeeping) ---------------------------------------
+extern "C" int dfr2d_plan_create(const dfr2d_problem *p, int n_parts, int part, dfr2d_plan **out) {
+    if (!p || !out || n_parts < 1 || part < 0 || part >= n_parts || p->K < n_parts) { g_create_error = "bad plan request"; return 1; }
+    dfr2d_plan *pl = new dfr2d_plan();
+    pl->nParts = n_parts; pl->part = part;
+    int rc = build_plan(p, *pl);
+    if (rc) { g_create_error = pl->err; delete pl; return rc; }
+    *out = pl;
+    return 0;
+}
+extern "C" void dfr2d_plan_destroy(dfr2d_plan *pl) { delete pl; }
+extern "C" int dfr2d_plan_sizes(const dfr2d_plan *pl, int64_t out[8]) {
+    if (!pl || !out) return 1;
+    out[0] = pl->k0; out[1] = pl->k1; out[2] = pl->G; out[3] = pl->Kp; out[4] = pl->NE; out[5] = pl->NEp;
+    out[6] = pl->nSendEdges; out[7] = pl->NBP;
+    return 0;
+}
+extern "C" int dfr2d_plan_edges(const dfr2d_plan *pl, int32_t *kL, int32_t *kR, int32_t *meta, int64_t *global_edge, int32_t *etoe) {
+    if (!pl) return 1;
+    for (int s = 0; s < pl->NE; s++) {
+        if (kL) kL[s] = pl->ekL[s];
+        if (kR) kR[s] = pl->ekR[s];
+        if (meta) meta[s] = pl->emeta[s];
+        if (global_edge) global_edge[s] = pl->edgeGlobal[s];
+    }
+    if (etoe) memcpy(etoe, pl->etoe.data(), pl->etoe.size() * sizeof(int));
+    return 0;
+}
+extern "C" int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64_t *recv_counts, int64_t *ghost_global,
+                               int32_t *send_elem, int32_t *send_row0, int32_t *recv_col, int32_t *recv_row0) {
+    if (!pl) return 1;
+    for (int i = 0; i < pl->nParts; i++) {
+        if (send_counts) send_counts[i] = pl->sendCounts[i];
+        if (recv_counts) recv_counts[i] = pl->recvCounts[i];
+    }
+    for (int g = 0; g < pl->G; g++) if (ghost_global) ghost_global[g] = pl->ghostGlobal[g];
+    for (int c = 0; c < pl->nSendEdges; c++) {
+        if (send_elem) send_elem[c] = pl->sendElem[c];
+        if (send_row0) send_row0[c] = pl->sendRow0[c];
+        if (recv_col) recv_col[c] = pl->recvCol[c];
+        if (recv_row0) recv_row0[c] = pl->recvRow0[c];
+    }
+    return 0;
+}

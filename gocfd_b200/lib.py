@@ -51,6 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count",
+    "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
 _lib = None
@@ -89,6 +90,13 @@ def load():
     lib.dfr2d_step_finish.argtypes = [H, C.POINTER(StepInfo)]
     lib.dfr2d_launch_count.argtypes = [H]
     lib.dfr2d_launch_count.restype = C.c_int64
+    lp = C.POINTER(C.c_int64)
+    lib.dfr2d_plan_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.c_int, C.POINTER(H)]
+    lib.dfr2d_plan_destroy.argtypes = [H]
+    lib.dfr2d_plan_destroy.restype = None
+    lib.dfr2d_plan_sizes.argtypes = [H, lp]
+    lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
+    lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
     _lib = lib
     return lib
 
@@ -252,3 +260,45 @@ class Dfr2d:
 
     def launch_count(self):
         return int(self.lib.dfr2d_launch_count(self.h))
+
+
+class Plan:
+    """Host-only partition plan of one (n_parts, part): integer tables only, no CUDA needed."""
+
+    def __init__(self, problem, n_parts, part):
+        lib = load()
+        s, keep = problem_struct(problem)
+        h = C.c_void_p()
+        rc = lib.dfr2d_plan_create(C.byref(s), n_parts, part, C.byref(h))
+        del keep
+        if rc != 0:
+            raise Dfr2dError("dfr2d_plan_create failed (%d): %s" % (rc, lib.dfr2d_last_error(None).decode()))
+        try:
+            sz = (C.c_int64 * 8)()
+            lib.dfr2d_plan_sizes(h, sz)
+            (self.k0, self.k1, self.G, self.Kp, self.NE, self.NEp, self.n_cut, self.NBP) = [int(x) for x in sz]
+            self.K = self.k1 - self.k0
+            self.kL = np.zeros(self.NE, np.int32)
+            self.kR = np.zeros(self.NE, np.int32)
+            self.meta = np.zeros(self.NE, np.int32)
+            self.global_edge = np.zeros(self.NE, np.int64)
+            self.etoe = np.zeros((3, self.Kp), np.int32)
+            lp = C.POINTER(C.c_int64)
+            lib.dfr2d_plan_edges(h, _i(self.kL), _i(self.kR), _i(self.meta), self.global_edge.ctypes.data_as(lp),
+                                 _i(self.etoe))
+            self.send_counts = np.zeros(n_parts, np.int64)
+            self.recv_counts = np.zeros(n_parts, np.int64)
+            self.ghost_global = np.zeros(max(self.G, 1), np.int64)
+            self.send_elem = np.zeros(max(self.n_cut, 1), np.int32)
+            self.send_row0 = np.zeros(max(self.n_cut, 1), np.int32)
+            self.recv_col = np.zeros(max(self.n_cut, 1), np.int32)
+            self.recv_row0 = np.zeros(max(self.n_cut, 1), np.int32)
+            lib.dfr2d_plan_halo(h, self.send_counts.ctypes.data_as(lp), self.recv_counts.ctypes.data_as(lp),
+                                self.ghost_global.ctypes.data_as(lp), _i(self.send_elem), _i(self.send_row0),
+                                _i(self.recv_col), _i(self.recv_row0))
+            for name in ("ghost_global",):
+                setattr(self, name, getattr(self, name)[:self.G])
+            for name in ("send_elem", "send_row0", "recv_col", "recv_row0"):
+                setattr(self, name, getattr(self, name)[:self.n_cut])
+        finally:
+            lib.dfr2d_plan_destroy(h)

@@ -159,6 +159,22 @@ int dfr2d_stage_edges(dfr2d_handle *h, int rk);   /* unpack halo + numerical edg
 int dfr2d_stage_update(dfr2d_handle *h, int rk);  /* divergence, dt, SSP-RK update (+ next stage's interpolation) */
 int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info); /* after stage 4: read back time/steps (info may be NULL) */
 
+/* ---- host-only partition plan (no CUDA): the bookkeeping dfr2d_create performs for (n_parts, part), exposed so
+ * the decomposition can be verified bit-exactly on a CPU-only machine.  Mirrors utils.PartitionMap +
+ * PartitionEdgesByK (parallelism.go:179-190) plus the ghost/halo lists that replace the goroutines' shared memory. */
+typedef struct dfr2d_plan dfr2d_plan;
+int dfr2d_plan_create(const dfr2d_problem *p, int n_parts, int part, dfr2d_plan **out);
+void dfr2d_plan_destroy(dfr2d_plan *pl);
+/* out = {k_begin, k_end, n_ghost_columns, padded_columns, n_local_edges, padded_edges, n_cut_edges, n_boundary_edges} */
+int dfr2d_plan_sizes(const dfr2d_plan *pl, int64_t out[8]);
+/* per local edge: owner / neighbour column (ghost columns >= k_end-k_begin; neighbour < 0 on boundaries), packed
+ * meta (numL | numR<<2 | bc<<4), global edge index; etoe = [3][padded_columns] edge slot (or -1-slot if not owner) */
+int dfr2d_plan_edges(const dfr2d_plan *pl, int32_t *kL, int32_t *kR, int32_t *meta, int64_t *global_edge, int32_t *etoe);
+/* per peer counts (doubles), global element id of every ghost column, and per cut edge the send (column,row0) and
+ * receive (ghost column,row0) addresses inside Q_Face; message order = (peer, global edge index) */
+int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64_t *recv_counts, int64_t *ghost_global,
+                    int32_t *send_elem, int32_t *send_row0, int32_t *recv_col, int32_t *recv_row0);
+
 /* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
 int64_t dfr2d_launch_count(const dfr2d_handle *h);
 

@@ -1,0 +1,137 @@
+"""CPU-only tests of the boundary: the C-ABI library loads and exports every symbol the header
+declares, and the multi-partition bookkeeping (partition ranges, local edge tables, ghost columns,
+halo message lists) is bit-exact against the reference's PartitionMap / edge ownership rules.
+No compute call is made here (there is no GPU in the CPU test environment)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, mesh_path
+from gocfd_b200.host.euler2d import Euler, PartitionMap
+from gocfd_b200.host.input_parameters import InputParameters2D
+from gocfd_b200.host.meshgen import structured_tri_mesh
+
+
+def _case(n, mesh, **kw):
+    base = dict(CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n, FinalTime=1.0, MaxIterations=10,
+                Gamma=1.4, Minf=0.1)
+    base.update(kw)
+    return Euler(InputParameters2D(**base), mesh)
+
+
+def test_library_exports_every_declared_symbol():
+    from gocfd_b200 import lib
+    header = open(os.path.join(ROOT, "include", "dfr2d.h")).read()
+    declared = set(re.findall(r"\b(dfr2d_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(lib.EXPORTS)
+    l = lib.load()
+    for name in declared:
+        assert hasattr(l, name), name
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, out), name
+    # no torch / C++ types leak through the boundary: every exported dfr2d_ symbol is unmangled C
+    assert not re.search(r"_Z\w*dfr2d_(create|step|set_state)", out)
+
+
+def test_create_rejects_bad_requests_without_touching_cuda():
+    from gocfd_b200 import lib
+    c = _case(2, structured_tri_mesh(4, 4))
+    with pytest.raises(lib.Dfr2dError):
+        lib.Dfr2d(c.problem, n_parts=2, part=2)
+    c.problem.N = 9
+    with pytest.raises(lib.Dfr2dError):
+        lib.Dfr2d(c.problem)
+
+
+@pytest.mark.parametrize("mesh_name,n_parts", [("grid", 2), ("grid", 3), ("grid", 8), ("naca", 2), ("naca", 5)])
+def test_partition_plan_tables(mesh_name, n_parts):
+    from gocfd_b200 import lib
+    mesh = structured_tri_mesh(12, 10) if mesh_name == "grid" else mesh_path("mesh_NACA0012_inv.su2")
+    c = _case(1, mesh, InitType="IVortex" if mesh_name == "grid" else "Freestream")
+    p = c.problem
+    pm = PartitionMap(n_parts, p.K)
+    plans = [lib.Plan(p, n_parts, r) for r in range(n_parts)]
+    ne = p.NpEdge
+    owned_edges = 0
+    for r, pl in enumerate(plans):
+        assert (pl.k0, pl.k1) == pm.get_bucket_range(r)             # Split1D ranges, bit-exact
+        mine = lambda k: pl.k0 <= k < pl.k1                         # noqa: E731
+        ge = pl.global_edge
+        # local edge set = every edge touching an owned element
+        want = [e for e in range(p.NE) if mine(p.edge_kL[e]) or (p.edge_nconn[e] == 2 and mine(p.edge_kR[e]))]
+        assert sorted(ge.tolist()) == want
+        col2glob = np.concatenate([np.arange(pl.k0, pl.k1), pl.ghost_global])
+        assert np.array_equal(col2glob[pl.kL], p.edge_kL[ge])
+        shared = p.edge_nconn[ge] == 2
+        assert np.array_equal(col2glob[pl.kR[shared]], p.edge_kR[ge][shared])
+        assert np.all(pl.kR[~shared] < 0)
+        assert np.array_equal(pl.meta & 3, p.edge_numL[ge])
+        assert np.array_equal((pl.meta >> 2) & 3, p.edge_numR[ge])
+        assert np.array_equal((pl.meta >> 4) & 15, p.edge_bc[ge])
+        # element -> edge slot with the owner bit (replaces both Go maps, edges.go:101-111)
+        for le in range(3):
+            s = pl.etoe[le, :pl.K]
+            slot = np.where(s >= 0, s, -1 - s)
+            gk = np.arange(pl.k0, pl.k1)
+            assert np.array_equal(ge[slot], p.EtoEdge[gk, le])
+            assert np.array_equal(s >= 0, p.edge_kL[p.EtoEdge[gk, le]] == gk)
+        owned_edges += int(np.sum([mine(k) for k in p.edge_kL[ge]]))
+    assert owned_edges == p.NE                                      # PartitionEdgesByK: every edge has one owner
+    # halo lists: what r sends to s is what s expects from r, edge by edge
+    rng = np.random.default_rng(0)
+    qface = rng.standard_normal((4, 3 * ne, p.K))                   # a global Q_Face
+    local = []
+    for pl in plans:
+        q = np.zeros((4, 3 * ne, pl.Kp))
+        q[:, :, :pl.K] = qface[:, :, pl.k0:pl.k1]
+        local.append(q)
+    per = 4 * ne
+    sent = {}
+    for r, pl in enumerate(plans):
+        buf = np.empty(pl.n_cut * per)
+        for ci in range(pl.n_cut):
+            rows = pl.send_row0[ci] + np.arange(ne)
+            buf[ci * per:(ci + 1) * per] = local[r][:, rows, pl.send_elem[ci]].reshape(-1)
+        off = np.concatenate([[0], np.cumsum(pl.send_counts)])
+        for s in range(n_parts):
+            sent[(r, s)] = buf[off[s]:off[s + 1]]
+        assert pl.send_counts[r] == 0
+    for s, pl in enumerate(plans):
+        assert [len(sent[(r, s)]) for r in range(n_parts)] == pl.recv_counts.tolist()
+        buf = np.concatenate([sent[(r, s)] for r in range(n_parts)])
+        for ci in range(pl.n_cut):
+            rows = pl.recv_row0[ci] + np.arange(ne)
+            local[s][:, rows, pl.recv_col[ci]] = buf[ci * per:(ci + 1) * per].reshape(4, ne)
+    # after the exchange every local edge sees exactly the global values on both sides
+    for r, pl in enumerate(plans):
+        ge = pl.global_edge
+        i = np.arange(ne)
+        rows_l = p.edge_numL[ge][:, None] * ne + i[None, :]
+        for nvar in range(4):
+            have = local[r][nvar][rows_l, pl.kL[:, None]]
+            want = qface[nvar][rows_l, p.edge_kL[ge][:, None]]
+            assert np.array_equal(have, want)
+        sh = np.flatnonzero(p.edge_nconn[ge] == 2)
+        rows_r = p.edge_numR[ge][sh][:, None] * ne + (ne - 1 - i)[None, :]
+        for nvar in range(4):
+            have = local[r][nvar][rows_r, pl.kR[sh][:, None]]
+            want = qface[nvar][rows_r, p.edge_kR[ge][sh][:, None]]
+            assert np.array_equal(have, want)
+
+
+def test_two_rank_gloo_exchange():
+    """world_size-2 gloo run of the host side of the multi-GPU step: plan, pack, all_to_all of the halo,
+    unpack, MAX-allreduce of the wave speed -- the same calls bench.py issues over NCCL."""
+    script = os.path.join(ROOT, "tests", "gloo_halo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2"], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [pr.communicate(timeout=300)[0] for pr in procs]
+    for pr, out in zip(procs, outs):
+        assert pr.returncode == 0, out
+        assert "OK" in out, out
