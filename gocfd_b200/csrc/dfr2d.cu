@@ -11,6 +11,8 @@
 
 #include "dfr2d_kernels.cuh"
 #include "dfr2d_diss_kernels.cuh"
+#include "dfr2d_elem_mma.cuh"
+#include "dfr2d_elem_pipe.cuh"
 
 using namespace dfr2d;
 
@@ -49,6 +51,11 @@ struct dfr2d_handle {
     bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
     int edgeBlocks = 0;
     bool smemAttrSet = false;
+    int pfTiles = 0;
+    int elemKernel = 4;               // 1: row-per-thread DFMA, 2: split-row DFMA, 3: DMMA, 4: pipelined DMMA (default)
+    double *mmaFrags = nullptr;
+    int sms = 148, mmaGrid = 148;
+    int pipeOcc[3] = {0, 0, 0};
 };
 
 #define CK(call)                                                                                        \
@@ -364,6 +371,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         CK(cudaMemset(h->q[r], 0, reg * sizeof(double)));
     }
     h->q[4] = h->q[1];
+    if (h->Kp > h->K)
+        for (int r = 0; r < 4; r++) k_fill_pad<<<64, 256>>>(h->q[r], NI, h->K, h->Kp);
     if (int rc = dev_alloc(h, &h->R, reg)) return rc;
     CK(cudaMemset(h->R, 0, reg * sizeof(double)));
     if (int rc = dev_alloc(h, &h->qface, (size_t)4 * 3 * NEd * Kp)) return rc;
@@ -444,6 +453,25 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     h->edgeBlocks = sms * 8;
+    h->pfTiles = 1;
+    if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
+    h->sms = sms;
+    // measured on B200 (profiles/r01c_*): the pipelined DMMA kernel wins at N >= 3, the row-per-thread DFMA kernel
+    // at N <= 2 (small operators: DMMA padding waste, fewer tiles per persistent CTA)
+    h->elemKernel = (N >= 3) ? 4 : 1;
+    if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
+    {
+        std::vector<double> fr;
+        switch (N) {
+            case 0: build_mma_frags<0>(p->DivInt, p->FluxEdgeInterp, fr); break;
+            case 1: build_mma_frags<1>(p->DivInt, p->FluxEdgeInterp, fr); break;
+            case 2: build_mma_frags<2>(p->DivInt, p->FluxEdgeInterp, fr); break;
+            case 3: build_mma_frags<3>(p->DivInt, p->FluxEdgeInterp, fr); break;
+            default: build_mma_frags<4>(p->DivInt, p->FluxEdgeInterp, fr); break;
+        }
+        if (int rc = dev_upload(h, &h->mmaFrags, fr)) return rc;
+    }
+    if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
     CK(cudaDeviceSynchronize());
     return 0;
 }
@@ -569,6 +597,7 @@ template <int N> static size_t elem_smem() { return (size_t)12 * Dim<N>::NpInt *
 static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     ElemArgs a{};
     a.K = h->K; a.Kp = h->Kp; a.NEp = h->NEp;
+    a.pfTiles = 0;
     a.qs = h->q[rk];
     a.q0 = h->q[0]; a.q1 = h->q[1]; a.q2 = h->q[2]; a.q3 = h->q[3]; a.q4 = h->q[4]; a.R = h->R;
     a.qface = fuseInterp ? h->qface : nullptr;
@@ -589,13 +618,72 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     if (h->ph.dissipation) {
         DISPATCH_N(h->N, {
             const size_t sm = elem_smem_diss<NN>();
-            if (!h->smemAttrSet) cudaFuncSetAttribute(k_elem<NN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (!h->smemAttrSet) {
+                cudaFuncSetAttribute(k_elem<NN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaFuncSetAttribute(k_elem<NN, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
             k_elem<NN, true><<<blocks, kElemThreads, sm, h->stream>>>(a);
         });
     } else {
+        if (h->elemKernel == 4) {
+            ElemMmaArgs ma{};
+            ma.a = a;
+            ma.frags = h->mmaFrags;
+            ma.nTiles = blocks;
+            const int nExtra = (rk == 0) ? 0 : (rk == 4 ? 4 : 1);
+            DISPATCH_N(h->N, {
+                if (!h->smemAttrSet) {
+                    cudaFuncSetAttribute(k_elem_pipe<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PipeDim<NN>::smem_bytes(4));
+                    cudaFuncSetAttribute(k_elem_pipe<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                }
+                const int oi = (nExtra == 0) ? 0 : (nExtra == 1 ? 1 : 2);
+                if (h->pipeOcc[oi] == 0) {
+                    int occ = 1;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_pipe<NN>, kPipeThreads, PipeDim<NN>::smem_bytes(nExtra));
+                    h->pipeOcc[oi] = std::max(occ, 1);
+                }
+                k_elem_pipe<NN><<<std::min(blocks, h->sms * h->pipeOcc[oi]), kPipeThreads, PipeDim<NN>::smem_bytes(nExtra), h->stream>>>(ma);
+            });
+            h->smemAttrSet = true;
+            return launch_check(h, "k_elem_pipe");
+        }
+        if (h->elemKernel == 3) {
+            ElemMmaArgs ma{};
+            ma.a = a;
+            ma.frags = h->mmaFrags;
+            ma.nTiles = blocks;
+            DISPATCH_N(h->N, {
+                const size_t sm = MmaDim<NN>::kSmemBytes;
+                if (!h->smemAttrSet) {
+                    cudaFuncSetAttribute(k_elem_mma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    cudaFuncSetAttribute(k_elem_mma<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                    int occ = 1;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_mma<NN>, kElemThreads, sm);
+                    h->mmaGrid = h->sms * std::max(occ, 1);
+                }
+                k_elem_mma<NN><<<std::min(blocks, h->mmaGrid), kElemThreads, sm, h->stream>>>(ma);
+            });
+            h->smemAttrSet = true;
+            return launch_check(h, "k_elem_mma");
+        }
+        if (h->elemKernel == 2) {
+            DISPATCH_N(h->N, {
+                const size_t sm = (size_t)4 * (Dim<NN>::NpInt + Dim<NN>::NpFlux) * kElemsPerBlock * sizeof(double);
+                if (!h->smemAttrSet) {
+                    cudaFuncSetAttribute(k_elem2<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                    cudaFuncSetAttribute(k_elem2<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                }
+                k_elem2<NN><<<blocks, kElem2Threads, sm, h->stream>>>(a);
+            });
+            h->smemAttrSet = true;
+            return launch_check(h, "k_elem2");
+        }
         DISPATCH_N(h->N, {
             const size_t sm = elem_smem<NN>();
-            if (!h->smemAttrSet) cudaFuncSetAttribute(k_elem<NN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+            if (!h->smemAttrSet) {
+                cudaFuncSetAttribute(k_elem<NN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaFuncSetAttribute(k_elem<NN, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
             k_elem<NN, false><<<blocks, kElemThreads, sm, h->stream>>>(a);
         });
     }
@@ -856,3 +944,11 @@ extern "C" int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64
     }
     return 0;
 }
+
+#ifdef DFR2D_PIPE_TIMING
+extern "C" int dfr2d_debug_pipe_clocks(unsigned long long out[8], int reset) {
+    cudaMemcpyFromSymbol(out, g_pipe_clk, 8 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_pipe_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -59,9 +59,54 @@ struct DevScalars {
     int nanFlag;
 };
 
+// ---- fast reciprocal / square root ----------------------------------------------------------------
+// IEEE double division and sqrt expand to ~15-25 instructions with a slow-path call each; the Riemann
+// solver needs ~13 divisions and 5 roots per edge point, which made k_edge issue-bound (ncu, profiles/
+// r01a).  These use the hardware approximations (rcp/rsqrt.approx.ftz.f64, ~2^-22) plus two Newton steps:
+// <= ~2 ulp, far inside the 1e-11 parity bar.  Only for arguments that are positive and normal in any
+// valid flow state (density, sound speed squared, ...).  -DDFR2D_EXACT_DIV restores IEEE operations.
+__device__ __forceinline__ double rcp_fast(double x) {
+#ifdef DFR2D_EXACT_DIV
+    return 1.0 / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#endif
+}
+
+// s = sqrt(x), rs = 1/sqrt(x) for x > 0
+__device__ __forceinline__ void sqrt_rsqrt_fast(double x, double &s, double &rs) {
+#ifdef DFR2D_EXACT_DIV
+    s = sqrt(x);
+    rs = 1.0 / s;
+#else
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double h = 0.5 * x;
+    r = r * fma(-h * r, r, 1.5);
+    r = r * fma(-h * r, r, 1.5);
+    double t = x * r;
+    t = fma(0.5 * r, fma(-t, t, x), t);
+    s = t;
+    rs = r;
+#endif
+}
+
+// sqrt(x) for x >= 0 where x may be exactly 0 (fluid at rest): guarded
+__device__ __forceinline__ double sqrt_nonneg(double x) {
+    if (!(x > 1e-280)) return sqrt(x);
+    double s, rs;
+    sqrt_rsqrt_fast(x, s, rs);
+    return s;
+}
+
 // ---- fluids.go:289-336 GetFlowFunctionBase ---------------------------------------------------
 __device__ __forceinline__ double static_pressure(double gamma, double rho, double rhoU, double rhoV, double E) {
-    double oorho = 1.0 / rho;
+    double oorho = rcp_fast(rho);
     double u = rhoU * oorho, v = rhoV * oorho;
     double U2 = u * u + v * v;
     double q = 0.5 * rho * U2;
@@ -70,51 +115,61 @@ __device__ __forceinline__ double static_pressure(double gamma, double rho, doub
 
 // (|u| + c) of a conserved state: Velocity + SoundSpeed, both as GetFlowFunctionBase computes them
 __device__ __forceinline__ double speed_plus_sound(double gamma, double rho, double rhoU, double rhoV, double E) {
-    double oorho = 1.0 / rho;
+    double oorho = rcp_fast(rho);
     double u = rhoU * oorho, v = rhoV * oorho;
     double U2 = u * u + v * v;
     double q = 0.5 * rho * U2;
     double p = (gamma - 1.0) * (E - q);
-    double C = sqrt(fabs(gamma * p * oorho));
-    return sqrt(U2) + C;
+    double C = sqrt_nonneg(fabs(gamma * p * oorho));
+    return sqrt_nonneg(U2) + C;
 }
 
 // ---- fluxes.go:76-87 FluxCalcBase --------------------------------------------------------------
 __device__ __forceinline__ void flux_calc(double gamma, const double Q[4], double Fx[4], double Fy[4]) {
     double rho = Q[0], rhoU = Q[1], rhoV = Q[2], E = Q[3];
-    double oorho = 1.0 / rho;
+    double oorho = rcp_fast(rho);
     double u = rhoU * oorho;
     double v = rhoV * oorho;
-    double p = static_pressure(gamma, rho, rhoU, rhoV, E);
+    double p = (gamma - 1.0) * (E - 0.5 * rho * (u * u + v * v));     // StaticPressure
     Fx[0] = rhoU; Fx[1] = rhoU * u + p; Fx[2] = rhoU * v; Fx[3] = u * (E + p);
     Fy[0] = rhoV; Fy[1] = rhoV * u; Fy[2] = rhoV * v + p; Fy[3] = v * (E + p);
 }
 
 // ---- fluxes.go:284-413 RoeFlux -----------------------------------------------------------------
+// Same formulas; divisions by a common denominator share one reciprocal (1/rho from rsqrt(rho)^2, 1/C and
+// 1/c2 from rsqrt(c2)).  wL returns (|u|+c) of the L state for StoreEdgeAggregates.
 __device__ __forceinline__ void roe_flux(double gamma, const double QL[4], const double QR[4], double nx, double ny,
-                                         double F[4]) {
+                                         double F[4], double &wL) {
     const double GM1 = gamma - 1.0;
     double rhoULr = QL[1] * nx + QL[2] * ny;
     double rhoVLr = QL[1] * (-ny) + QL[2] * nx;
     double rhoURr = QR[1] * nx + QR[2] * ny;
     double rhoVRr = QR[1] * (-ny) + QR[2] * nx;
-    double rhoL = QL[0], uL = rhoULr / QL[0], vL = rhoVLr / QL[0];
-    double rhoR = QR[0], uR = rhoURr / QR[0], vR = rhoVRr / QR[0];
-    double pL = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
-    double pR = static_pressure(gamma, QR[0], QR[1], QR[2], QR[3]);
-    double hL = (QL[3] + pL) / rhoL, hR = (QR[3] + pR) / rhoR;
-    double rhoLs = sqrt(rhoL), rhoRs = sqrt(rhoR);
-    double rhoLsRs = rhoLs + rhoRs;
+    double rhoL = QL[0], rhoR = QR[0];
+    double rhoLs, rhoRs, orLs, orRs;
+    sqrt_rsqrt_fast(rhoL, rhoLs, orLs);
+    sqrt_rsqrt_fast(rhoR, rhoRs, orRs);
+    const double oorL = orLs * orLs, oorR = orRs * orRs;
+    double uL = rhoULr * oorL, vL = rhoVLr * oorL;
+    double uR = rhoURr * oorR, vR = rhoVRr * oorR;
+    // pressure from the rotated velocities (rotation preserves u^2+v^2)
+    const double U2L = uL * uL + vL * vL, U2R = uR * uR + vR * vR;
+    double pL = GM1 * (QL[3] - 0.5 * rhoL * U2L);
+    double pR = GM1 * (QR[3] - 0.5 * rhoR * U2R);
+    double hL = (QL[3] + pL) * oorL, hR = (QR[3] + pR) * oorR;
+    const double oo = rcp_fast(rhoLs + rhoRs);
     double rho = rhoLs * rhoRs;
-    double u = (rhoLs * uL + rhoRs * uR) / rhoLsRs;
-    double v = (rhoLs * vL + rhoRs * vR) / rhoLsRs;
-    double h = (rhoLs * hL + rhoRs * hR) / rhoLsRs;
+    double u = (rhoLs * uL + rhoRs * uR) * oo;
+    double v = (rhoLs * vL + rhoRs * vR) * oo;
+    double h = (rhoLs * hL + rhoRs * hR) * oo;
     double c2 = GM1 * (h - 0.5 * (u * u + v * v));
-    double C = sqrt(c2);
-    double dW1 = -0.5 * (rho * (uR - uL)) / C + 0.5 * (pR - pL) / c2;
-    double dW2 = (rhoR - rhoL) - (pR - pL) / c2;
+    double C, ooC;
+    sqrt_rsqrt_fast(c2, C, ooC);
+    const double ooc2 = ooC * ooC;
+    double dW1 = -0.5 * (rho * (uR - uL)) * ooC + 0.5 * (pR - pL) * ooc2;
+    double dW2 = (rhoR - rhoL) - (pR - pL) * ooc2;
     double dW3 = rho * (vR - vL);
-    double dW4 = 0.5 * (rho * (uR - uL)) / C + 0.5 * (pR - pL) / c2;
+    double dW4 = 0.5 * (rho * (uR - uL)) * ooC + 0.5 * (pR - pL) * ooc2;
     dW1 = fabs(u - C) * dW1;
     dW2 = fabs(u) * dW2;
     dW3 = fabs(u) * dW3;
@@ -131,6 +186,7 @@ __device__ __forceinline__ void roe_flux(double gamma, const double QL[4], const
     F[1] = nx * f1 - ny * f2;     // rotate back to Cartesian
     F[2] = ny * f1 + nx * f2;
     F[3] = f3;
+    wL = sqrt_nonneg(U2L) + sqrt_nonneg(fabs(gamma * pL * oorL));
 }
 
 // ---- fluxes.go:161-190 LaxFlux -----------------------------------------------------------------
@@ -139,13 +195,14 @@ __device__ __forceinline__ void lax_flux(double gamma, const double QL[4], const
     double rhoL = QL[0], rhoR = QR[0];
     double rhoUL = QL[1], rhoVL = QL[2], rhoUR = QR[1], rhoVR = QR[2];
     double EL = QL[3], ER = QR[3];
-    double uL = rhoUL / rhoL, vL = rhoVL / rhoL;
-    double uR = rhoUR / rhoR, vR = rhoVR / rhoR;
-    double pL = static_pressure(gamma, QL[0], QL[1], QL[2], QL[3]);
-    double pR = static_pressure(gamma, QR[0], QR[1], QR[2], QR[3]);
-    double CL = sqrt(fabs(gamma * pL * (1.0 / rhoL)));
-    double CR = sqrt(fabs(gamma * pR * (1.0 / rhoR)));
-    double maxV = fmax(sqrt(uL * uL + vL * vL) + CL, sqrt(uR * uR + vR * vR) + CR);
+    const double oorL = rcp_fast(rhoL), oorR = rcp_fast(rhoR);
+    double uL = rhoUL * oorL, vL = rhoVL * oorL;
+    double uR = rhoUR * oorR, vR = rhoVR * oorR;
+    double pL = (gamma - 1.0) * (EL - 0.5 * rhoL * (uL * uL + vL * vL));
+    double pR = (gamma - 1.0) * (ER - 0.5 * rhoR * (uR * uR + vR * vR));
+    double CL = sqrt_nonneg(fabs(gamma * pL * oorL));
+    double CR = sqrt_nonneg(fabs(gamma * pR * oorR));
+    double maxV = fmax(sqrt_nonneg(uL * uL + vL * vL) + CL, sqrt_nonneg(uR * uR + vR * vR) + CR);
     F[0] = 0.5 * (nx * (rhoUL + rhoUR) + ny * (rhoVL + rhoVR));
     F[1] = 0.5 * (nx * (rhoUL * uL + rhoUR * uR + pL + pR) + ny * (rhoUL * vL + rhoUR * vR));
     F[2] = 0.5 * (nx * (rhoVL * uL + rhoVR * uR) + ny * (rhoVL * vL + rhoVR * vR + pL + pR));

@@ -34,6 +34,17 @@ __global__ void k_halo_unpack(int total, int npEdge, int Kp, double *qface, cons
     qface[((size_t)n * 3 * npEdge + row0[c] + i) * Kp + col[c]] = buf[t];
 }
 
+// Columns [K, Kp) of a [4][npInt][Kp] register get a benign constant state (rho=1, E=2.5, no momentum) so that the
+// persistent element kernel can treat every 32-element tile as full; their metrics are zero, so they stay constant.
+__global__ void k_fill_pad(double *q, int npInt, int K, int Kp) {
+    const int pad = Kp - K;
+    const long long total = (long long)4 * npInt * pad;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(t / pad), c = (int)(t % pad), v = r / npInt;
+        q[(size_t)r * Kp + K + c] = (v == 0) ? 1.0 : (v == 3 ? 2.5 : 0.0);
+    }
+}
+
 // Matrix.Max of each Residual[n] (utils/matrix_extended.go:1085-1096): signed max, one CTA per variable
 __global__ void __launch_bounds__(1024) k_signed_max(const double *R, int npInt, int K, int Kp, double *out) {
     const int n = blockIdx.x;

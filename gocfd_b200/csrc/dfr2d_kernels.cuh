@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) k_edge(EdgeArgs a) {
 #pragma unroll
         for (int i = 0; i < NE_; i++) {
             double QL[4], F[4];
+            double wL = 0.0;
+            bool haveW = false;
             const size_t offL = (size_t)(numL * NE_ + i) * a.Kp + kL;
 #pragma unroll
             for (int n = 0; n < 4; n++) QL[n] = a.qface[n * qplane + offL];
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(256) k_edge(EdgeArgs a) {
                 switch (a.ph.fluxType) {
                     case DFR2D_FLUX_Average: avg_flux(gamma, QL, QR, nx, ny, F); break;
                     case DFR2D_FLUX_LaxFriedrichs: lax_flux(gamma, QL, QR, nx, ny, F); break;
-                    case DFR2D_FLUX_Roe: roe_flux(gamma, QL, QR, nx, ny, F); break;
+                    case DFR2D_FLUX_Roe: roe_flux(gamma, QL, QR, nx, ny, F, wL); haveW = true; break;
                     default: roe_er_flux(gamma, QL, QR, nx, ny, F); break;
                 }
             } else {
@@ -122,7 +124,8 @@ __global__ void __launch_bounds__(256) k_edge(EdgeArgs a) {
 #pragma unroll
             for (int n = 0; n < 4; n++) a.eflux[n * fplane + (size_t)i * a.NEp + e] = F[n];
             // StoreEdgeAggregates: owner side, post-BC state (edges.go:260-273)
-            double w = oohk * speed_plus_sound(gamma, QL[0], QL[1], QL[2], QL[3]);
+            if (!haveW) wL = speed_plus_sound(gamma, QL[0], QL[1], QL[2], QL[3]);
+            const double w = oohk * wL;
             if (w > wmax) wmax = w;
         }
         a.agg[e] = wmax;
@@ -167,8 +170,15 @@ __global__ void __launch_bounds__(kElemThreads) k_interp(int K, int Kp, const do
 
 template <int N> __device__ __forceinline__ void limit_filter_row(double (&u)[Dim<N>::NpInt], double sigmaK);
 
+// Bulk L2 prefetch of a contiguous byte range (sm_90+): decouples the HBM->L2 stream of a FUTURE tile from
+// the load phase of the CTA that will consume it (the kernel is bulk-synchronous with few resident warps).
+__device__ __forceinline__ void prefetch_l2(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 struct ElemArgs {
     int K, Kp, NEp;
+    int pfTiles;                            // prefetch distance in tiles (0 = off)
     const double *qs;                       // stage input register [4][NpInt][Kp]
     double *q0, *q1, *q2, *q3, *q4, *R;     // c.Q, Q1..Q4, Residual
     double *qface;                          // [4][3NpEdge][Kp], written for the next stage when non-null
@@ -213,6 +223,32 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
     const bool valid = k < a.K;
     const int kc = valid ? k : a.K - 1;   // clamp: out-of-range lanes compute on a valid element, store nothing
     const size_t Kp = a.Kp;
+
+    if (a.pfTiles > 0) {
+        // rows of the tile `pfTiles` ahead: stage input, the extra RK registers of this stage, geometry, and the
+        // edge-flux slots around the tile (edges are sorted by owner column: slot ~ 1.5 * column)
+        const long long kt = (long long)(blockIdx.x + a.pfTiles) * E;
+        if (kt + E <= a.K) {
+            constexpr unsigned RB = E * sizeof(double);
+            for (int r = threadIdx.x; r < 4 * NI; r += kElemThreads) {
+                prefetch_l2(a.qs + (size_t)r * Kp + kt, RB);
+                if (a.rk >= 1) prefetch_l2(a.q0 + (size_t)r * Kp + kt, RB);
+                if (a.rk == 4) {
+                    prefetch_l2(a.q2 + (size_t)r * Kp + kt, RB);
+                    prefetch_l2(a.q3 + (size_t)r * Kp + kt, RB);
+                    prefetch_l2(a.R + (size_t)r * Kp + kt, RB);
+                }
+            }
+            if (threadIdx.x < 4) prefetch_l2(a.Jinv + (size_t)threadIdx.x * Kp + kt, RB);
+            else if (threadIdx.x < 7) prefetch_l2(a.IInII + (size_t)(threadIdx.x - 4) * Kp + kt, RB);
+            else if (threadIdx.x < 10) prefetch_l2(a.etoe + (size_t)(threadIdx.x - 7) * Kp + kt, E * sizeof(int));
+            else if (threadIdx.x == 10) prefetch_l2(a.Jdet + kt, RB);
+            else if (threadIdx.x >= 32 && threadIdx.x < 32 + 4 * NEd) {
+                const long long s0 = ((kt * 3 / 2) / 16) * 16;
+                if (s0 + 64 <= a.NEp) prefetch_l2(a.eflux + (size_t)(threadIdx.x - 32) * a.NEp + s0, 64 * sizeof(double));
+            }
+        }
+    }
 
     double qs[NI];
 #pragma unroll
@@ -397,6 +433,184 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
             const long long st = a.sc->steps + 1;
             a.sc->steps = st;
             if (tnew >= a.ph.FinalTime || st >= (long long)a.ph.maxIter) a.sc->finished = 1;   // CheckIfFinished
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_elem2: the inviscid element kernel with each (element, variable) row split over two threads
+// (even / odd output nodes).  Same arithmetic as k_elem<N,false>; twice the resident warps at half
+// the registers, the gathered edge fluxes staged in shared memory, and the fresh register exchanged
+// through shared memory for the fused edge interpolation.  CTA = 32 elements x 4 variables x 2 halves
+// = 8 warps; warp w handles variable (w & 3), half (w >> 2) so the operator stays a warp-uniform
+// constant-bank operand.  ncu on the first version showed k_elem latency-bound at 12 warps/SM
+// (profiles/r01a_*): issue slots 41 %, FP64 pipe 31 %, DRAM 30 %.
+// ------------------------------------------------------------------------------------------------
+constexpr int kElem2Threads = 8 * kElemsPerBlock;
+
+template <int N, int HF>
+__device__ __forceinline__ void elem2_tail(const ElemArgs &a, double *sQ, const double *sF, int e, int n, int k, int kc,
+                                           bool valid, double jdet, double dtk) {
+    constexpr int NI = Dim<N>::NpInt, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3, E = kElemsPerBlock;
+    constexpr int NO = (NI - HF + 1) / 2;          // my output nodes i = HF + 2c
+    constexpr int NM = (NF3 - HF + 1) / 2;         // my Q_Face rows m = HF + 2c
+    const Ops<N> &op = ops<N>();
+    const size_t Kp = a.Kp;
+    double acc[NO > 0 ? NO : 1];
+#pragma unroll
+    for (int c = 0; c < NO; c++) acc[c] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NF; j++) {
+        const double f = sF[(n * NF + j) * E + e];
+#pragma unroll
+        for (int c = 0; c < NO; c++) acc[c] = fma(op.DivInt[HF + 2 * c][j], f, acc[c]);
+    }
+    const double moojd = -(1.0 / jdet);
+#pragma unroll
+    for (int c = 0; c < NO; c++) acc[c] *= moojd;
+    if (a.rhsOut != nullptr) {
+        if (valid) {
+#pragma unroll
+            for (int c = 0; c < NO; c++) a.rhsOut[((size_t)n * NI + HF + 2 * c) * Kp + k] = acc[c];
+        }
+        return;
+    }
+    const size_t base = (size_t)n * NI * Kp + kc;
+    double *dst = (a.rk == 0) ? a.q1 : (a.rk == 1) ? a.q2 : (a.rk == 2) ? a.q3 : (a.rk == 3) ? a.q4 : a.q0;
+    bool bad = false;
+#pragma unroll
+    for (int c = 0; c < NO; c++) {
+        const int i = HF + 2 * c;
+        const size_t o = base + (size_t)i * Kp;
+        const double qsi = sQ[(n * NI + i) * E + e];
+        const double rhs = acc[c];
+        double qn;
+        switch (a.rk) {
+            case 0: qn = qsi + RK0_A * (dtk * rhs); break;
+            case 1: qn = RK1_A * a.q0[o] + RK1_B * qsi + RK1_C * (dtk * rhs); break;
+            case 2: qn = RK2_A * a.q0[o] + RK2_B * qsi + RK2_C * (dtk * rhs); break;
+            case 3:
+                qn = RK3_A * a.q0[o] + RK3_B * qsi + RK3_C * (dtk * rhs);
+                if (valid) a.R[o] = rhs;
+                break;
+            default: {
+                const double q0 = a.q0[o];
+                const double dtR3 = dtk * a.R[o];
+                const double r = -q0 + RK4_A * a.q2[o] + RK4_B * a.q3[o] + RK4_C * qsi + RK4_D * dtR3 + RK4_E * (dtk * rhs);
+                if (valid) a.R[o] = r;
+                qn = q0 + r;
+            } break;
+        }
+        bad |= (qn != qn);
+        if (valid) dst[o] = qn;
+        acc[c] = qn;
+    }
+    if (bad && valid) a.sc->nanFlag = 1;
+    if (a.qface == nullptr) return;            // (uniform) no fused interpolation requested
+    __syncthreads();                           // every thread has read its stage-input values from sQ
+#pragma unroll
+    for (int c = 0; c < NO; c++) sQ[(n * NI + HF + 2 * c) * E + e] = acc[c];
+    __syncthreads();
+    if (!valid) return;
+    double *qf = a.qface + (size_t)n * NF3 * Kp + k;
+#pragma unroll
+    for (int c = 0; c < NM; c++) {
+        const int m = HF + 2 * c;
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NI; i++) s = fma(op.FEI[m][i], sQ[(n * NI + i) * E + e], s);
+        qf[(size_t)m * Kp] = s;
+    }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kElem2Threads, 3) k_elem2(ElemArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, E = kElemsPerBlock;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) {
+        if (a.rk == 4 && a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.sc->time[a.par ^ 1] = a.sc->time[a.par];
+            a.sc->finished = 1;
+        }
+        return;
+    }
+    extern __shared__ double smem[];
+    double *sQ = smem;                    // [4][NI][E]   stage input, later the fresh register
+    double *sF = smem + 4 * NI * E;       // [4][NF][E]   RT DOFs: interior (Fr, Fs) rows then the edge rows
+    const int e = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = w & 3, hf = w >> 2;
+    const int k = blockIdx.x * E + e;
+    const bool valid = k < a.K;
+    const int kc = valid ? k : a.K - 1;
+    const size_t Kp = a.Kp;
+
+    // phase 1: my half of the row, my half of the edge DOFs (SetRTFluxOnEdges, edges.go:454-483), dt
+    for (int i = hf; i < NI; i += 2) sQ[(n * NI + i) * E + e] = a.qs[((size_t)n * NI + i) * Kp + kc];
+    const double jdet = a.Jdet[kc];
+    double dtk;
+    {
+        double wmaxk = -1.7976931348623157e308;
+#pragma unroll
+        for (int le = 0; le < 3; le++) {
+            const int s = a.etoe[(size_t)le * Kp + kc];
+            const bool owner = s >= 0;
+            const int slot = owner ? s : -1 - s;
+            const double iin = a.IInII[(size_t)le * Kp + kc];
+            const double *f = a.eflux + ((size_t)n * NEd) * a.NEp + slot;
+            for (int r = le * NEd + ((le * NEd + hf) & 1); r < (le + 1) * NEd; r += 2) {
+                const int i = r - le * NEd;
+                const double v = f[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
+                sF[(n * NF + 2 * NI + r) * E + e] = owner ? v * iin : -v * iin;
+            }
+            if (a.ph.localDT) wmaxk = fmax(wmaxk, a.agg[slot]);
+        }
+        if (a.ph.localDT) {
+            const double d = (a.rk == 0) ? -100.0 : a.DT[kc];
+            dtk = a.ph.CFL / fmax(d, wmaxk);
+        } else {
+            const double gw = __longlong_as_double((long long)a.sc->wave[a.slot][0]);
+            dtk = a.ph.CFL / gw;
+            const double t = a.sc->time[a.par];
+            if (t + dtk > a.ph.FinalTime) dtk = a.ph.FinalTime - t;
+        }
+    }
+    __syncthreads();
+
+    // phase 2: SetRTFluxInternal, point j handled by warp j mod 8
+    {
+        const double j0 = a.Jinv[0 * Kp + kc], j1 = a.Jinv[1 * Kp + kc], j2 = a.Jinv[2 * Kp + kc], j3 = a.Jinv[3 * Kp + kc];
+        for (int j = w; j < NI; j += 8) {
+            double Q[4], Fx[4], Fy[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) Q[m] = sQ[(m * NI + j) * E + e];
+            flux_calc(a.ph.gamma, Q, Fx, Fy);
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                sF[(m * NF + j) * E + e] = jdet * (j0 * Fx[m] + j1 * Fy[m]);
+                sF[(m * NF + j + NI) * E + e] = jdet * (j2 * Fx[m] + j3 * Fy[m]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase 3/4: contraction, update, fused interpolation -- per half so that operator rows are compile-time
+    if (hf == 0) elem2_tail<N, 0>(a, sQ, sF, e, n, k, kc, valid, jdet, dtk);
+    else elem2_tail<N, 1>(a, sQ, sF, e, n, k, kc, valid, jdet, dtk);
+
+    if (a.rhsOut == nullptr) {
+        if (a.ph.localDT && valid && w == 0) a.DT[k] = dtk;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            a.sc->wave[a.slot ^ 1][0] = 0ull;
+            a.sc->wave[a.slot ^ 1][1] = 0ull;
+            if (!a.ph.localDT) a.sc->globalDT = dtk;
+            if (a.rk == 4) {
+                const double tnew = a.sc->time[a.par] + (a.ph.localDT ? a.sc->globalDT : dtk);
+                a.sc->time[a.par ^ 1] = tnew;
+                a.sc->timeOut = tnew;
+                const long long st = a.sc->steps + 1;
+                a.sc->steps = st;
+                if (tnew >= a.ph.FinalTime || st >= (long long)a.ph.maxIter) a.sc->finished = 1;
+            }
         }
     }
 }
