@@ -203,8 +203,21 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     }
     pl.G = (int)ghostGlobal.size();
     pl.Kp = ((pl.K + pl.G + 31) / 32) * 32;
-    // sort by the owner-side column so that owner-side loads of neighbouring threads coalesce
-    std::stable_sort(led.begin(), led.end(), [](const LE &a, const LE &b) { return a.l < b.l; });
+    // default: sort by the owner-side column so that owner-side loads of neighbouring threads coalesce.
+    // DFR2D_EDGE_SORT=1 sorts by (owner's local edge number, owner column) instead: one Q_Face row per warp on the
+    // owner side.
+    {
+        const char *ev = getenv("DFR2D_EDGE_SORT");
+        const bool byEdgeNumber = (ev && atoi(ev) == 1);     // measured: no net gain on B200 (k_edge slower, k_elem faster)
+        const int32_t *numL = p->edge_numL;
+        if (byEdgeNumber)
+            std::stable_sort(led.begin(), led.end(), [numL](const LE &a, const LE &b) {
+                const int na = numL[a.ge], nb = numL[b.ge];
+                return na != nb ? na < nb : a.l < b.l;
+            });
+        else
+            std::stable_sort(led.begin(), led.end(), [](const LE &a, const LE &b) { return a.l < b.l; });
+    }
     pl.NE = (int)led.size();
     pl.NEp = ((pl.NE + 31) / 32) * 32;
     pl.NV = (int)p->NV;
@@ -453,6 +466,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     h->edgeBlocks = sms * 8;
+    if (const char *ev = getenv("DFR2D_EDGE_BLOCKS_PER_SM")) h->edgeBlocks = sms * std::max(1, atoi(ev));
     h->pfTiles = 1;
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
     h->sms = sms;

@@ -58,8 +58,11 @@ __device__ __forceinline__ bool step_is_noop(const DevScalars *sc, const Phys &p
 // The BC routines overwrite Q_Face in place in the reference; the only later reader of the
 // overwritten rows is StoreEdgeAggregates, so the post-BC state stays in registers here.
 // ------------------------------------------------------------------------------------------------
+#ifndef DFR2D_EDGE_MINBLOCKS
+#define DFR2D_EDGE_MINBLOCKS 2
+#endif
 template <int N>
-__global__ void __launch_bounds__(256) k_edge(EdgeArgs a) {
+__global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) {
     constexpr int NE_ = Dim<N>::NpEdge;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
     const double gamma = a.ph.gamma;
