@@ -224,11 +224,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(args.warmup)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()          # started before the warm-up so that samples exist even for sub-second timed regions
+    run_steps(args.warmup)
+    barrier()
     l0 = dev.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
