@@ -25,6 +25,12 @@ namespace dfr2d {
 #ifndef DFR2D_PIPE_MINBLOCKS
 #define DFR2D_PIPE_MINBLOCKS 2
 #endif
+#ifndef DFR2D_PIPE_LATE_WAIT
+#define DFR2D_PIPE_LATE_WAIT 1
+#endif
+#ifndef DFR2D_PIPE_PACED
+#define DFR2D_PIPE_PACED 1
+#endif
 #ifndef DFR2D_PIPE_WARPS
 #define DFR2D_PIPE_WARPS 8
 #endif
@@ -152,6 +158,22 @@ __global__ void __launch_bounds__(kPipeThreads, DFR2D_PIPE_MINBLOCKS) k_elem_pip
         }                                                                                               \
     }
 
+    // the same loads one at a time, so that they can be paced through the compute phases of the current tile (a warp
+    // that issues ~25 loads back to back sits in the LSU queue for ~2000 cycles while HBM back-pressures)
+#define PIPE_LQ(c)  do { if (haveN && (c) < QR && part + P * (c) < NI) pq[(c)] = qsRow[(size_t)(c) * P * Kp + kkN]; } while (0)
+#define PIPE_LE(c)  do { if (haveN && (c) < ER) { const int row = part + P * (c);                                      \
+        if (row < NF3) { const int le = (row >= NEd) + (row >= 2 * NEd), i = row - le * NEd;                          \
+            const int sl = pick3(le, sC0, sC1, sC2); const bool own = sl >= 0;                                         \
+            pe[(c)] = efRow[(size_t)(own ? i : NEd - 1 - i) * a.NEp + (own ? sl : -1 - sl)]; } } } while (0)
+#define PIPE_LG()   do { if (haveN) {                                                                                  \
+        pIin0 = a.IInII[kkN + lane]; pIin1 = a.IInII[Kp + kkN + lane]; pIin2 = a.IInII[2 * Kp + kkN + lane];           \
+        pJd = a.Jdet[kkN + lane]; pJ0 = a.Jinv[kkN + lane]; pJ1 = a.Jinv[Kp + kkN + lane];                             \
+        pJ2 = a.Jinv[2 * Kp + kkN + lane]; pJ3 = a.Jinv[3 * Kp + kkN + lane];                                          \
+        if (a.ph.localDT && w == 0) {                                                                                  \
+            pAgg0 = a.agg[sC0 >= 0 ? sC0 : -1 - sC0]; pAgg1 = a.agg[sC1 >= 0 ? sC1 : -1 - sC1];                        \
+            pAgg2 = a.agg[sC2 >= 0 ? sC2 : -1 - sC2]; pDT = a.DT[kkN + lane]; } } } while (0)
+#define PIPE_FENCE() asm volatile("" ::: "memory")
+
     PIPE_LOAD_SLOTS(blockIdx.x, sC0, sC1, sC2);
     PIPE_ISSUE_LOADS(blockIdx.x);
     PIPE_LOAD_SLOTS(blockIdx.x + gridDim.x, sN0, sN1, sN2);
@@ -212,8 +234,15 @@ __global__ void __launch_bounds__(kPipeThreads, DFR2D_PIPE_MINBLOCKS) k_elem_pip
         PIPE_TICK(2);
         // ---- put tile t+1 in flight, and the edge slots of tile t+2 -------------------------------------------
         sC0 = sN0; sC1 = sN1; sC2 = sN2;
+        const bool haveN = tile + gridDim.x < args.nTiles;
+        const size_t kkN = (size_t)(tile + gridDim.x) * E;
+#if DFR2D_PIPE_PACED
+        PIPE_LG();
+        PIPE_LOAD_SLOTS(tile + 2 * gridDim.x, sN0, sN1, sN2);
+#else
         PIPE_ISSUE_LOADS(tile + gridDim.x);
         PIPE_LOAD_SLOTS(tile + 2 * gridDim.x, sN0, sN1, sN2);
+#endif
         PIPE_TICK(3);
         __syncthreads();
         PIPE_TICK(4);
@@ -233,8 +262,18 @@ __global__ void __launch_bounds__(kPipeThreads, DFR2D_PIPE_MINBLOCKS) k_elem_pip
                     sF[(m * MD::FROWS + j + NI) * SE + lane] = jdet * (j2 * Fx[m] + j3 * Fy[m]);
                 }
             }
+#if DFR2D_PIPE_PACED
+            PIPE_LQ(2 * jj); PIPE_LQ(2 * jj + 1); PIPE_FENCE();
+#endif
         }
+#if DFR2D_PIPE_PACED
+#pragma unroll
+        for (int c = 2 * ((NI + kPipeWarps - 1) / kPipeWarps); c < QR; c++) PIPE_LQ(c);
+        PIPE_FENCE();
+#endif
+#if !DFR2D_PIPE_LATE_WAIT
         asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
         __syncthreads();
         PIPE_TICK(5);
 
@@ -255,7 +294,21 @@ __global__ void __launch_bounds__(kPipeThreads, DFR2D_PIPE_MINBLOCKS) k_elem_pip
             for (int mt = 0; mt < M1; mt++)
 #pragma unroll
                 for (int t = 0; t < NT; t++) dmma884(c1[mt][t][0], c1[mt][t][1], a1[mt], b[t]);
+#if DFR2D_PIPE_PACED
+            PIPE_LE(ks); PIPE_FENCE();
+#endif
         }
+#if DFR2D_PIPE_PACED
+#pragma unroll
+        for (int c = K1; c < ER; c++) PIPE_LE(c);
+#endif
+#if DFR2D_PIPE_LATE_WAIT
+        // the RK registers are only needed from here on: give their cp.async the whole DMMA loop to land
+        if (nExtra > 0) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncthreads();
+        }
+#endif
         // epilogue in fragment layout: lane holds rows i = 8 mt + fr, elements e0 = 8 (NT part + t) + 2 fc, e0 + 1
 #pragma unroll
         for (int mt = 0; mt < M1; mt++) {
@@ -343,6 +396,10 @@ __global__ void __launch_bounds__(kPipeThreads, DFR2D_PIPE_MINBLOCKS) k_elem_pip
 #ifdef DFR2D_PIPE_TIMING
     if (threadIdx.x == 0) for (int i = 0; i < 8; i++) atomicAdd(&g_pipe_clk[i], (unsigned long long)clkAcc[i]);
 #endif
+#undef PIPE_LQ
+#undef PIPE_LE
+#undef PIPE_LG
+#undef PIPE_FENCE
 #undef PIPE_LOAD_SLOTS
 #undef PIPE_ISSUE_LOADS
     if (bad) a.sc->nanFlag = 1;
