@@ -34,7 +34,9 @@ struct dfr2d_handle {
     double *Jdet = nullptr, *Jinv = nullptr, *IInII = nullptr;
     int *etoe = nullptr;
     // edges
-    int *ekL = nullptr, *ekR = nullptr, *emeta = nullptr;
+    int *ekL = nullptr, *ekR = nullptr, *emeta = nullptr, *bndList = nullptr;
+    int nBnd = 0;
+    int edgeSplit = 1;                // 1: lean interior-edge kernel + boundary-list kernel; 0: one generic kernel
     double *enx = nullptr, *eny = nullptr, *eoohk = nullptr, *bpx = nullptr, *bpy = nullptr;
     // dissipation
     DissBuffers ds{};
@@ -56,6 +58,7 @@ struct dfr2d_handle {
     double *mmaFrags = nullptr;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
+    int edgePPT = 0;
 };
 
 #define CK(call)                                                                                        \
@@ -156,7 +159,7 @@ struct dfr2d_plan {
     int N = 0, nParts = 1, part = 0;
     int64_t Kglobal = 0, k0 = 0, k1 = 0;
     int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
-    std::vector<int> ekL, ekR, emeta, etoe, sendElem, sendRow0, recvCol, recvRow0;
+    std::vector<int> ekL, ekR, emeta, etoe, sendElem, sendRow0, recvCol, recvRow0, bndList;
     std::vector<double> enx, eny, eoohk, eooLen, bpx, bpy, Jdet, Jinv, IInII;
     std::vector<int64_t> ghostGlobal, edgeGlobal, sendCounts, recvCounts;
     int nSendEdges = 0, nRecvEdges = 0;
@@ -259,6 +262,7 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
                 return 3;
             }
             ekR[s] = -1 - nbp;
+            pl.bndList.push_back(s);
             for (int i = 0; i < NEd; i++) {
                 bpx.push_back(p->bp_x[it->second * NEd + i]);
                 bpy.push_back(p->bp_y[it->second * NEd + i]);
@@ -406,6 +410,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (int rc = dev_upload(h, &h->enx, enx, h->NEp)) return rc;
     if (int rc = dev_upload(h, &h->eny, eny, h->NEp)) return rc;
     if (int rc = dev_upload(h, &h->eoohk, eoohk, h->NEp)) return rc;
+    if (int rc = dev_upload(h, &h->bndList, pl.bndList)) return rc;
+    h->nBnd = (int)pl.bndList.size();
     if (int rc = dev_upload(h, &h->bpx, bpx)) return rc;
     if (int rc = dev_upload(h, &h->bpy, bpy)) return rc;
     if (h->nParts > 1) {
@@ -466,6 +472,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     h->edgeBlocks = sms * 8;
+    if (const char *ev = getenv("DFR2D_EDGE_PPT")) h->edgePPT = atoi(ev);
+    if (const char *ev = getenv("DFR2D_EDGE_SPLIT")) h->edgeSplit = atoi(ev);
     if (const char *ev = getenv("DFR2D_EDGE_BLOCKS_PER_SM")) h->edgeBlocks = sms * std::max(1, atoi(ev));
     h->pfTiles = 1;
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
@@ -601,7 +609,44 @@ static int run_edges(dfr2d_handle *h, int rk) {
     a.stepIndex = h->stepIndex;
     a.ph = h->ph;
     const int blocks = std::max(1, std::min(h->edgeBlocks, (h->NE + 255) / 256));
-    DISPATCH_N(h->N, (k_edge<NN><<<blocks, 256, 0, h->stream>>>(a)));
+    // points per thread: DFR2D_EDGE_PPT overrides (must divide N+2); agg is combined by atomicMax when an edge is split
+    // measured (tools/sweep_edge_ppt.sh): whole edges per thread on big meshes, one point per thread when there are
+    // too few edges to fill the machine (C2: 300K edges)
+    int ppt = h->edgePPT;
+    if (ppt <= 0) ppt = (h->NE < 64 * h->sms * 256) ? 1 : h->N + 2;
+    if ((h->N + 2) % ppt != 0) ppt = h->N + 2;
+    if (ppt != h->N + 2 && h->ph.localDT) CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
+    a.list = nullptr; a.nlist = 0;
+#define EDGE_LAUNCH(KERN)                                                                      \
+    DISPATCH_N(h->N, {                                                                          \
+        constexpr int NEd_ = NN + 2;                                                            \
+        if (ppt == 1) KERN(NN, 1);                                                              \
+        else if (NEd_ % 2 == 0 && ppt == 2) KERN(NN, (NEd_ % 2 == 0 ? 2 : 1));                  \
+        else if (NEd_ % 3 == 0 && ppt == 3) KERN(NN, (NEd_ % 3 == 0 ? 3 : 1));                  \
+        else KERN(NN, NEd_);                                                                    \
+    })
+    if (h->edgeSplit) {
+        const int ib = std::max(1, std::min(h->edgeBlocks * 2, (int)(((long long)h->NEp * ((h->N + 2) / ppt) + 255) / 256)));
+        switch (h->ph.fluxType) {
+#define KI_AVG(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_Average, P_><<<ib, 256, 0, h->stream>>>(a)
+#define KI_LAX(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_><<<ib, 256, 0, h->stream>>>(a)
+#define KI_ROE(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_Roe, P_><<<ib, 256, 0, h->stream>>>(a)
+#define KI_RER(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_RoeER, P_><<<ib, 256, 0, h->stream>>>(a)
+            case DFR2D_FLUX_Average: EDGE_LAUNCH(KI_AVG); break;
+            case DFR2D_FLUX_LaxFriedrichs: EDGE_LAUNCH(KI_LAX); break;
+            case DFR2D_FLUX_Roe: EDGE_LAUNCH(KI_ROE); break;
+            default: EDGE_LAUNCH(KI_RER); break;
+        }
+        if (int rc = launch_check(h, "k_edge_int")) return rc;
+        if (h->nBnd == 0) return 0;
+        a.list = h->bndList; a.nlist = h->nBnd;
+        const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
+#define KB(NN_, P_) k_edge<NN_, P_><<<bb, 256, 0, h->stream>>>(a)
+        EDGE_LAUNCH(KB);
+        return launch_check(h, "k_edge(boundary)");
+    }
+#define KG(NN_, P_) k_edge<NN_, P_><<<blocks, 256, 0, h->stream>>>(a)
+    EDGE_LAUNCH(KG);
     (void)rk;
     return launch_check(h, "k_edge");
 }

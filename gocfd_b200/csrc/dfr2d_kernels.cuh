@@ -17,6 +17,8 @@ constexpr int kElemThreads = 4 * kElemsPerBlock; // one thread per (element, con
 struct EdgeArgs {
     int ne, NEp, Kp;
     const int *kL, *kR, *meta;          // kR < 0: boundary edge, boundary-point slot = -1 - kR
+    const int *list;                    // optional: process only these edge slots (boundary edges)
+    int nlist;
     const double *nx, *ny, *oohk;
     const double *bpx, *bpy;            // [NBPloc][NpEdge]
     const double *qface;                // [4][3NpEdge][Kp]
@@ -61,21 +63,33 @@ __device__ __forceinline__ bool step_is_noop(const DevScalars *sc, const Phys &p
 #ifndef DFR2D_EDGE_MINBLOCKS
 #define DFR2D_EDGE_MINBLOCKS 2
 #endif
-template <int N>
+// PPT = edge points per thread.  PPT == NpEdge: one thread per edge (per-edge aggregate written directly).  Smaller PPT:
+// the points of an edge are split over NpEdge/PPT threads in different warps -- fewer registers, more warps in flight
+// for this latency-bound gather kernel; the per-edge aggregate (only consumed with local time stepping) is then
+// combined with atomicMax on the bit pattern (agg is zeroed by the host beforehand).
+template <int N, int PPT>
 __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) {
     constexpr int NE_ = Dim<N>::NpEdge;
+    constexpr int G = NE_ / PPT;
+    static_assert(NE_ % PPT == 0, "points per thread must divide NpEdge");
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
     const double gamma = a.ph.gamma;
     const size_t qplane = (size_t)Dim<N>::NF3 * a.Kp;
     const size_t fplane = (size_t)NE_ * a.NEp;
     double blockmax = 0.0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.ne; e += gridDim.x * blockDim.x) {
+    const int span = a.list ? a.nlist : a.NEp;
+    const long long total = (long long)G * span;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(t / span);
+        const int e = a.list ? a.list[t % span] : (int)(t % span);
+        if (e >= a.ne) continue;
         const int kL = a.kL[e], kR = a.kR[e], meta = a.meta[e];
         const int numL = meta & 3, numR = (meta >> 2) & 3, bc = (meta >> 4) & 15;
         const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
         double wmax = -1.7976931348623157e308;
 #pragma unroll
-        for (int i = 0; i < NE_; i++) {
+        for (int ii = 0; ii < PPT; ii++) {
+            const int i = g * PPT + ii;
             double QL[4], F[4];
             double wL = 0.0;
             bool haveW = false;
@@ -131,7 +145,65 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
             const double w = oohk * wL;
             if (w > wmax) wmax = w;
         }
-        a.agg[e] = wmax;
+        if (G == 1) a.agg[e] = wmax;
+        else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.agg[e]), wmax);
+        blockmax = fmax(blockmax, wmax);
+    }
+    __shared__ double smax[8];
+    blockmax = warp_max(blockmax);
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
+        v = warp_max(v);
+        if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][0], v);
+    }
+}
+
+// Interior (shared) edges only, flux type fixed at compile time: none of the boundary-condition code (pow/exp, three
+// free-stream records) is in this kernel, which halves its register count and doubles the warps in flight.
+// Boundary edges are skipped here and handled by k_edge<N,PPT> over the compact boundary list.
+template <int N, int FLUX, int PPT>
+__global__ void __launch_bounds__(256, 4) k_edge_int(EdgeArgs a) {
+    constexpr int NE_ = Dim<N>::NpEdge;
+    constexpr int G = NE_ / PPT;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    const double gamma = a.ph.gamma;
+    const size_t qplane = (size_t)Dim<N>::NF3 * a.Kp;
+    const size_t fplane = (size_t)NE_ * a.NEp;
+    double blockmax = 0.0;
+    const long long total = (long long)G * a.NEp;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(t % a.NEp), g = (int)(t / a.NEp);
+        if (e >= a.ne) continue;
+        const int kR = a.kR[e];
+        if (kR < 0) continue;
+        const int kL = a.kL[e], meta = a.meta[e];
+        const int numL = meta & 3, numR = (meta >> 2) & 3;
+        const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
+        double wmax = -1.7976931348623157e308;
+#pragma unroll
+        for (int ii = 0; ii < PPT; ii++) {
+            const int i = g * PPT + ii;
+            double QL[4], QR[4], F[4], wL;
+            const size_t offL = (size_t)(numL * NE_ + i) * a.Kp + kL;
+            const size_t offR = (size_t)(numR * NE_ + (NE_ - 1 - i)) * a.Kp + kR;
+#pragma unroll
+            for (int n = 0; n < 4; n++) { QL[n] = a.qface[n * qplane + offL]; QR[n] = a.qface[n * qplane + offR]; }
+            if (FLUX == DFR2D_FLUX_Roe) roe_flux(gamma, QL, QR, nx, ny, F, wL);
+            else {
+                if (FLUX == DFR2D_FLUX_Average) avg_flux(gamma, QL, QR, nx, ny, F);
+                else if (FLUX == DFR2D_FLUX_LaxFriedrichs) lax_flux(gamma, QL, QR, nx, ny, F);
+                else roe_er_flux(gamma, QL, QR, nx, ny, F);
+                wL = speed_plus_sound(gamma, QL[0], QL[1], QL[2], QL[3]);
+            }
+#pragma unroll
+            for (int n = 0; n < 4; n++) a.eflux[n * fplane + (size_t)i * a.NEp + e] = F[n];
+            const double w = oohk * wL;
+            if (w > wmax) wmax = w;
+        }
+        if (G == 1) a.agg[e] = wmax;
+        else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.agg[e]), wmax);
         blockmax = fmax(blockmax, wmax);
     }
     __shared__ double smax[8];
