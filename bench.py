@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--nx", type=int, default=0, help="override the mesh size (debug)")
+    ap.add_argument("--order", type=int, default=-1, help="override the polynomial order (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -180,6 +181,8 @@ def main():
     nx, ny, n = WORKLOADS[args.workload]
     if args.nx:
         nx = ny = args.nx
+    if args.order >= 0:
+        n = args.order
     t_setup = time.perf_counter()
     c = build_case(nx, ny, n)
     p = c.problem

@@ -478,9 +478,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->pfTiles = 1;
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
     h->sms = sms;
-    // measured on B200 (profiles/r01c_*): the pipelined DMMA kernel wins at N >= 3, the row-per-thread DFMA kernel
-    // at N <= 2 (small operators: DMMA padding waste, fewer tiles per persistent CTA)
-    h->elemKernel = (N >= 3) ? 4 : 1;
+    // measured on B200 (profiles/r01c_*): the pipelined DMMA kernel wins at N = 4 (6.6 vs 8.1 ms), the row-per-thread DFMA kernel
+    // at N <= 3 (small operators: DMMA padding waste, fewer tiles per persistent CTA)
+    h->elemKernel = (N >= 4) ? 4 : 1;
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
     {
         std::vector<double> fr;

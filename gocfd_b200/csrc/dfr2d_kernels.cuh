@@ -60,6 +60,9 @@ __device__ __forceinline__ bool step_is_noop(const DevScalars *sc, const Phys &p
 // The BC routines overwrite Q_Face in place in the reference; the only later reader of the
 // overwritten rows is StoreEdgeAggregates, so the post-BC state stays in registers here.
 // ------------------------------------------------------------------------------------------------
+#ifndef DFR2D_EDGEINT_MINBLOCKS
+#define DFR2D_EDGEINT_MINBLOCKS 3
+#endif
 #ifndef DFR2D_EDGE_MINBLOCKS
 #define DFR2D_EDGE_MINBLOCKS 2
 #endif
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
 // free-stream records) is in this kernel, which halves its register count and doubles the warps in flight.
 // Boundary edges are skipped here and handled by k_edge<N,PPT> over the compact boundary list.
 template <int N, int FLUX, int PPT>
-__global__ void __launch_bounds__(256, 4) k_edge_int(EdgeArgs a) {
+__global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeArgs a) {
     constexpr int NE_ = Dim<N>::NpEdge;
     constexpr int G = NE_ / PPT;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
