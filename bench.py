@@ -27,7 +27,9 @@ WORKLOADS = {
     # name: (nx, ny, N)
     "c5": (2000, 2000, 4),      # 8,000,000 triangles, P=4 (north-star target config)
     "c2": (316, 316, 2),        # 199,712 triangles, P=2
+    "c3": (2000, 500, 4),       # 2,000,000 triangles, P=4: Sod tube (In/Out/Wall), PerssonC0 sensor + dissipation path
 }
+DISSIPATION_WORKLOADS = ("c3",)
 
 
 def algorithmic_bytes(n):
@@ -40,10 +42,32 @@ def algorithmic_bytes(n):
     return total, elem, edge
 
 
-def build_case(nx, ny, n, max_iter=10 ** 9):
+def algorithmic_bytes_visc(n):
+    """B_visc(N) of SURVEY.md 8d: the inviscid bytes plus the sensor / vertex merge / RT gradient / viscous flux /
+    limiter traffic of the PerssonC0 path, per element per stage."""
+    np_int, np_edge = (n + 1) * (n + 2) // 2, n + 2
+    return algorithmic_bytes(n)[0] + 8.0 * (17.6 * np_int + 84 * np_edge + 18)
+
+
+def build_case(nx, ny, n, max_iter=10 ** 9, dissipation=False):
     from gocfd_b200.host.euler2d import Euler
     from gocfd_b200.host.input_parameters import InputParameters2D
     from gocfd_b200.host.meshgen import structured_tri_mesh
+    if dissipation:
+        # config C3 scaled up: the shipped sod-aligned meshes are [0,1] x [0,~0.1] tubes with in/out/wall tags
+        ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=n,
+                               FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.0, Limiter="persson c0", Kappa=5.0)
+        mesh = structured_tri_mesh(nx, ny, 0.0, 1.0, 0.0, float(ny) / float(nx),
+                                   side_tags={"left": "in", "right": "out", "top": "wall", "bottom": "wall"})
+        c = Euler(ip, mesh)
+        # a raw jump inside a P4 element undershoots to negative density at the edge points (the reference would
+        # NaN-panic as well), so the front is smeared over half an element width and kept off the grid lines
+        x, _ = c.DFR.solution_xy()
+        h = 1.0 / nx
+        w = 0.5 * (1.0 - np.tanh((x - (0.5 + 0.3 * h)) / (0.5 * h)))
+        for v in range(4):
+            c.Q[v] = c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w
+        return c
     ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n,
                            FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.1)
     return Euler(ip, structured_tri_mesh(nx, ny, tag="wall"))
@@ -201,8 +225,10 @@ def main():
     if args.order >= 0:
         n = args.order
     t_setup = time.perf_counter()
-    c = build_case(nx, ny, n)
+    diss = args.workload in DISSIPATION_WORKLOADS
+    c = build_case(nx, ny, n, dissipation=diss)
     p = c.problem
+    assert bool(p.Dissipation) == diss
     dev = lib.Dfr2d(p, n_parts=world, part=rank, device=local_rank)
     stream = torch.cuda.current_stream()
     dev.set_stream(stream.cuda_stream)
@@ -216,17 +242,28 @@ def main():
     dev.set_state(q_host)
 
     if world > 1:
-        sc, rc = dev.halo_counts()
-        sp, rp = dev.halo_buffers()
-        send_t = torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda")[:sum(sc)]
-        recv_t = torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda")[:sum(rc)]
-        wave_t = [None, None]
+        # one NCCL all_to_all per exchange point of the stage (1 inviscid, 3 with dissipation) + the MAX allreduce
+        def exchange(which):
+            sc, rc = dev.exchange_counts(which)
+            sp, rp = dev.exchange_buffers(which)
+            st = torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda")[:sum(sc)]
+            rt = torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda")[:sum(rc)]
+            return lambda: dist.all_to_all_single(rt, st, rc, sc)
+        x_edge = exchange(dev.XCHG_EDGE)
+        x_vtx = exchange(dev.XCHG_VERTEX) if diss else None
+        x_diss = exchange(dev.XCHG_DISS) if diss else None
 
         def one_step():
             for rk in range(5):
+                if diss:
+                    dev.stage_sensor(rk)
+                    x_vtx()
                 dev.stage_prepare(rk)
-                dist.all_to_all_single(recv_t, send_t, rc, sc)
+                x_edge()
                 dev.stage_edges(rk)
+                if diss:
+                    x_diss()
+                    dev.stage_visc(rk)
                 wp = dev.wavespeed_buffer()
                 w = torch.as_tensor(_DevArray(wp, 2), device="cuda")
                 dist.all_reduce(w, op=dist.ReduceOp.MAX)
@@ -273,7 +310,7 @@ def main():
     b_total, b_elem, b_edge = algorithmic_bytes(n)
     k_local = k1 - k0
     t_elem, t_edge = [], []
-    if world == 1:
+    if world == 1 and not diss:
         evs = []
         for _ in range(2):
             for rk in range(5):
@@ -296,6 +333,12 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     roofline = None
+    if diss:
+        bv = algorithmic_bytes_visc(n)
+        ach = bv * p.K * 5 * args.steps / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad, k_visc_edge, k_elem<N,true>)",
+                    "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
+                    "peak_source": peak_src, "bytes_per_element_stage": bv}
     if t_elem:
         te = statistics.mean(t_elem) * 1e-3
         ach = b_elem * k_local / te / 1e9
@@ -355,8 +398,10 @@ def main():
             "metric": "DOF-stage-updates/s", "value": value, "unit": "DOF-stage-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: isentropic vortex, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, "
-                                   "IVortex+Riemann boundaries" % (args.workload, nx, ny, p.K, n, p.NpInt),
+            "config": {"workload": ("%s: Sod shock tube, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, PerssonC0 "
+                                    "sensor + artificial dissipation, In/Out/Wall boundaries" if diss else
+                                    "%s: isentropic vortex, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, "
+                                    "IVortex+Riemann boundaries") % (args.workload, nx, ny, p.K, n, p.NpInt),
                        "partition": "PartitionMap.Split1D element ranges over %d GPU(s)" % world,
                        "l2": "no flush needed: per-GPU working set %.1f GB >> 126 MB L2"
                              % ((5 * 4 * p.NpInt + 12 * p.NpEdge + 6 * p.NpEdge) * 8 * k_local / 1e9),
@@ -365,7 +410,7 @@ def main():
             "us_per_element_iteration": ms * 1e3 / args.steps / p.K,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and not diss:
             line["cpu_baseline"] = cpu_baseline(n)
         print(json.dumps(line))
     dev.close()

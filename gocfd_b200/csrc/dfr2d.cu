@@ -46,6 +46,12 @@ struct dfr2d_handle {
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int *sendElem = nullptr, *sendRow0 = nullptr, *recvCol = nullptr, *recvRow0 = nullptr;
     int nSendEdges = 0, nRecvEdges = 0;
+    int ePer = 0;                     // doubles per cut edge in the Q_Face message (4 NpEdge, +3 vertex eps with dissipation)
+    // dissipation exchanges (multi-partition): shared-vertex max merge and DissX/DissY edge rows
+    std::vector<int64_t> vtxCounts, dissCounts;
+    int nVtx = 0;
+    int *vtxList = nullptr;
+    double *vSendBuf = nullptr, *vRecvBuf = nullptr, *dSendBuf = nullptr, *dRecvBuf = nullptr;
     // time loop
     DevScalars *sc = nullptr;
     DevScalars *scHost = nullptr;     // pinned
@@ -164,6 +170,9 @@ struct dfr2d_plan {
     std::vector<int64_t> ghostGlobal, edgeGlobal, sendCounts, recvCounts;
     int nSendEdges = 0, nRecvEdges = 0;
     int64_t sendTotal = 0, recvTotal = 0;
+    int ePer = 0;
+    std::vector<int> vtxList;              // shared vertices grouped by peer, ascending vertex id within a peer
+    std::vector<int64_t> vtxCounts;        // doubles per peer in the vertex message (2 per listed vertex)
     std::string err;
 };
 
@@ -317,7 +326,8 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
         std::stable_sort(cuts.begin(), cuts.end(), [](const Cut &a, const Cut &b) {
             return a.peer != b.peer ? a.peer < b.peer : a.ge < b.ge;
         });
-        const int64_t per = 4 * NEd;
+        const int64_t per = 4 * NEd + (p->dissipation ? 3 : 0);
+        pl.ePer = (int)per;
         for (auto &c : cuts) {
             pl.sendCounts[c.peer] += per;
             pl.recvCounts[c.peer] += per;
@@ -328,6 +338,44 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
         }
         pl.nSendEdges = pl.nRecvEdges = (int)cuts.size();
         pl.sendTotal = pl.recvTotal = per * (int64_t)cuts.size();
+    }
+
+    // ---- shared vertices (dissipation): the element -> vertex max merge (euler.go:1048-1065) must see the
+    // incident elements of every partition.  Each pair of partitions that both touch a vertex exchanges its
+    // local maxima for it; both sides list the vertices in ascending global id, so the messages line up.
+    pl.vtxCounts.assign(pl.nParts, 0);
+    if (pl.nParts > 1 && p->dissipation) {
+        std::vector<int> firstPart((size_t)p->NV, -1);
+        std::vector<std::pair<int64_t, int>> multi;      // (vertex, partition) for vertices touched by >= 2 partitions
+        for (int pt = 0; pt < pl.nParts; pt++) {
+            int64_t lo, hi;
+            split1d(p->K, pl.nParts, pt, &lo, &hi);
+            for (int64_t k = lo; k < hi; k++)
+                for (int v = 0; v < 3; v++) {
+                    const int64_t vid = p->EToV[k * 3 + v];
+                    if (firstPart[vid] < 0) firstPart[vid] = pt;
+                    else if (firstPart[vid] != pt) multi.emplace_back(vid, pt);
+                }
+        }
+        std::sort(multi.begin(), multi.end());
+        multi.erase(std::unique(multi.begin(), multi.end()), multi.end());
+        std::vector<std::vector<int>> byPeer(pl.nParts);
+        for (size_t i = 0; i < multi.size();) {
+            size_t j = i;
+            const int64_t vid = multi[i].first;
+            bool mineTouches = firstPart[vid] == pl.part;
+            while (j < multi.size() && multi[j].first == vid) { mineTouches |= multi[j].second == pl.part; j++; }
+            if (mineTouches) {
+                if (firstPart[vid] != pl.part) byPeer[firstPart[vid]].push_back((int)vid);
+                for (size_t t = i; t < j; t++)
+                    if (multi[t].second != pl.part) byPeer[multi[t].second].push_back((int)vid);
+            }
+            i = j;
+        }
+        for (int pt = 0; pt < pl.nParts; pt++) {
+            pl.vtxCounts[pt] = 2 * (int64_t)byPeer[pt].size();
+            pl.vtxList.insert(pl.vtxList.end(), byPeer[pt].begin(), byPeer[pt].end());
+        }
     }
 
     return 0;
@@ -373,6 +421,10 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->K = pl.K; h->G = pl.G; h->Kp = pl.Kp; h->NE = pl.NE; h->NEp = pl.NEp; h->NV = pl.NV; h->NBP = pl.NBP;
     h->sendCounts = pl.sendCounts; h->recvCounts = pl.recvCounts;
     h->nSendEdges = pl.nSendEdges; h->nRecvEdges = pl.nRecvEdges; h->sendTotal = pl.sendTotal; h->recvTotal = pl.recvTotal;
+    h->ePer = pl.ePer;
+    h->vtxCounts = pl.vtxCounts;
+    h->nVtx = (int)pl.vtxList.size();
+    h->dissCounts.assign(h->nParts, 0);
     const int Kp = h->Kp, K = h->K;
     const int64_t k0 = h->k0;
     const double np12 = (double)((N + 1) * (N + 1));
@@ -431,6 +483,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
             for (int v = 0; v < 3; v++) etov[(size_t)v * Kp + k] = p->EToV[kg * 3 + v];
             hk[k] = p->EdgeLenMax[kg] / np12;
         }
+        // a ghost column's three vertex values arrive with the Q_Face message into private slots behind the real vertices
+        for (int g = 0; g < h->G; g++)
+            for (int v = 0; v < 3; v++) etov[(size_t)v * Kp + K + g] = h->NV + 3 * g + v;
         std::vector<double> nxk((size_t)3 * Kp, 0.0), nyk((size_t)3 * Kp, 0.0);
         for (int k = 0; k < K; k++)
             for (int le = 0; le < 3; le++) {
@@ -447,7 +502,16 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_alloc(h, &d.epsk, (size_t)Kp)) return rc;
         if (int rc = dev_alloc(h, &d.se, (size_t)Kp)) return rc;
         if (int rc = dev_alloc(h, &d.sigmaV, (size_t)h->NV)) return rc;
-        if (int rc = dev_alloc(h, &d.epsV, (size_t)h->NV)) return rc;
+        if (int rc = dev_alloc(h, &d.epsV, (size_t)h->NV + 3 * (size_t)h->G)) return rc;
+        CK(cudaMemset(d.epsV, 0, ((size_t)h->NV + 3 * (size_t)h->G) * sizeof(double)));
+        if (h->nParts > 1) {
+            for (int pt = 0; pt < h->nParts; pt++) h->dissCounts[pt] = (h->sendCounts[pt] / h->ePer) * 8 * NEd;
+            if (int rc = dev_upload(h, &h->vtxList, pl.vtxList)) return rc;
+            if (int rc = dev_alloc(h, &h->vSendBuf, (size_t)2 * h->nVtx)) return rc;
+            if (int rc = dev_alloc(h, &h->vRecvBuf, (size_t)2 * h->nVtx)) return rc;
+            if (int rc = dev_alloc(h, &h->dSendBuf, (size_t)8 * NEd * h->nSendEdges)) return rc;
+            if (int rc = dev_alloc(h, &h->dRecvBuf, (size_t)8 * NEd * h->nRecvEdges)) return rc;
+        }
         if (int rc = dev_alloc(h, &d.dissX, (size_t)4 * h->NpFlux * Kp)) return rc;
         if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * h->NpFlux * Kp)) return rc;
         if (int rc = dev_alloc(h, &d.vflux, (size_t)4 * NEd * h->NEp)) return rc;
@@ -502,7 +566,6 @@ extern "C" int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int d
     if (!p || !out) { g_create_error = "null argument"; return 1; }
     if (p->N < 0 || p->N > DFR2D_MAX_ORDER) { g_create_error = "polynomial order out of range 0..4"; return 1; }
     if (n_parts < 1 || part < 0 || part >= n_parts || p->K < n_parts) { g_create_error = "bad partition request"; return 1; }
-    if (p->dissipation && n_parts > 1) { g_create_error = "artificial dissipation is single-partition only in this build"; return 1; }
     dfr2d_handle *h = new dfr2d_handle();
     h->N = p->N; h->device = device; h->nParts = n_parts; h->part = part;
     int rc = create_impl(h, p);
@@ -580,20 +643,58 @@ static int run_interp(dfr2d_handle *h, const double *reg) {
 
 static int run_pack(dfr2d_handle *h) {
     if (h->nSendEdges == 0) return 0;
-    const int per = 4 * h->NpEdge;
-    const int total = h->nSendEdges * per;
-    k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->NpEdge, h->Kp, h->qface, h->sendElem, h->sendRow0,
-                                                            h->sendBuf);
+    const int tail = h->ePer - 4 * h->NpEdge;
+    const int total = h->nSendEdges * h->ePer;
+    k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->ePer, h->NpEdge, 3 * h->NpEdge, 0, h->Kp, h->qface,
+                                                            h->sendElem, h->sendRow0, h->sendBuf, 0, tail, h->ds.etov, h->ds.epsV);
     return launch_check(h, "k_halo_pack");
 }
 
 static int run_unpack(dfr2d_handle *h) {
     if (h->nRecvEdges == 0) return 0;
-    const int per = 4 * h->NpEdge;
-    const int total = h->nRecvEdges * per;
-    k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->NpEdge, h->Kp, h->qface, h->recvCol, h->recvRow0,
-                                                              h->recvBuf);
+    const int tail = h->ePer - 4 * h->NpEdge;
+    const int total = h->nRecvEdges * h->ePer;
+    k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->ePer, h->NpEdge, 3 * h->NpEdge, 0, h->Kp, h->qface,
+                                                              h->recvCol, h->recvRow0, h->recvBuf, 0, tail, h->K, h->NV, h->ds.epsV);
     return launch_check(h, "k_halo_unpack");
+}
+
+// DissX / DissY edge rows of the cut edges (rows 2 NpInt + edge * NpEdge + i of the sender's element)
+static int run_pack_diss(dfr2d_handle *h) {
+    if (h->nSendEdges == 0) return 0;
+    const int body = 4 * h->NpEdge, total = h->nSendEdges * body;
+    for (int xy = 0; xy < 2; xy++) {
+        k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, 2 * body, h->NpEdge, h->NpFlux, 2 * h->NpInt, h->Kp,
+                                                                xy ? h->ds.dissY : h->ds.dissX, h->sendElem, h->sendRow0,
+                                                                h->dSendBuf, xy * body, 0, nullptr, nullptr);
+        if (int rc = launch_check(h, "k_halo_pack(diss)")) return rc;
+    }
+    return 0;
+}
+
+static int run_unpack_diss(dfr2d_handle *h) {
+    if (h->nRecvEdges == 0) return 0;
+    const int body = 4 * h->NpEdge, total = h->nRecvEdges * body;
+    for (int xy = 0; xy < 2; xy++) {
+        k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, 2 * body, h->NpEdge, h->NpFlux, 2 * h->NpInt, h->Kp,
+                                                                  xy ? h->ds.dissY : h->ds.dissX, h->recvCol, h->recvRow0,
+                                                                  h->dRecvBuf, xy * body, 0, h->K, h->NV, nullptr);
+        if (int rc = launch_check(h, "k_halo_unpack(diss)")) return rc;
+    }
+    return 0;
+}
+
+static int run_pack_vertex(dfr2d_handle *h) {
+    if (h->nVtx == 0) return 0;
+    k_vertex_pack<<<(h->nVtx + 255) / 256, 256, 0, h->stream>>>(h->nVtx, h->vtxList, h->ds.sigmaV, h->ds.epsV, h->vSendBuf);
+    return launch_check(h, "k_vertex_pack");
+}
+
+static int run_unpack_vertex(dfr2d_handle *h) {
+    if (h->nVtx == 0) return 0;
+    k_vertex_unpack_max<<<(h->nVtx + 255) / 256, 256, 0, h->stream>>>(h->nVtx, h->vtxList, (unsigned long long *)h->ds.sigmaV,
+                                                                      (unsigned long long *)h->ds.epsV, h->vRecvBuf);
+    return launch_check(h, "k_vertex_unpack_max");
 }
 
 static int run_edges(dfr2d_handle *h, int rk) {
@@ -750,8 +851,8 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     return launch_check(h, "k_elem");
 }
 
-// sensor + vertex merge + (rk == 2) limiter + edge interpolation: phases P1-P3 of StepWorker (euler.go:574-616)
-static int run_diss_prepare(dfr2d_handle *h, int rk) {
+// sensor + element -> vertex max merge: phases P1-P2 of StepWorker (euler.go:574-600)
+static int run_diss_sensor(dfr2d_handle *h, int rk) {
     DissBuffers &d = h->ds;
     CK(cudaMemsetAsync(d.sigmaV, 0, (size_t)h->NV * sizeof(double), h->stream));
     CK(cudaMemsetAsync(d.epsV, 0, (size_t)h->NV * sizeof(double), h->stream));
@@ -763,19 +864,24 @@ static int run_diss_prepare(dfr2d_handle *h, int rk) {
     sa.sigmaV = (unsigned long long *)d.sigmaV; sa.epsV = (unsigned long long *)d.epsV;
     sa.sc = h->sc; sa.par = (int)(h->stepIndex & 1); sa.stepIndex = h->stepIndex; sa.ph = h->ph;
     DISPATCH_N(h->N, (k_sensor<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(sa)));
-    if (int rc = launch_check(h, "k_sensor")) return rc;
+    return launch_check(h, "k_sensor");
+}
+
+// vertex -> element mean, (rk == 2) limiter, edge interpolation: phase P3 (euler.go:601-616)
+static int run_diss_prepare(dfr2d_handle *h, int rk) {
+    DissBuffers &d = h->ds;
     PrepArgs pa{};
     pa.K = h->K; pa.Kp = h->Kp;
     pa.q = h->q[rk]; pa.qface = h->qface;
     pa.etov = d.etov; pa.sigmaV = d.sigmaV; pa.sigma = d.sigma;
-    pa.sc = h->sc; pa.rk = rk; pa.par = sa.par; pa.stepIndex = h->stepIndex; pa.ph = h->ph;
+    pa.sc = h->sc; pa.rk = rk; pa.par = (int)(h->stepIndex & 1); pa.stepIndex = h->stepIndex; pa.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
     DISPATCH_N(h->N, (k_diss_prepare<NN><<<blocks, kElemThreads, 0, h->stream>>>(pa)));
     return launch_check(h, "k_diss_prepare");
 }
 
-// RT gradient x epsilon, then the viscous edge flux: phases P5-P6 (euler.go:624-635)
-static int run_diss_edges(dfr2d_handle *h, int rk) {
+// RT gradient x epsilon: phase P5 (euler.go:624-628)
+static int run_diss_grad(dfr2d_handle *h, int rk) {
     DissBuffers &d = h->ds;
     GradArgs ga{};
     ga.K = h->K; ga.Kp = h->Kp;
@@ -790,7 +896,12 @@ static int run_diss_edges(dfr2d_handle *h, int rk) {
         const size_t sm = (size_t)4 * (Dim<NN>::NpInt + Dim<NN>::NF3) * kElemsPerBlock * sizeof(double);
         k_grad<NN><<<blocks, kElemThreads, sm, h->stream>>>(ga);
     });
-    if (int rc = launch_check(h, "k_grad")) return rc;
+    return launch_check(h, "k_grad");
+}
+
+// viscous edge flux: phase P6 (euler.go:629-635)
+static int run_diss_visc(dfr2d_handle *h) {
+    DissBuffers &d = h->ds;
     ViscEdgeArgs va{};
     va.ne = h->NE; va.NEp = h->NEp; va.Kp = h->Kp;
     va.kL = h->ekL; va.kR = h->ekR; va.meta = h->emeta;
@@ -798,18 +909,30 @@ static int run_diss_edges(dfr2d_handle *h, int rk) {
     va.qface = h->qface; va.dissX = d.dissX; va.dissY = d.dissY;
     va.etov = d.etov; va.epsV = d.epsV;
     va.vflux = d.vflux; va.aggv = d.aggv;
-    va.sc = h->sc; va.slot = (int)(h->stageCounter & 1); va.par = ga.par; va.stepIndex = h->stepIndex; va.ph = h->ph;
+    va.sc = h->sc; va.slot = (int)(h->stageCounter & 1); va.par = (int)(h->stepIndex & 1); va.stepIndex = h->stepIndex; va.ph = h->ph;
     const int eb = std::max(1, std::min(h->edgeBlocks, (h->NE + 255) / 256));
     DISPATCH_N(h->N, (k_visc_edge<NN><<<eb, 256, 0, h->stream>>>(va)));
     return launch_check(h, "k_visc_edge");
 }
 
 // ---- stage phases (also the multi-process API) ---------------------------------------------------------
+// inviscid:     prepare [interp, pack E]  ->E->  edges [unpack E, k_edge]  ->allreduce->  update
+// dissipation:  sensor [k_sensor, pack V] ->V->  prepare [unpack V, k_diss_prepare, pack E] ->E->
+//               edges [unpack E, k_edge, k_grad, pack D] ->D-> visc [unpack D, k_visc_edge] ->allreduce-> update
+static int stage_sensor(dfr2d_handle *h, int rk) {
+    if (!h->ph.dissipation) return 0;
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
+    if (int rc = run_diss_sensor(h, rk)) return rc;
+    return run_pack_vertex(h);
+}
+
 static int stage_prepare(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     if (h->ph.dissipation) {
-        if (int rc = run_diss_prepare(h, rk)) return rc;     // sensor, vertex merge, limiter, interpolation
+        if (int rc = run_unpack_vertex(h)) return rc;
+        if (int rc = run_diss_prepare(h, rk)) return rc;     // vertex mean, limiter, interpolation
     } else if (!h->qfaceValid) {
         if (int rc = run_interp(h, h->q[rk])) return rc;
     }
@@ -821,8 +944,19 @@ static int stage_edges(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
     if (int rc = run_unpack(h)) return rc;
     if (int rc = run_edges(h, rk)) return rc;
-    if (h->ph.dissipation) return run_diss_edges(h, rk);     // gradient + viscous edge flux
+    if (h->ph.dissipation) {
+        if (int rc = run_diss_grad(h, rk)) return rc;
+        return run_pack_diss(h);
+    }
     return 0;
+}
+
+static int stage_visc(dfr2d_handle *h, int rk) {
+    (void)rk;
+    if (!h->ph.dissipation) return 0;
+    CK(cudaSetDevice(h->device));
+    if (int rc = run_unpack_diss(h)) return rc;
+    return run_diss_visc(h);
 }
 
 static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
@@ -837,6 +971,8 @@ static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
     return 0;
 }
 
+extern "C" int dfr2d_stage_sensor(dfr2d_handle *h, int rk) { return h ? stage_sensor(h, rk) : 1; }
+extern "C" int dfr2d_stage_visc(dfr2d_handle *h, int rk) { return h ? stage_visc(h, rk) : 1; }
 extern "C" int dfr2d_stage_prepare(dfr2d_handle *h, int rk) { return h ? stage_prepare(h, rk) : 1; }
 extern "C" int dfr2d_stage_edges(dfr2d_handle *h, int rk) { return h ? stage_edges(h, rk) : 1; }
 extern "C" int dfr2d_stage_update(dfr2d_handle *h, int rk) { return h ? stage_update(h, rk, nullptr) : 1; }
@@ -868,8 +1004,10 @@ extern "C" int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info) {
     for (int s = 0; s < nsteps; s++) {
         if (h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) break;   // host-visible half of CheckIfFinished
         for (int rk = 0; rk < 5; rk++) {
+            if (int rc = stage_sensor(h, rk)) return rc;
             if (int rc = stage_prepare(h, rk)) return rc;
             if (int rc = stage_edges(h, rk)) return rc;
+            if (int rc = stage_visc(h, rk)) return rc;
             if (int rc = stage_update(h, rk, nullptr)) return rc;
         }
     }
@@ -886,8 +1024,10 @@ extern "C" int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out) {
         if (int rc = dev_alloc(h, &h->rhsScratch, (size_t)4 * h->NpInt * h->Kp)) return rc;
     }
     h->qfaceValid = false;
+    if (int rc = stage_sensor(h, rk)) return rc;
     if (int rc = stage_prepare(h, rk)) return rc;
     if (int rc = stage_edges(h, rk)) return rc;
+    if (int rc = stage_visc(h, rk)) return rc;
     if (int rc = stage_update(h, rk, h->rhsScratch)) return rc;
     h->qfaceValid = false;
     return copy_out(h, h->rhsScratch, RHS_out);
@@ -952,6 +1092,21 @@ extern "C" int dfr2d_halo_buffers(dfr2d_handle *h, void **s, void **r) {
     if (r) *r = h->recvBuf;
     return 0;
 }
+extern "C" int dfr2d_exchange_counts(const dfr2d_handle *h, int which, int64_t *s, int64_t *r) {
+    if (!h || which < 0 || which > 2) return 1;
+    const std::vector<int64_t> &c = which == DFR2D_XCHG_EDGE ? h->sendCounts : (which == DFR2D_XCHG_VERTEX ? h->vtxCounts : h->dissCounts);
+    for (int i = 0; i < h->nParts; i++) {      // every exchange is symmetric: what goes to a peer comes back from it
+        if (s) s[i] = c[i];
+        if (r) r[i] = c[i];
+    }
+    return 0;
+}
+extern "C" int dfr2d_exchange_buffers(dfr2d_handle *h, int which, void **s, void **r) {
+    if (!h || which < 0 || which > 2) return 1;
+    if (s) *s = which == DFR2D_XCHG_EDGE ? h->sendBuf : (which == DFR2D_XCHG_VERTEX ? h->vSendBuf : h->dSendBuf);
+    if (r) *r = which == DFR2D_XCHG_EDGE ? h->recvBuf : (which == DFR2D_XCHG_VERTEX ? h->vRecvBuf : h->dRecvBuf);
+    return 0;
+}
 extern "C" int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **p) {
     if (!h || !p) return 1;
     *p = (void *)&h->sc->wave[h->stageCounter & 1][0];
@@ -1001,6 +1156,13 @@ extern "C" int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64
         if (recv_col) recv_col[c] = pl->recvCol[c];
         if (recv_row0) recv_row0[c] = pl->recvRow0[c];
     }
+    return 0;
+}
+
+extern "C" int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_t *vertex_ids) {
+    if (!pl) return 1;
+    for (int i = 0; i < pl->nParts; i++) if (counts) counts[i] = pl->vtxCounts[i];
+    if (vertex_ids) for (size_t i = 0; i < pl->vtxList.size(); i++) vertex_ids[i] = pl->vtxList[i];
     return 0;
 }
 

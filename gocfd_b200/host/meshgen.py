@@ -11,7 +11,9 @@ import numpy as np
 from .readfiles import Mesh2D
 
 
-def structured_tri_mesh(nx, ny, x0=-10.0, x1=10.0, y0=-10.0, y1=10.0, tag="wall"):
+def structured_tri_mesh(nx, ny, x0=-10.0, x1=10.0, y0=-10.0, y1=10.0, tag="wall", side_tags=None):
+    """side_tags = {"bottom": .., "right": .., "top": .., "left": ..} overrides `tag` per side (e.g. the shock-tube
+    layout of test_cases/Euler2D/shock-tube: left "in", right "out", top/bottom "wall")."""
     xs = np.linspace(x0, x1, nx + 1)
     ys = np.linspace(y0, y1, ny + 1)
     vx = np.tile(xs, ny + 1)
@@ -32,4 +34,9 @@ def structured_tri_mesh(nx, ny, x0=-10.0, x1=10.0, y0=-10.0, y1=10.0, tag="wall"
     s = np.arange(ny)
     right = np.stack([s * (nx + 1) + nx, (s + 1) * (nx + 1) + nx], axis=1)
     left = np.stack([(s + 1) * (nx + 1), s * (nx + 1)], axis=1)
-    return Mesh2D(vx, vy, etov, {tag: np.concatenate([bottom, right, top, left])})
+    if side_tags is None:
+        return Mesh2D(vx, vy, etov, {tag: np.concatenate([bottom, right, top, left])})
+    groups = {}
+    for name, edges in (("bottom", bottom), ("right", right), ("top", top), ("left", left)):
+        groups.setdefault(side_tags.get(name, tag), []).append(edges)
+    return Mesh2D(vx, vy, etov, {t: np.concatenate(e) for t, e in groups.items()})

@@ -50,7 +50,8 @@ EXPORTS = [
     "dfr2d_residual", "dfr2d_rhs", "dfr2d_set_register", "dfr2d_get_register", "dfr2d_get_field",
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
-    "dfr2d_step_finish", "dfr2d_launch_count",
+    "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -85,7 +86,10 @@ def load():
     lib.dfr2d_halo_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.dfr2d_halo_buffers.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.dfr2d_wavespeed_buffer.argtypes = [H, C.POINTER(C.c_void_p)]
-    for name in ("dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update"):
+    lib.dfr2d_exchange_counts.argtypes = [H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.dfr2d_exchange_buffers.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.dfr2d_plan_vertices.argtypes = [H, C.POINTER(C.c_int64), _ip]
+    for name in ("dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update", "dfr2d_stage_sensor", "dfr2d_stage_visc"):
         getattr(lib, name).argtypes = [H, C.c_int]
     lib.dfr2d_step_finish.argtypes = [H, C.POINTER(StepInfo)]
     lib.dfr2d_launch_count.argtypes = [H]
@@ -244,6 +248,25 @@ class Dfr2d:
         self._ck(self.lib.dfr2d_wavespeed_buffer(self.h, C.byref(p)))
         return p.value
 
+    XCHG_EDGE, XCHG_VERTEX, XCHG_DISS = 0, 1, 2
+
+    def exchange_counts(self, which):
+        s = (C.c_int64 * self.n_parts)()
+        r = (C.c_int64 * self.n_parts)()
+        self._ck(self.lib.dfr2d_exchange_counts(self.h, which, s, r))
+        return list(s), list(r)
+
+    def exchange_buffers(self, which):
+        s, r = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.dfr2d_exchange_buffers(self.h, which, C.byref(s), C.byref(r)))
+        return s.value, r.value
+
+    def stage_sensor(self, rk):
+        self._ck(self.lib.dfr2d_stage_sensor(self.h, rk))
+
+    def stage_visc(self, rk):
+        self._ck(self.lib.dfr2d_stage_visc(self.h, rk))
+
     def stage_prepare(self, rk):
         self._ck(self.lib.dfr2d_stage_prepare(self.h, rk))
 
@@ -296,6 +319,11 @@ class Plan:
             lib.dfr2d_plan_halo(h, self.send_counts.ctypes.data_as(lp), self.recv_counts.ctypes.data_as(lp),
                                 self.ghost_global.ctypes.data_as(lp), _i(self.send_elem), _i(self.send_row0),
                                 _i(self.recv_col), _i(self.recv_row0))
+            self.vertex_counts = np.zeros(n_parts, np.int64)
+            lib.dfr2d_plan_vertices(h, self.vertex_counts.ctypes.data_as(lp), None)
+            self.vertex_ids = np.zeros(max(int(self.vertex_counts.sum()) // 2, 1), np.int32)
+            lib.dfr2d_plan_vertices(h, self.vertex_counts.ctypes.data_as(lp), _i(self.vertex_ids))
+            self.vertex_ids = self.vertex_ids[:int(self.vertex_counts.sum()) // 2]
             for name in ("ghost_global",):
                 setattr(self, name, getattr(self, name)[:self.G])
             for name in ("send_elem", "send_row0", "recv_col", "recv_row0"):

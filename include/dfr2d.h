@@ -157,6 +157,20 @@ int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **dev_two_doubles);
 int dfr2d_stage_prepare(dfr2d_handle *h, int rk); /* edge interpolation if stale + pack the halo send buffer */
 int dfr2d_stage_edges(dfr2d_handle *h, int rk);   /* unpack halo + numerical edge fluxes + wave-speed maxima */
 int dfr2d_stage_update(dfr2d_handle *h, int rk);  /* divergence, dt, SSP-RK update (+ next stage's interpolation) */
+/* With the PerssonC0 limiter a stage has three exchange points instead of one:
+ *   dfr2d_stage_sensor  [sensor, element->vertex max merge, pack]           -> exchange DFR2D_XCHG_VERTEX
+ *   dfr2d_stage_prepare [unpack(max), vertex->element, limiter, interp, pack] -> exchange DFR2D_XCHG_EDGE
+ *   dfr2d_stage_edges   [unpack, edge flux, RT gradient x epsilon, pack]    -> exchange DFR2D_XCHG_DISS
+ *   dfr2d_stage_visc    [unpack, viscous edge flux]  -> MAX-allreduce of the wave-speed pair -> dfr2d_stage_update
+ * (phases P1-P8 of StepWorker, euler.go:574-651; the goroutines' shared memory becomes these messages).
+ * stage_sensor / stage_visc are no-ops without the limiter, so a host may always call all five. */
+enum { DFR2D_XCHG_EDGE = 0, DFR2D_XCHG_VERTEX = 1, DFR2D_XCHG_DISS = 2 };
+int dfr2d_stage_sensor(dfr2d_handle *h, int rk);
+int dfr2d_stage_visc(dfr2d_handle *h, int rk);
+/* per-peer doubles (arrays of n_parts; every exchange is symmetric) and device buffers of exchange `which`;
+ * which = DFR2D_XCHG_EDGE gives the same answers as dfr2d_halo_counts / dfr2d_halo_buffers */
+int dfr2d_exchange_counts(const dfr2d_handle *h, int which, int64_t *send_counts, int64_t *recv_counts);
+int dfr2d_exchange_buffers(dfr2d_handle *h, int which, void **send_dev, void **recv_dev);
 int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info); /* after stage 4: read back time/steps (info may be NULL) */
 
 /* ---- host-only partition plan (no CUDA): the bookkeeping dfr2d_create performs for (n_parts, part), exposed so
@@ -174,6 +188,9 @@ int dfr2d_plan_edges(const dfr2d_plan *pl, int32_t *kL, int32_t *kR, int32_t *me
  * receive (ghost column,row0) addresses inside Q_Face; message order = (peer, global edge index) */
 int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64_t *recv_counts, int64_t *ghost_global,
                     int32_t *send_elem, int32_t *send_row0, int32_t *recv_col, int32_t *recv_row0);
+/* dissipation only: shared vertices grouped by peer (ascending global vertex id within a peer); counts are doubles
+ * per peer (2 per vertex: sigma, epsilon).  vertex_ids may be NULL to query the counts first. */
+int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_t *vertex_ids);
 
 /* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
 int64_t dfr2d_launch_count(const dfr2d_handle *h);

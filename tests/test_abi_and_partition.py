@@ -135,3 +135,46 @@ def test_two_rank_gloo_exchange():
     for pr, out in zip(procs, outs):
         assert pr.returncode == 0, out
         assert "OK" in out, out
+
+
+@pytest.mark.parametrize("mesh_name,n_parts", [("sod", 2), ("sod", 3), ("naca", 5), ("naca", 8)])
+def test_shared_vertex_plan_reproduces_the_global_vertex_max(mesh_name, n_parts):
+    """Dissipation across partitions: the per-peer shared-vertex lists are exactly the pairwise
+    intersections of the partitions' vertex sets, both sides agree on the order, and local max + exchange + max equals
+    MergeElementScalarToVertices over the whole mesh (euler.go:1048-1065)."""
+    from gocfd_b200 import lib
+    if mesh_name == "sod":
+        c = _case(2, mesh_path("sod-aligned-100pts.su2"), InitType="shocktube", Limiter="persson c0", Kappa=5.0)
+    else:
+        c = _case(2, mesh_path("mesh_NACA0012_inv.su2"), InitType="Freestream", Minf=0.8, Limiter="PerssonC0")
+    p = c.problem
+    assert p.Dissipation
+    plans = [lib.Plan(p, n_parts, r) for r in range(n_parts)]
+    ne = p.NpEdge
+    touched = [set(np.unique(p.EToV[pl.k0:pl.k1]).tolist()) for pl in plans]
+    rng = np.random.default_rng(3)
+    elem_val = rng.random(p.K)
+    want = np.zeros(p.NV)
+    np.maximum.at(want, p.EToV.reshape(-1), np.repeat(elem_val, 3))
+    local = []
+    for pl in plans:
+        v = np.zeros(p.NV)
+        np.maximum.at(v, p.EToV[pl.k0:pl.k1].reshape(-1), np.repeat(elem_val[pl.k0:pl.k1], 3))
+        local.append(v)
+    merged = [v.copy() for v in local]
+    for r, pl in enumerate(plans):
+        # Q_Face message carries 3 extra doubles (vertex epsilon of the sender's element) per cut edge
+        if pl.n_cut:
+            assert int(pl.send_counts.sum()) == pl.n_cut * (4 * ne + 3)
+        off = np.concatenate([[0], np.cumsum(pl.vertex_counts // 2)])
+        assert pl.vertex_counts[r] == 0
+        for s in range(n_parts):
+            ids = pl.vertex_ids[off[s]:off[s + 1]]
+            assert ids.tolist() == sorted(touched[r] & touched[s]) if s != r else len(ids) == 0
+            # what r sends to s is what s expects from r, in the same order
+            offs = np.concatenate([[0], np.cumsum(plans[s].vertex_counts // 2)])
+            assert np.array_equal(ids, plans[s].vertex_ids[offs[r]:offs[r + 1]])
+            np.maximum.at(merged[s], ids, local[r][ids])
+    for r in range(n_parts):
+        mine = sorted(touched[r])
+        assert np.array_equal(merged[r][mine], want[mine])

@@ -219,30 +219,50 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
+class _Exchange:
+    """One exchange point of the per-stage protocol (bench.py does the same with NCCL all_to_all_single);
+    here every partition lives on the same device and the bytes move by device copies."""
+
+    def __init__(self, devs, which):
+        import torch
+        self.n = len(devs)
+        self.counts = [d.exchange_counts(which) for d in devs]
+        self.bufs = []
+        for d, (sc, rc) in zip(devs, self.counts):
+            sp, rp = d.exchange_buffers(which)
+            self.bufs.append((torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda") if sum(sc) else None,
+                              torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda") if sum(rc) else None))
+        self.soff = [np.concatenate([[0], np.cumsum(c[0])]).astype(int) for c in self.counts]
+        self.roff = [np.concatenate([[0], np.cumsum(c[1])]).astype(int) for c in self.counts]
+
+    def run(self):
+        for r in range(self.n):
+            for s in range(self.n):
+                cnt = self.counts[r][0][s]
+                if cnt:
+                    assert self.counts[s][1][r] == cnt
+                    self.bufs[s][1][self.roff[s][r]:self.roff[s][r] + cnt] = \
+                        self.bufs[r][0][self.soff[r][s]:self.soff[r][s] + cnt]
+
+
 def _multi_partition_step(devs, nsteps):
     """The per-stage protocol of bench.py with the NCCL calls replaced by same-device copies."""
     import torch
-    n = len(devs)
-    counts = [d.halo_counts() for d in devs]
-    bufs = []
-    for d, (sc, rc) in zip(devs, counts):
-        sp, rp = d.halo_buffers()
-        bufs.append((torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda"),
-                     torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda")))
-    soff = [np.concatenate([[0], np.cumsum(c[0])]).astype(int) for c in counts]
-    roff = [np.concatenate([[0], np.cumsum(c[1])]).astype(int) for c in counts]
+    xe, xv, xd = (_Exchange(devs, w) for w in (0, 1, 2))
+    assert xe.counts == [d.halo_counts() for d in devs]
     for _ in range(nsteps):
         for rk in range(5):
             for d in devs:
+                d.stage_sensor(rk)
+            xv.run()
+            for d in devs:
                 d.stage_prepare(rk)
-            for r in range(n):
-                for s in range(n):
-                    cnt = counts[r][0][s]
-                    if cnt:
-                        assert counts[s][1][r] == cnt
-                        bufs[s][1][roff[s][r]:roff[s][r] + cnt] = bufs[r][0][soff[r][s]:soff[r][s] + cnt]
+            xe.run()
             for d in devs:
                 d.stage_edges(rk)
+            xd.run()
+            for d in devs:
+                d.stage_visc(rk)
             waves = [torch.as_tensor(_DevArray(d.wavespeed_buffer(), 2), device="cuda") for d in devs]
             gmax = torch.stack(waves).max(dim=0).values.clone()
             for w in waves:
@@ -296,4 +316,60 @@ def test_multi_partition_naca_local_dt():
         d.get_state(q)
     assert rel_l2(q, ora.get_state()) < TOL
     for d in devs:
+        d.close()
+
+
+@pytest.mark.parametrize("n_parts,n", [(2, 2), (3, 4), (4, 1)])
+def test_multi_partition_sod_with_dissipation(n_parts, n):
+    """PerssonC0 across partitions -- shared-vertex max merge, Q_Face + ghost vertex epsilon,
+    DissX/DissY edge rows.  Bitwise equal to the single-partition device run, 1e-11 against the oracle."""
+    from gocfd_b200 import lib
+    from oracle.euler2d_oracle import OracleSolver
+    c = _sod(n, CFL=2.0)
+    c.Q = _smeared_sod_state(c, 0.004 if n == 1 else 0.002)
+    ora = OracleSolver(c.problem)
+    ora.set_state(c.Q)
+    devs = [lib.Dfr2d(c.problem, n_parts=n_parts, part=r) for r in range(n_parts)]
+    assert sum(sum(d.exchange_counts(1)[0]) for d in devs) > 0 and sum(sum(d.exchange_counts(2)[0]) for d in devs) > 0
+    for d in devs:
+        d.set_state(c.Q)
+    infos = _multi_partition_step(devs, 3)
+    ora.step(1)
+    assert ora.SigmaScalar.max() > 0.05, "the sensor must be active for this test to mean anything"
+    b = ora.step(2)
+    q = np.zeros_like(c.Q)
+    for d in devs:
+        d.get_state(q)
+    assert rel_l2(q, ora.get_state()) < TOL
+    for i in infos:
+        assert i["steps"] == 3 and abs(i["time"] - b["time"]) <= 1e-12 * b["time"]
+    one = lib.Dfr2d(c.problem)
+    one.set_state(c.Q)
+    one.step(3)
+    assert np.array_equal(one.get_state(), q)
+    sig = np.zeros(c.problem.K)
+    for d in devs:
+        sig[d.partition_range()[0]:d.partition_range()[1]] = d.get_field(1)[d.partition_range()[0]:d.partition_range()[1]]
+    assert np.array_equal(sig, one.get_field(1))
+    for d in devs + [one]:
+        d.close()
+
+
+def test_multi_partition_naca_transonic_dissipation_local_dt():
+    """Unstructured numbering (large, irregular cuts; vertices shared by 3+ partitions), local dt + DTVisc carry-over."""
+    from gocfd_b200 import lib
+    c = make(dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=12, Minf=0.8, Alpha=2.0,
+                  Limiter="PerssonC0", Kappa=4.5), mesh_path("mesh_NACA0012_inv.su2"))
+    devs = [lib.Dfr2d(c.problem, n_parts=5, part=r) for r in range(5)]
+    for d in devs:
+        d.set_state(c.Q)
+    _multi_partition_step(devs, 8)
+    q = np.zeros_like(c.Q)
+    for d in devs:
+        d.get_state(q)
+    one = lib.Dfr2d(c.problem)
+    one.set_state(c.Q)
+    one.step(8)
+    assert np.array_equal(one.get_state(), q)
+    for d in devs + [one]:
         d.close()
