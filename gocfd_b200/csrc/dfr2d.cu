@@ -13,6 +13,7 @@
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
 #include "dfr2d_elem_pipe.cuh"
+#include "dfr2d_elem_tma.cuh"
 
 using namespace dfr2d;
 
@@ -64,6 +65,7 @@ struct dfr2d_handle {
     double *mmaFrags = nullptr;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
+    int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
     int edgePPT = 0;
 };
 
@@ -544,8 +546,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->sms = sms;
     // measured on B200 (profiles/r01c_*): the pipelined DMMA kernel wins at N = 4 (6.6 vs 8.1 ms), the row-per-thread DFMA kernel
     // at N <= 3 (small operators: DMMA padding waste, fewer tiles per persistent CTA)
-    h->elemKernel = (N >= 4) ? 4 : 1;
+    h->elemKernel = (N >= 4) ? 5 : 1;
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
+    if (const char *ev = getenv("DFR2D_TMA_STAGES")) h->tmaStages = atoi(ev);
     {
         std::vector<double> fr;
         switch (N) {
@@ -785,6 +788,26 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
             k_elem<NN, true><<<blocks, kElemThreads, sm, h->stream>>>(a);
         });
     } else {
+        if (h->elemKernel == 5) {
+            ElemTmaArgs ta{};
+            ta.a = a;
+            ta.nTiles = blocks;
+            ta.nExtra = (rk == 0 || rhsOut != nullptr) ? 0 : (rk == 4 ? 4 : 1);
+            DISPATCH_N(h->N, {
+                using TD = TmaDim<NN>;
+                const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words
+                int stages = (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1));
+                stages = std::max(1, std::min(stages, kTmaMaxStages));
+                if (h->tmaStages > 0) stages = std::min(stages, h->tmaStages);
+                ta.nStages = stages;
+                const size_t sm = TD::smem_bytes(ta.nExtra, stages);
+                if (!h->smemAttrSet)
+                    cudaFuncSetAttribute(k_elem_tma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                k_elem_tma<NN><<<std::min(blocks, h->sms), kTmaThreads, sm, h->stream>>>(ta);
+            });
+            h->smemAttrSet = true;
+            return launch_check(h, "k_elem_tma");
+        }
         if (h->elemKernel == 4) {
             ElemMmaArgs ma{};
             ma.a = a;

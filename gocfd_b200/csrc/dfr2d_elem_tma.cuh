@@ -1,0 +1,460 @@
+// k_elem_tma<N>: the inviscid element kernel as a warp-specialised producer/consumer pipeline (kernel #5).
+//
+// What the measurements of kernel #4 (k_elem_pipe) said (profiles/r01e_*): per 32-element tile an SM spent
+// ~7,700 cycles = (HBM time of the tile's 97 KB at the SM's bandwidth share, ~4,400) + (DMMA floor, ~2,150) + (flux and
+// epilogue ALU work) -- the parts ADD because every warp does all of them in lock-step phases separated by CTA
+// barriers, so when HBM back-pressures the LSU queue the tensor pipe idles and vice versa.  Here they overlap:
+//
+//   * ONE producer warp per CTA moves every byte asynchronously: the [row][32 elements] slabs of the stage input, of the
+//     RK registers and of the metrics arrive by bulk async copies (cp.async.bulk, the TMA engine, one 256-byte row per
+//     copy so that smem rows can keep the bank-conflict-free stride of 36 doubles), the edge-flux gather by 8-byte
+//     cp.async; both complete on the stage's mbarrier.  No load ever occupies a register or an issue slot of a warp
+//     that does arithmetic.
+//   * 8 consumer warps work in two groups of 4 on two different tiles; inside a group every warp owns 8 columns
+//     (= one DMMA n-tile) of the tile for ALL four conserved variables and never synchronises with another warp:
+//     no __syncthreads in the steady state, phases of different warps drift apart and fill each other's bubbles.
+//   * The physical flux is evaluated directly in B-fragment layout: lane (fr, fc) of the m8n8k4 DMMA holds B[k = fc][n = fr],
+//     so it evaluates point p = 4m + fc of element fr once and feeds Fr to k-step 2m and Fs to k-step 2m+1 for all four
+//     variables (the k-order of the contraction is permuted accordingly in the operator fragments).  F_RT_DOF never
+//     exists in shared memory; the operator fragments (A operands) stay in registers for the whole kernel.
+//   * The fresh register is written in place into the warp's own columns of the stage-input slab, which then serves as
+//     the B operand of the fused FluxEdgeInterp contraction (next stage's Q_Face).
+//
+// Reference semantics are those of k_elem_pipe / k_elem (SetRTFluxInternal euler.go:701-726, SetRTFluxOnEdges
+// edges.go:454-483, RHSInternalPoints euler.go:665-699, rkAdvance :502-565, InterpolateSolutionToEdges edges.go:485-491).
+#pragma once
+#include "dfr2d_elem_mma.cuh"
+
+namespace dfr2d {
+
+constexpr int kTmaConsWarps = 8;                         // two groups of four
+constexpr int kTmaProdWarps = 4;                         // warp 0: row slabs + dt; warps 1-3: gather of local edge 0-2
+constexpr int kTmaThreads = (kTmaConsWarps + kTmaProdWarps) * 32;   // 12 warps: registers are allotted per 4 warps
+constexpr int kTmaFullCount = kTmaProdWarps * 64;        // per producer lane: its cp.async completions + one plain arrive
+constexpr int kTmaMaxStages = 6;
+
+template <int N> struct TmaDim {
+    static constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
+    static constexpr int SE = 36;                                  // row stride of the slabs (doubles): 4 k-rows x 8 n conflict free
+    static constexpr int M1 = (NI + 7) / 8, KI = (NI + 3) / 4, KE = (NF3 + 3) / 4, K1 = 2 * KI + KE;
+    static constexpr int M2 = (NF3 + 7) / 8, K2 = (NI + 3) / 4;
+    static constexpr int qOff = 0;                                 // [4 NI][SE] stage input
+    static constexpr int eOff = 4 * NI * SE;                       // [4 NF3][SE] gathered numerical edge flux (raw)
+    static constexpr int gOff = eOff + 4 * NF3 * SE;               // [9][32]: Jdet, Jinv0..3, (+-)IInII0..2, dt
+    static constexpr int xOff = gOff + 9 * 32;                     // [nExtra][4 NI][SE]: q0 (, q2, q3, R)
+    static constexpr int xSize = 4 * NI * SE;
+    static int stage_doubles(int nExtra) { return xOff + nExtra * xSize; }
+    static size_t smem_bytes(int nExtra, int stages) { return (size_t)stage_doubles(nExtra) * stages * sizeof(double); }
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+// global -> shared bulk async copy (TMA engine), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(double *dst, const double *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(unsigned dst, const double *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16_u32(unsigned dst, const double *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+// one [rows][32] slab of a [.][Kp] array -> shared rows of stride SE: every warp instruction moves two full 256-byte rows
+template <int ROWS, int SE_>
+__device__ __forceinline__ void slab_g2s(unsigned dstBase, const double *srcBase, size_t Kp, int lane) {
+    const int half = lane >> 4, ch = lane & 15;
+    const double *src = srcBase + (size_t)half * Kp + 2 * ch;
+    unsigned d = dstBase + (unsigned)((half * SE_ + 2 * ch) * sizeof(double));
+#pragma unroll 5
+    for (int r = 0; r < ROWS; r += 2) {
+        if (ROWS % 2 == 0 || r + half < ROWS) cp_async16_u32(d, src);
+        src += 2 * Kp;
+        d += (unsigned)(2 * SE_ * sizeof(double));
+    }
+}
+__device__ __forceinline__ void cp_async8_u32(unsigned dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all cp.async issued so far by this thread have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct ElemTmaArgs {
+    ElemArgs a;
+    int nTiles, nStages, nExtra;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
+    using TD = TmaDim<N>;
+    constexpr int NI = TD::NI, NEd = TD::NEd, NF3 = TD::NF3, SE = TD::SE, E = kElemsPerBlock;
+    constexpr int M1 = TD::M1, KI = TD::KI, KE = TD::KE, K1 = TD::K1, M2 = TD::M2, K2 = TD::K2;
+    const ElemArgs &a = args.a;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) {
+        if (a.rk == 4 && a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+            a.sc->time[a.par ^ 1] = a.sc->time[a.par];
+            a.sc->finished = 1;
+        }
+        return;
+    }
+    extern __shared__ __align__(128) double smem_tma[];
+    double *smem = smem_tma;
+    __shared__ __align__(8) unsigned long long fullBar[kTmaMaxStages], emptyBar[kTmaMaxStages];
+    const int S = args.nStages, nExtra = args.nExtra;
+    const int stageDoubles = TD::xOff + nExtra * TD::xSize;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t Kp = a.Kp;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&fullBar[s], kTmaFullCount);
+            mbar_init(&emptyBar[s], 4);              // the four consumer warps of the tile
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // the two operators pass through shared memory once (the ring is not in use yet) so that every consumer lane can
+    // pick its A-fragment entries with lane-dependent indices without serialised constant-bank reads
+    {
+        const Ops<N> &op = ops<N>();
+        constexpr int NFL = Dim<N>::NpFlux;
+        for (int t = threadIdx.x; t < NI * NFL; t += kTmaThreads) smem[t] = op.DivInt[t / NFL][t % NFL];
+        for (int t = threadIdx.x; t < NF3 * NI; t += kTmaThreads) smem[NI * NFL + t] = op.FEI[t / NI][t % NI];
+    }
+    __syncthreads();
+
+    double dtGlobal = 0.0;
+    if (!a.ph.localDT) {
+        const double gw = __longlong_as_double((long long)a.sc->wave[a.slot][0]);
+        dtGlobal = a.ph.CFL / gw;
+        const double t = a.sc->time[a.par];
+        if (t + dtGlobal > a.ph.FinalTime) dtGlobal = a.ph.FinalTime - t;
+    }
+    const int nLocal = (args.nTiles > (int)blockIdx.x) ? (args.nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (warp >= kTmaConsWarps) {
+        // =================================== producer warps ==================================================
+        // 168 registers per thread are allotted at launch (12 warps x 168 x 32 = 64,512); the producers keep 56 and
+        // hand the rest to the consumers (setmaxnreg, 4 x 56 + 8 x 224 = the same total)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int pw = warp - kTmaConsWarps;
+        if (pw == 0) {
+            // ---- row slabs by the TMA engine; dt per element (lane = element) -------------------------------------
+            int c0 = 0, c1 = 0, c2 = 0;
+            double g0 = 0, g1 = 0, g2 = 0, dtOld = 0;
+            auto load_dt = [&](int n) {
+                if (a.ph.localDT && n < nLocal) {
+                    const size_t kk = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E + lane;
+                    c0 = a.etoe[kk]; c1 = a.etoe[Kp + kk]; c2 = a.etoe[2 * Kp + kk];
+                    g0 = a.agg[c0 >= 0 ? c0 : -1 - c0]; g1 = a.agg[c1 >= 0 ? c1 : -1 - c1]; g2 = a.agg[c2 >= 0 ? c2 : -1 - c2];
+                    dtOld = a.DT[kk];
+                }
+            };
+            load_dt(0);
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");      // consumers hold their operator fragments
+            int s = 0;
+            unsigned ph = 1;                        // parity of the previous phase of emptyBar[s]
+            for (int n = 0; n < nLocal; n++) {
+                if (n >= S) mbar_wait(&emptyBar[s], ph);
+                const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
+                double *st = smem + (size_t)s * stageDoubles;
+                const unsigned stU = smem_u32(st);
+                // stage input, the stage-3 residual (rk 4) and the metrics: coalesced 16-byte async copies
+                slab_g2s<4 * NI, SE>(stU + (unsigned)(TD::qOff * sizeof(double)), a.qs + k0, Kp, lane);
+                if (nExtra == 4) slab_g2s<4 * NI, SE>(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)), a.R + k0, Kp, lane);
+                if (lane < 16) cp_async16_u32(stU + (unsigned)((TD::gOff + 2 * lane) * sizeof(double)), a.Jdet + k0 + 2 * lane);
+                slab_g2s<4, 32>(stU + (unsigned)((TD::gOff + 32) * sizeof(double)), a.Jinv + k0, Kp, lane);
+                double dtk = dtGlobal;
+                if (a.ph.localDT) {
+                    const double wmaxk = fmax(fmax(g0, g1), g2);
+                    const double d = (a.rk == 0) ? -100.0 : dtOld;
+                    dtk = a.ph.CFL / fmax(d, wmaxk);
+                    if (a.rhsOut == nullptr) a.DT[k0 + lane] = dtk;
+                }
+                st[TD::gOff + 8 * 32 + lane] = dtk;
+                cp_async_arrive_noinc(&fullBar[s]);
+                mbar_arrive(&fullBar[s]);
+                load_dt(n + 1);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        } else {
+            // ---- gather of the numerical flux of local edge `le` of every element of the tile (lane = element): the
+            // source walks the edge's rows upwards (one pointer increment per copy), the destination row runs up for
+            // the owner and down (reversed point order) for the neighbour; sign x IInII of SetRTFluxOnEdges
+            // (edges.go:469-479) goes along as a per-element scale
+            const int le = pw - 1;
+            int cs = 0, ns = 0, ns2 = 0;            // edge slot of tile n, n+1, n+2 (loads are issued three tiles ahead)
+            double iin = 0.0, iinN = 0.0;           // IInII of tile n, n+1 (two tiles ahead)
+            auto load_slot = [&](int n, int &sl) {
+                if (n < nLocal) sl = a.etoe[(size_t)le * Kp + (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E + lane];
+            };
+            auto load_iin = [&](int n, double &v) {
+                if (n < nLocal) v = a.IInII[(size_t)le * Kp + (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E + lane];
+            };
+            load_slot(0, cs);
+            load_iin(0, iin);
+            load_slot(1, ns);
+            load_iin(1, iinN);
+            load_slot(2, ns2);
+            asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");
+            const size_t srcStep = (size_t)a.NEp;
+            int s = 0;
+            unsigned ph = 1;                        // parity of the previous phase of emptyBar[s]
+            for (int n = 0; n < nLocal; n++) {
+                if (n >= S) mbar_wait(&emptyBar[s], ph);
+                double *st = smem + (size_t)s * stageDoubles;
+                if (le < (nExtra == 4 ? 3 : nExtra)) {
+                    // RK register slab number `le` of this stage (q0, q2, q3); R travels with the stage input in warp 0
+                    const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
+                    slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((TD::xOff + le * TD::xSize) * sizeof(double)),
+                                         (le == 0 ? a.q0 : (le == 1 ? a.q2 : a.q3)) + k0, Kp, lane);
+                }
+                const bool own = cs >= 0;
+                st[TD::gOff + (5 + le) * 32 + lane] = own ? iin : -iin;
+                const double *src = a.eflux + (own ? cs : -1 - cs);
+                const int dStep = own ? (int)(SE * sizeof(double)) : -(int)(SE * sizeof(double));
+                const unsigned seU = smem_u32(st) + (unsigned)((TD::eOff + lane + (le * NEd + (own ? 0 : NEd - 1)) * SE) * sizeof(double));
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    unsigned d = seU + (unsigned)(v * NF3 * SE * sizeof(double));
+#pragma unroll
+                    for (int i = 0; i < NEd; i++) {
+                        cp_async8_u32(d, src);
+                        src += srcStep;
+                        d += dStep;
+                    }
+                }
+                cp_async_arrive_noinc(&fullBar[s]);
+                mbar_arrive(&fullBar[s]);
+                cs = ns; ns = ns2; iin = iinN;
+                load_iin(n + 2, iinN);
+                load_slot(n + 3, ns2);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // =================================== consumer warps ==================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int group = warp >> 2, wq = warp & 3;
+        const int fr = lane >> 2, fc = lane & 3;
+        const int eB = 8 * wq + fr;                  // B-operand column of this lane
+        const int eC = 8 * wq + 2 * fc;              // first of the two accumulator columns of this lane
+        constexpr int NFL = Dim<N>::NpFlux;
+        const double *opD = smem, *opF = smem + NI * NFL;
+        // operator fragments, A[row = fr][k = fc] of every (m-tile, k-step); k-steps 2m / 2m+1 carry Fr / Fs of points
+        // 4m..4m+3, k-steps 2KI.. the edge rows
+        double a1[M1][K1], a2[M2][K2];
+#pragma unroll
+        for (int mt = 0; mt < M1; mt++) {
+            const int row = 8 * mt + fr;
+#pragma unroll
+            for (int m = 0; m < KI; m++) {
+                const int p = 4 * m + fc;
+                const bool ok = row < NI && p < NI;
+                a1[mt][2 * m] = ok ? opD[row * NFL + p] : 0.0;
+                a1[mt][2 * m + 1] = ok ? opD[row * NFL + NI + p] : 0.0;
+            }
+#pragma unroll
+            for (int ke = 0; ke < KE; ke++) {
+                const int r = 4 * ke + fc;
+                a1[mt][2 * KI + ke] = (row < NI && r < NF3) ? opD[row * NFL + 2 * NI + r] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < M2; mt++) {
+            const int row = 8 * mt + fr;
+#pragma unroll
+            for (int ks = 0; ks < K2; ks++) {
+                const int j = 4 * ks + fc;
+                a2[mt][ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");      // operator table consumed: the ring may be filled
+        bool bad = false;
+        double *dst = (a.rk == 0) ? a.q1 : (a.rk == 1) ? a.q2 : (a.rk == 2) ? a.q3 : (a.rk == 3) ? a.q4 : a.q0;
+
+        int s = group % S;
+        unsigned ph = (unsigned)((group / S) & 1);
+        for (int n = group; n < nLocal; n += 2) {
+            const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
+            double *st = smem + (size_t)s * stageDoubles;
+            double *sQ = st + TD::qOff;
+            const double *sE = st + TD::eOff, *g = st + TD::gOff;
+            mbar_wait(&fullBar[s], ph);
+
+            // ---- C1 = DivInt . F_RT_DOF with the flux evaluated in B-fragment layout ----------------------------
+            const double jd = g[eB], j0 = g[32 + eB], j1 = g[64 + eB], j2 = g[96 + eB], j3 = g[128 + eB];
+            const double sc0 = g[5 * 32 + eB], sc1 = g[6 * 32 + eB], sc2 = g[7 * 32 + eB];
+            double c1[4][M1][2];
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+#pragma unroll
+                for (int mt = 0; mt < M1; mt++) c1[v][mt][0] = c1[v][mt][1] = 0.0;
+#pragma unroll
+            for (int m = 0; m < KI; m++) {
+                const int p = 4 * m + fc;
+                double Fr[4] = {0.0, 0.0, 0.0, 0.0}, Fs[4] = {0.0, 0.0, 0.0, 0.0};
+                if (4 * m + 3 < NI || p < NI) {
+                    double Q[4], Fx[4], Fy[4];
+#pragma unroll
+                    for (int v = 0; v < 4; v++) Q[v] = sQ[(v * NI + p) * SE + eB];
+                    flux_calc(a.ph.gamma, Q, Fx, Fy);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        Fr[v] = jd * (j0 * Fx[v] + j1 * Fy[v]);
+                        Fs[v] = jd * (j2 * Fx[v] + j3 * Fy[v]);
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) dmma884(c1[v][mt][0], c1[v][mt][1], a1[mt][2 * m], Fr[v]);
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) dmma884(c1[v][mt][0], c1[v][mt][1], a1[mt][2 * m + 1], Fs[v]);
+            }
+#pragma unroll
+            for (int ke = 0; ke < KE; ke++) {
+                const int r = 4 * ke + fc;
+                double b[4] = {0.0, 0.0, 0.0, 0.0};
+                if (4 * ke + 3 < NF3 || r < NF3) {
+                    const int le = (r >= NEd) + (r >= 2 * NEd);
+                    const double scl = pick3(le, sc0, sc1, sc2);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) b[v] = sE[(v * NF3 + r) * SE + eB] * scl;
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) dmma884(c1[v][mt][0], c1[v][mt][1], a1[mt][2 * KI + ke], b[v]);
+            }
+
+            // ---- epilogue in accumulator layout: rows 8 mt + fr, columns eC, eC + 1 ------------------------------
+            const double2 jdc = *reinterpret_cast<const double2 *>(&g[eC]);
+            const double2 dt = *reinterpret_cast<const double2 *>(&g[8 * 32 + eC]);
+            const double mo0 = -(1.0 / jdc.x), mo1 = -(1.0 / jdc.y);
+            const double *sX = st + TD::xOff;
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+#pragma unroll
+                for (int mt = 0; mt < M1; mt++) {
+                    const int i = 8 * mt + fr;
+                    if (i < NI) {
+                        const double rhs0 = c1[v][mt][0] * mo0, rhs1 = c1[v][mt][1] * mo1;
+                        const size_t o = ((size_t)v * NI + i) * Kp + k0 + eC;
+                        if (a.rhsOut != nullptr) {
+                            *reinterpret_cast<double2 *>(a.rhsOut + o) = make_double2(rhs0, rhs1);
+                            continue;
+                        }
+                        const int so = (v * NI + i) * SE + eC;
+                        const double2 qs = *reinterpret_cast<const double2 *>(&sQ[so]);
+                        double2 qn;
+                        if (a.rk == 0) {
+                            qn.x = qs.x + RK0_A * (dt.x * rhs0);
+                            qn.y = qs.y + RK0_A * (dt.y * rhs1);
+                        } else if (a.rk < 4) {
+                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[so]);
+                            const double ca = (a.rk == 1) ? RK1_A : (a.rk == 2) ? RK2_A : RK3_A;
+                            const double cb = (a.rk == 1) ? RK1_B : (a.rk == 2) ? RK2_B : RK3_B;
+                            const double cc = (a.rk == 1) ? RK1_C : (a.rk == 2) ? RK2_C : RK3_C;
+                            qn.x = ca * q0v.x + cb * qs.x + cc * (dt.x * rhs0);
+                            qn.y = ca * q0v.y + cb * qs.y + cc * (dt.y * rhs1);
+                            if (a.rk == 3) *reinterpret_cast<double2 *>(a.R + o) = make_double2(rhs0, rhs1);
+                        } else {
+                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[so]);
+                            const double2 q2v = *reinterpret_cast<const double2 *>(&sX[so + 1 * TD::xSize]);
+                            const double2 q3v = *reinterpret_cast<const double2 *>(&sX[so + 2 * TD::xSize]);
+                            const double2 rv = *reinterpret_cast<const double2 *>(&sX[so + 3 * TD::xSize]);
+                            double2 r;
+                            r.x = -q0v.x + RK4_A * q2v.x + RK4_B * q3v.x + RK4_C * qs.x + RK4_D * (dt.x * rv.x) + RK4_E * (dt.x * rhs0);
+                            r.y = -q0v.y + RK4_A * q2v.y + RK4_B * q3v.y + RK4_C * qs.y + RK4_D * (dt.y * rv.y) + RK4_E * (dt.y * rhs1);
+                            qn.x = q0v.x + r.x;
+                            qn.y = q0v.y + r.y;
+                            *reinterpret_cast<double2 *>(a.R + o) = r;
+                        }
+                        bad |= (qn.x != qn.x) || (qn.y != qn.y);
+                        *reinterpret_cast<double2 *>(dst + o) = qn;
+                        *reinterpret_cast<double2 *>(&sQ[so]) = qn;      // in place: B operand of the interpolation below
+                    }
+                }
+            }
+            const bool doInterp = a.rhsOut == nullptr && a.qface != nullptr;
+            double c2[4][M2][2];
+            if (doInterp) {
+                __syncwarp();
+                // ---- C2 = FluxEdgeInterp . q_new: next stage's Q_Face ---------------------------------------------
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) c2[v][mt][0] = c2[v][mt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < K2; ks++) {
+                    const int j = 4 * ks + fc;
+                    double b[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (4 * ks + 3 < NI || j < NI) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) b[v] = sQ[(v * NI + j) * SE + eB];
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+#pragma unroll
+                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[mt][ks], b[v]);
+                }
+            }
+            // ---- the stage is consumed: hand it back to the producer (generic-proxy accesses ordered before the
+            // async-proxy refill), then stream out Q_Face from registers
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyBar[s]);
+            if (doInterp) {
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) {
+                        const int m = 8 * mt + fr;
+                        if (m < NF3)
+                            *reinterpret_cast<double2 *>(a.qface + ((size_t)v * NF3 + m) * Kp + k0 + eC) =
+                                make_double2(c2[v][mt][0], c2[v][mt][1]);
+                    }
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }      // this group's next tile is two fills further on
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+        if (bad) a.sc->nanFlag = 1;
+    }
+
+    if (a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        a.sc->wave[a.slot ^ 1][0] = 0ull;
+        a.sc->wave[a.slot ^ 1][1] = 0ull;
+        if (!a.ph.localDT) a.sc->globalDT = dtGlobal;
+        if (a.rk == 4) {
+            const double tnew = a.sc->time[a.par] + (a.ph.localDT ? a.sc->globalDT : dtGlobal);
+            a.sc->time[a.par ^ 1] = tnew;
+            a.sc->timeOut = tnew;
+            const long long st = a.sc->steps + 1;
+            a.sc->steps = st;
+            if (tnew >= a.ph.FinalTime || st >= (long long)a.ph.maxIter) a.sc->finished = 1;
+        }
+    }
+}
+
+}  // namespace dfr2d
