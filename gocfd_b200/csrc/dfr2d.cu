@@ -797,13 +797,15 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
                 using TD = TmaDim<NN>;
                 const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words
                 int stages = (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1));
-                stages = std::max(1, std::min(stages, kTmaMaxStages));
-                if (h->tmaStages > 0) stages = std::min(stages, h->tmaStages);
+                stages = std::max(2, std::min(stages, kTmaMaxStages));     // two consumer groups: a waiter may be at most one phase ahead
+                if (h->tmaStages > 1) stages = std::min(stages, h->tmaStages);
                 ta.nStages = stages;
                 const size_t sm = TD::smem_bytes(ta.nExtra, stages);
+                // (a 12-consumer-warp instantiation was measured: 152 registers per consumer spill the operator fragments,
+                // and three groups need a ring of >= 3 stages, which stage 4 does not have -- two groups of four it is)
                 if (!h->smemAttrSet)
-                    cudaFuncSetAttribute(k_elem_tma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
-                k_elem_tma<NN><<<std::min(blocks, h->sms), kTmaThreads, sm, h->stream>>>(ta);
+                    cudaFuncSetAttribute(k_elem_tma<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                k_elem_tma<NN, 8><<<std::min(blocks, h->sms), (8 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
             });
             h->smemAttrSet = true;
             return launch_check(h, "k_elem_tma");
@@ -1087,6 +1089,42 @@ extern "C" int dfr2d_get_field(dfr2d_handle *h, int which, double *out) {
     CK(cudaMemcpyAsync(out + h->k0, src, (size_t)h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_interp, int np_graph, float *out) {
+    if (!h || !graph_interp || !out) return 1;
+    const int NG = 3 * (1 + h->NpEdge) + h->NpInt;
+    if (np_graph != NG) { h->err = "GraphInterp must have 3(1+NpEdge)+NpInt rows (GetRSForGraphMesh)"; return 1; }
+    if (flow_function < 0 || flow_function > 13) {
+        h->err = "only the GetFlowFunction family (Density..Entropy, fluids.go:209-223) is evaluated on the device";
+        return 1;
+    }
+    CK(cudaSetDevice(h->device));
+    double *gi = nullptr;
+    float *dout = nullptr;
+    const size_t nOut = (size_t)h->K * NG;
+    CK(cudaMalloc(&gi, (size_t)NG * h->NpInt * sizeof(double)));
+    cudaError_t e = cudaMalloc(&dout, std::max<size_t>(nOut, 1) * sizeof(float));
+    if (e != cudaSuccess) { cudaFree(gi); h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return 2; }
+    int rc = 0;
+    e = cudaMemcpyAsync(gi, graph_interp, (size_t)NG * h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        PlotArgs pa{};
+        pa.K = h->K; pa.Kp = h->Kp; pa.ff = flow_function;
+        pa.q = h->q[0]; pa.gi = gi; pa.out = dout;
+        pa.gamma = h->ph.fs[0].Gamma; pa.Pinf = h->ph.fs[0].Pinf; pa.QQinf = h->ph.fs[0].QQinf;
+        const int blocks = (h->K + kPlotThreads - 1) / kPlotThreads;
+        DISPATCH_N(h->N, (k_plot_field<NN><<<blocks, kPlotThreads, 0, h->stream>>>(pa)));
+        rc = launch_check(h, "k_plot_field");
+        if (!rc) {
+            e = cudaMemcpyAsync(out + (size_t)h->k0 * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        }
+    }
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
+    cudaFree(gi);
+    cudaFree(dout);
+    return rc;
 }
 
 extern "C" int dfr2d_set_stream(dfr2d_handle *h, void *s) {

@@ -416,6 +416,89 @@ __global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Field read-back: Euler.GetPlotField for the GetFlowFunction family (plot.go:14-86) --
+// flow function per solution node (fluids.go:289-336), GraphInterp product (DG2D/dfr_startup.go:62-63),
+// AverageGraphFieldVertices (DG2D/graphics_support2.go:184-199), transpose to [element][graph node] and the
+// float32 narrowing of the AVS writer (DG2D/graphics_support.go:80-93), so that a plot costs one pass over the
+// state and NpGraph floats per element over PCIe instead of four float64 registers.
+// ------------------------------------------------------------------------------------------------
+struct PlotArgs {
+    int K, Kp, ff;
+    const double *q;       // [4][NpInt][Kp]
+    const double *gi;      // [NpGraph][NpInt] row-major (device copy of DFR.GraphInterp)
+    float *out;            // [K][NpGraph]
+    double gamma, Pinf, QQinf;
+};
+
+__device__ __forceinline__ double flow_function(int pf, double gamma, double Pinf, double QQinf, double rho, double rhoU,
+                                                double rhoV, double E) {
+    const double GM1 = gamma - 1.0, oorho = 1.0 / rho;
+    switch (pf) {
+        case 0: return rho;
+        case 1: return rhoU;
+        case 2: return rhoV;
+        case 3: return E;
+        case 10: return rhoU * oorho;
+        case 11: return rhoV * oorho;
+        default: break;
+    }
+    const double u = rhoU * oorho, v = rhoV * oorho;
+    const double U2 = u * u + v * v;
+    const double q = 0.5 * rho * U2;
+    const double p = GM1 * (E - q);
+    switch (pf) {
+        case 9: return sqrt(U2);
+        case 6: return q;
+        case 5: return p;
+        case 7: return (p - Pinf) / QQinf;
+        case 8: return sqrt(fabs(gamma * p * oorho));
+        case 12: return (E + p) / rho;
+        case 13: return log(p) - gamma * log(rho);
+        case 4: return sqrt(U2) / sqrt(fabs(gamma * p * oorho));
+        default: return 0.0;
+    }
+}
+
+constexpr int kPlotThreads = 128;
+
+template <int N>
+__global__ void __launch_bounds__(kPlotThreads) k_plot_field(PlotArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NG = 3 * (1 + NEd) + NI, ST = NG | 1;   // odd smem stride
+    __shared__ float sOut[kPlotThreads * ST];
+    const int kb = blockIdx.x * kPlotThreads, k = kb + threadIdx.x;
+    if (k < a.K) {
+        double f[NI];
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const size_t o = (size_t)i * a.Kp + k;
+            const size_t plane = (size_t)NI * a.Kp;
+            f[i] = flow_function(a.ff, a.gamma, a.Pinf, a.QQinf, a.q[o], a.q[plane + o], a.q[2 * plane + o], a.q[3 * plane + o]);
+        }
+        double g[NG];
+#pragma unroll
+        for (int r = 0; r < NG; r++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NI; j++) s = fma(a.gi[r * NI + j], f[j], s);
+            g[r] = s;
+        }
+        // the three vertex nodes take the mean of their two neighbours along the element boundary
+        constexpr int NPE = NEd + 2;
+#pragma unroll
+        for (int e = 0; e < 3; e++) {
+            const int iV = e * (NPE - 1), iVp = iV + 1, iVm = (e == 0) ? 3 * (NPE - 1) - 1 : e * (NPE - 1) - 1;
+            g[iV] = 0.5 * (g[iVp] + g[iVm]);
+        }
+#pragma unroll
+        for (int r = 0; r < NG; r++) sOut[threadIdx.x * ST + r] = (float)g[r];
+    }
+    __syncthreads();
+    const int nk = min(kPlotThreads, a.K - kb);
+    float *dst = a.out + (size_t)kb * NG;
+    for (int t = threadIdx.x; t < nk * NG; t += kPlotThreads) dst[t] = sOut[(t / NG) * ST + (t % NG)];
+}
+
 template <int N> static size_t elem_smem_diss() { return (size_t)12 * Dim<N>::NpInt * kElemsPerBlock * sizeof(double); }
 
 }  // namespace dfr2d

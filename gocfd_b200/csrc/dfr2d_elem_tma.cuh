@@ -27,9 +27,7 @@
 
 namespace dfr2d {
 
-constexpr int kTmaConsWarps = 8;                         // two groups of four
 constexpr int kTmaProdWarps = 4;                         // warp 0: row slabs + dt; warps 1-3: gather of local edge 0-2
-constexpr int kTmaThreads = (kTmaConsWarps + kTmaProdWarps) * 32;   // 12 warps: registers are allotted per 4 warps
 constexpr int kTmaFullCount = kTmaProdWarps * 64;        // per producer lane: its cp.async completions + one plain arrive
 constexpr int kTmaMaxStages = 6;
 
@@ -104,8 +102,11 @@ struct ElemTmaArgs {
     int nTiles, nStages, nExtra;
 };
 
-template <int N>
-__global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
+// CW = consumer warps (8: two groups of four, 224 registers each; 12: three groups, 152 registers each)
+template <int N, int CW>
+__global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemTmaArgs args) {
+    constexpr int kTmaConsWarps = CW, kTmaThreads = (CW + kTmaProdWarps) * 32, kGroups = CW / 4;
+    constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = (CW == 8) ? 224 : 152;
     using TD = TmaDim<N>;
     constexpr int NI = TD::NI, NEd = TD::NEd, NF3 = TD::NF3, SE = TD::SE, E = kElemsPerBlock;
     constexpr int M1 = TD::M1, KI = TD::KI, KE = TD::KE, K1 = TD::K1, M2 = TD::M2, K2 = TD::K2;
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
         // =================================== producer warps ==================================================
         // 168 registers per thread are allotted at launch (12 warps x 168 x 32 = 64,512); the producers keep 56 and
         // hand the rest to the consumers (setmaxnreg, 4 x 56 + 8 x 224 = the same total)
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));
         const int pw = warp - kTmaConsWarps;
         if (pw == 0) {
             // ---- row slabs by the TMA engine; dt per element (lane = element) -------------------------------------
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
         }
     } else {
         // =================================== consumer warps ==================================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsRegs));
         const int group = warp >> 2, wq = warp & 3;
         const int fr = lane >> 2, fc = lane & 3;
         const int eB = 8 * wq + fr;                  // B-operand column of this lane
@@ -293,7 +294,7 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
 
         int s = group % S;
         unsigned ph = (unsigned)((group / S) & 1);
-        for (int n = group; n < nLocal; n += 2) {
+        for (int n = group; n < nLocal; n += kGroups) {
             const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
             double *st = smem + (size_t)s * stageDoubles;
             double *sQ = st + TD::qOff;
@@ -436,8 +437,9 @@ __global__ void __launch_bounds__(kTmaThreads, 1) k_elem_tma(ElemTmaArgs args) {
                                 make_double2(c2[v][mt][0], c2[v][mt][1]);
                     }
             }
-            if (++s == S) { s = 0; ph ^= 1u; }      // this group's next tile is two fills further on
-            if (++s == S) { s = 0; ph ^= 1u; }
+#pragma unroll
+            for (int t = 0; t < kGroups; t++)       // this group's next tile is kGroups fills further on
+                if (++s == S) { s = 0; ph ^= 1u; }
         }
         if (bad) a.sc->nanFlag = 1;
     }

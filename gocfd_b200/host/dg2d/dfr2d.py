@@ -224,6 +224,25 @@ class DFR2D:
     def shock_finder(self):
         return ShockFinderMatrices(self.SolutionElement)
 
+    def graph_rs(self):
+        """GetRSForGraphMesh (DG2D/graphics_support.go:130-162): per edge the leading vertex then the RT edge
+        points, counter-clockwise, followed by the interior points -- 3(1+NpEdge)+NpInt graph nodes."""
+        rt = self.FluxElement
+        ni, ne = rt.NpInt, rt.NpEdge
+        vr, vs = [-1.0, 1.0, -1.0], [-1.0, -1.0, 1.0]
+        r, s = [], []
+        for n in range(3):
+            r.append(vr[n]); s.append(vs[n])
+            off = 2 * ni + n * ne
+            r.extend(rt.R[off:off + ne]); s.extend(rt.S[off:off + ne])
+        r.extend(rt.R[:ni]); s.extend(rt.S[:ni])
+        return np.array(r), np.array(s)
+
+    def graph_interp(self):
+        """DFR.GraphInterp = SolutionBasis.GetInterpMatrix(GraphR, GraphS) (DG2D/dfr_startup.go:62-63)."""
+        r, s = self.graph_rs()
+        return np.ascontiguousarray(self.SolutionElement.JB2D.interp_matrix(r, s))
+
     def barycentric_coords(self):
         """[NpFlux, 3] vertex interpolation weights at every RT point (dissipation.go:414-449)."""
         rt = self.FluxElement

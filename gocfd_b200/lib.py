@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -81,6 +81,7 @@ def load():
     lib.dfr2d_set_register.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_get_register.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_get_field.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_plot_field.argtypes = [H, C.c_int, _dp, C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_set_stream.argtypes = [H, C.c_void_p]
     lib.dfr2d_partition_range.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.dfr2d_halo_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -221,6 +222,15 @@ class Dfr2d:
     def get_field(self, which):
         out = np.zeros(self.p.K)
         self._ck(self.lib.dfr2d_get_field(self.h, which, _d(out)))
+        return out
+
+    def plot_field(self, flow_function, graph_interp, out=None):
+        """GetPlotField on the device: float32 [K, NpGraph] (own rows of a multi-partition handle)."""
+        gi = np.ascontiguousarray(graph_interp, dtype=np.float64)
+        if out is None:
+            out = np.zeros((self.p.K, gi.shape[0]), dtype=np.float32)
+        self._ck(self.lib.dfr2d_plot_field(self.h, int(flow_function), _d(gi), gi.shape[0],
+                                           out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
     # ---- multi-partition plumbing -------------------------------------------------------

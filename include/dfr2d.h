@@ -142,6 +142,14 @@ int dfr2d_set_register(dfr2d_handle *h, int reg, const double *Q);
 int dfr2d_get_register(dfr2d_handle *h, int reg, double *Q);
 int dfr2d_get_field(dfr2d_handle *h, int which, double *out /* [K] */);
 
+/* Field read-back for plots: Euler.GetPlotField (model_problems/Euler2D/plot.go:14-86) for the flow functions that go
+ * through FreeStream.GetFlowFunction (fluids.go:209-223: Density=0 .. Entropy=13) evaluated on c.Q on the device:
+ * node values -> DFR.GraphInterp product (DG2D/dfr_startup.go:62-63) -> AverageGraphFieldVertices
+ * (DG2D/graphics_support2.go:184-199) -> transpose -> float32 (what AVSFieldWriter.saveField stores,
+ * DG2D/graphics_support.go:80-93).  graph_interp = [np_graph x NpInt] row-major with np_graph = 3(1+NpEdge)+NpInt;
+ * out = [K x np_graph] (global element index; own rows only are written). */
+int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_interp, int np_graph, float *out);
+
 /* ---- plumbing for one-process-per-GPU hosts (torch.distributed / NCCL) ---------------------
  * The library never calls a collective itself: per stage the host moves the halo bytes and
  * max-reduces two doubles, between the three phases below.  Single-partition users only need

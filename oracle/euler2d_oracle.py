@@ -250,6 +250,61 @@ def roe_er_flux(gamma, ql, qr, nx, ny):
     return f
 
 
+# FlowFunction numbering, fluids.go:209-223
+FF_Density, FF_XMomentum, FF_YMomentum, FF_Energy, FF_Mach, FF_StaticPressure, FF_DynamicPressure, \
+    FF_PressureCoefficient, FF_SoundSpeed, FF_Velocity, FF_XVelocity, FF_YVelocity, FF_Enthalpy, FF_Entropy = range(14)
+
+
+def flow_function(fs, q, pf):
+    """FreeStream.GetFlowFunctionBase (fluids.go:289-336) on arrays; fs = FreeStream.as_array() tuple."""
+    gamma, p_inf, qq_inf = fs[0], fs[5], fs[6]
+    rho, rho_u, rho_v, e = q
+    gm1 = gamma - 1.0
+    oorho = 1.0 / rho
+    if pf <= FF_Energy:
+        return np.array(q[pf], dtype=np.float64, copy=True)
+    if pf == FF_XVelocity:
+        return rho_u * oorho
+    if pf == FF_YVelocity:
+        return rho_v * oorho
+    u, v = rho_u * oorho, rho_v * oorho
+    u2 = u * u + v * v
+    qq = 0.5 * rho * u2
+    p = gm1 * (e - qq)
+    if pf == FF_Velocity:
+        return np.sqrt(u2)
+    if pf == FF_DynamicPressure:
+        return qq
+    if pf == FF_StaticPressure:
+        return p
+    if pf == FF_PressureCoefficient:
+        return (p - p_inf) / qq_inf
+    if pf == FF_SoundSpeed:
+        return np.sqrt(np.abs(gamma * p * oorho))
+    if pf == FF_Enthalpy:
+        return (e + p) / rho
+    if pf == FF_Entropy:
+        return np.log(p) - gamma * np.log(rho)
+    if pf == FF_Mach:
+        return np.sqrt(u2) / np.sqrt(np.abs(gamma * p * oorho))
+    raise ValueError("flow function %d does not go through GetFlowFunction" % pf)
+
+
+def plot_field(p, q, pf, graph_interp):
+    """Euler.GetPlotField for the GetFlowFunction family (plot.go:14-86): node values, GraphInterp product,
+    AverageGraphFieldVertices (DG2D/graphics_support2.go:184-199), transpose -> [K, NpGraph]; the AVS writer then
+    narrows to float32 (DG2D/graphics_support.go:80-93), which the caller applies."""
+    fld = flow_function(tuple(p.FSFar.as_array()), q, pf)
+    field = graph_interp @ fld
+    npe = p.NpEdge + 2
+    for n_edge in range(3):
+        iv = n_edge * (npe - 1)
+        ivp = iv + 1
+        ivm = 3 * (npe - 1) - 1 if n_edge == 0 else n_edge * (npe - 1) - 1
+        field[iv] = 0.5 * (field[ivp] + field[ivm])
+    return np.ascontiguousarray(field.T)
+
+
 _FLUX_FUNCS = {FLUX_Average: avg_flux, FLUX_LaxFriedrichs: lax_flux, FLUX_Roe: roe_flux, FLUX_RoeER: roe_er_flux}
 
 

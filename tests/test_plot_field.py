@@ -1,0 +1,112 @@
+"""Field read-back path: Euler.GetPlotField restated in the oracle and on the device.
+
+The reference has no asserting test for GraphInterp / GetPlotField (its tests only plot), so the oracle is pinned
+by what the construction guarantees: GraphInterp reproduces every polynomial of degree <= N exactly at the graph
+nodes (DG2D/dfr_startup.go:62-63), the three vertex rows are the mean of their boundary neighbours
+(DG2D/graphics_support2.go:184-199), and the flow functions are the closed forms of fluids.go:289-336.
+"""
+import numpy as np
+import pytest
+
+from conftest import mesh_path
+from gocfd_b200.host.dg2d.dfr2d import DFR2D
+from gocfd_b200.host.euler2d import Euler
+from gocfd_b200.host.input_parameters import InputParameters2D
+from gocfd_b200.host.meshgen import structured_tri_mesh
+from oracle import euler2d_oracle as ora
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_graph_interp_reproduces_polynomials(n):
+    d = DFR2D(n)
+    gi = d.graph_interp()
+    gr, gs = d.graph_rs()
+    el = d.SolutionElement
+    ne = d.FluxElement.NpEdge
+    assert gi.shape == (3 * (1 + ne) + el.Np, el.Np)
+    for a in range(n + 1):
+        for b in range(n + 1 - a):
+            f_nodes = el.R ** a * el.S ** b
+            np.testing.assert_allclose(gi @ f_nodes, gr ** a * gs ** b, atol=2e-12)
+    # graph node order: vertex, NpEdge edge points (x3), then the interior points themselves
+    np.testing.assert_allclose(gi[3 * (1 + ne):], np.eye(el.Np), atol=1e-12)
+    assert (gr[0], gs[0]) == (-1.0, -1.0) and (gr[1 + ne], gs[1 + ne]) == (1.0, -1.0)
+
+
+def _case(n=2, **kw):
+    base = dict(CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n, FinalTime=1.0, MaxIterations=10,
+                Gamma=1.4, Minf=0.4)
+    base.update(kw)
+    return Euler(InputParameters2D(**base), structured_tri_mesh(7, 5))
+
+
+def test_oracle_plot_field_closed_forms_and_vertex_rule():
+    c = _case(3)
+    p = c.problem
+    gi = c.DFR.graph_interp()
+    ne = p.NpEdge
+    rho, ru, rv, e = c.Q
+    fs = tuple(p.FSFar.as_array())
+    pres = (p.Gamma - 1.0) * (e - 0.5 * (ru * ru + rv * rv) / rho)
+    np.testing.assert_allclose(ora.flow_function(fs, c.Q, ora.FF_StaticPressure), pres, rtol=1e-14)
+    np.testing.assert_allclose(ora.flow_function(fs, c.Q, ora.FF_Mach),
+                               np.sqrt((ru * ru + rv * rv) / rho ** 2) / np.sqrt(p.Gamma * pres / rho), rtol=1e-13)
+    np.testing.assert_allclose(ora.flow_function(fs, c.Q, ora.FF_PressureCoefficient), (pres - fs[5]) / fs[6], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(ora.flow_function(fs, c.Q, ora.FF_Entropy), np.log(pres) - p.Gamma * np.log(rho), rtol=1e-12, atol=1e-14)
+    out = ora.plot_field(p, c.Q, ora.FF_Density, gi)
+    assert out.shape == (p.K, 3 * (1 + ne) + p.NpInt)
+    raw = (gi @ rho).T
+    npe = ne + 2
+    for n_edge in range(3):
+        iv = n_edge * (npe - 1)
+        ivm = 3 * (npe - 1) - 1 if n_edge == 0 else iv - 1
+        np.testing.assert_array_equal(out[:, iv], 0.5 * (raw[:, iv + 1] + raw[:, ivm]))
+    keep = np.setdiff1d(np.arange(out.shape[1]), [0, npe - 1, 2 * (npe - 1)])
+    np.testing.assert_array_equal(out[:, keep], raw[:, keep])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 4])
+def test_device_plot_field_matches_oracle(n):
+    from gocfd_b200 import lib
+    c = _case(n)
+    p = c.problem
+    gi = c.DFR.graph_interp()
+    dev = lib.Dfr2d(p)
+    dev.set_state(c.Q)
+    dev.step(2)
+    q = dev.get_state()
+    for ff in range(14):
+        want = ora.plot_field(p, q, ff, gi)
+        got = dev.plot_field(ff, gi)
+        assert got.dtype == np.float32 and got.shape == want.shape
+        # float64 arithmetic narrowed to float32 at the end on both sides: at most one float32 ulp apart
+        np.testing.assert_allclose(got, want.astype(np.float32), rtol=2.5e-7, atol=1e-7)
+    with pytest.raises(lib.Dfr2dError):
+        dev.plot_field(100, gi)
+    with pytest.raises(lib.Dfr2dError):
+        dev.plot_field(0, gi[:-1])
+    dev.close()
+
+
+@pytest.mark.gpu
+def test_device_plot_field_partitions_cover_the_mesh():
+    from gocfd_b200 import lib
+    c = Euler(InputParameters2D(CFL=1.0, FluxType="Roe", InitType="Freestream", PolynomialOrder=2, FinalTime=1.0,
+                                MaxIterations=10, Gamma=1.4, Minf=0.8, Alpha=2.0), mesh_path("mesh_NACA0012_inv.su2"))
+    p = c.problem
+    gi = c.DFR.graph_interp()
+    rng = np.random.default_rng(5)
+    q = c.Q * (1.0 + 0.05 * rng.standard_normal(c.Q.shape))
+    one = lib.Dfr2d(p)
+    one.set_state(q)
+    ref = one.plot_field(ora.FF_Mach, gi)
+    out = np.zeros_like(ref)
+    devs = [lib.Dfr2d(p, n_parts=3, part=r) for r in range(3)]
+    for d in devs:
+        d.set_state(q)
+        d.plot_field(ora.FF_Mach, gi, out)
+    np.testing.assert_array_equal(out, ref)
+    np.testing.assert_allclose(ref, ora.plot_field(p, q, ora.FF_Mach, gi).astype(np.float32), rtol=2.5e-7, atol=1e-7)
+    for d in devs + [one]:
+        d.close()
