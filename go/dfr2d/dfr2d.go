@@ -195,4 +195,53 @@ func (s *Solver) Residual() (r [4]float64) {
 	return
 }
 
+// PlotField is Euler.GetPlotField (plot.go:14-86) for the GetFlowFunction family, evaluated on the device:
+// flow function -> GraphInterp -> AverageGraphFieldVertices -> transpose -> float32, i.e. exactly the slice
+// AVSFieldWriter.saveField stores (DG2D/graphics_support.go:80-93).  The caller hands it to the writer instead of
+// RecombineShardsKBy4 + GetPlotField (euler.go:192-207).
+func (s *Solver) PlotField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []float32 {
+	gi := c.DFR.GraphInterp
+	nr, _ := gi.Dims()
+	out := make([]float32, s.k*nr)
+	s.check(C.dfr2d_plot_field(s.h, C.int(ff), d(gi.DataP), C.int(nr), (*C.float)(unsafe.Pointer(&out[0]))), "dfr2d_plot_field")
+	return out
+}
+
 func (s *Solver) Close() { C.dfr2d_destroy(s.h); s.h = nil }
+
+// MultiSolver drives one handle per GPU from a single Go process: the per-stage protocol of include/dfr2d.h
+// (sensor / prepare / edges / visc / update with three exchange points and one MAX reduction), the halo bytes
+// moved by the caller-supplied functions (cudaMemcpyPeerAsync or NCCL bindings).  bench.py runs the same protocol
+// with one process per GPU over torch.distributed.
+type MultiSolver struct {
+	Parts    []*Solver
+	Exchange func(which int) // moves every partition's send buffer of exchange `which` into its peers' receive buffers
+	MaxWave  func()          // MAX-allreduce of dfr2d_wavespeed_buffer (two doubles) over the partitions
+}
+
+func (m *MultiSolver) Step() {
+	for rk := 0; rk < 5; rk++ {
+		for _, s := range m.Parts {
+			s.check(C.dfr2d_stage_sensor(s.h, C.int(rk)), "dfr2d_stage_sensor")
+		}
+		m.Exchange(int(C.DFR2D_XCHG_VERTEX))
+		for _, s := range m.Parts {
+			s.check(C.dfr2d_stage_prepare(s.h, C.int(rk)), "dfr2d_stage_prepare")
+		}
+		m.Exchange(int(C.DFR2D_XCHG_EDGE))
+		for _, s := range m.Parts {
+			s.check(C.dfr2d_stage_edges(s.h, C.int(rk)), "dfr2d_stage_edges")
+		}
+		m.Exchange(int(C.DFR2D_XCHG_DISS))
+		for _, s := range m.Parts {
+			s.check(C.dfr2d_stage_visc(s.h, C.int(rk)), "dfr2d_stage_visc")
+		}
+		m.MaxWave()
+		for _, s := range m.Parts {
+			s.check(C.dfr2d_stage_update(s.h, C.int(rk)), "dfr2d_stage_update")
+		}
+	}
+	for _, s := range m.Parts {
+		s.check(C.dfr2d_step_finish(s.h, nil), "dfr2d_step_finish")
+	}
+}
