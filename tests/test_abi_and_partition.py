@@ -178,3 +178,15 @@ def test_shared_vertex_plan_reproduces_the_global_vertex_max(mesh_name, n_parts)
     for r in range(n_parts):
         mine = sorted(touched[r])
         assert np.array_equal(merged[r][mine], want[mine])
+
+
+def test_two_rank_gloo_dissipation_exchange():
+    """world_size-2 gloo run of the dissipation path's shared-vertex exchange."""
+    script = os.path.join(ROOT, "tests", "gloo_vertex_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29733", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2", mesh_path("sod-aligned-100pts.su2")], env=env,
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [pr.communicate(timeout=300)[0] for pr in procs]
+    for pr, out in zip(procs, outs):
+        assert pr.returncode == 0, out
+        assert "OK" in out, out
