@@ -342,7 +342,7 @@ def main():
     if t_elem:
         te = statistics.mean(t_elem) * 1e-3
         ach = b_elem * k_local / te / 1e9
-        roofline = {"bound": "hbm", "kernel": ("k_elem_pipe<%d> (persistent, FP64 DMMA contractions)" if n >= 3 else "k_elem<%d,false>") % n, "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": ("k_elem_tma<%d,8> (warp-specialised async-copy pipeline, FP64 DMMA contractions)" if n >= 4 else "k_elem<%d,false>") % n, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b_elem * k_local, "avg_launch_ms": te * 1e3,
                     "edge_kernel": {"achieved": b_edge * k_local / (statistics.mean(t_edge) * 1e-3) / 1e9,
@@ -350,7 +350,7 @@ def main():
                     "whole_stage": {"bytes_per_element": b_total,
                                     "achieved": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9,
                                     "frac": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9 / peak / world}}
-        prof = os.path.join(ROOT, "profiles", "r01e_traffic.json")
+        prof = os.path.join(ROOT, "profiles", "r01h_traffic.json")
         if os.path.exists(prof):
             try:
                 roofline["traffic"] = json.load(open(prof)).get("k_elem_N%d" % n)
