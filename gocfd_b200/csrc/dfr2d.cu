@@ -798,7 +798,11 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
                 const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words
                 int stages = (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1));
                 stages = std::max(2, std::min(stages, kTmaMaxStages));     // two consumer groups: a waiter may be at most one phase ahead
-                if (h->tmaStages > 1) stages = std::min(stages, h->tmaStages);
+                // measured (profiles/r01i_ring_depth.txt): a deeper ring is SLOWER -- the shared memory it takes comes out
+                // of L1, and the 8-byte edge-flux gather lives on L1 hits (neighbouring elements share sectors and
+                // edges).  3 stages for rk 0-2 (121-173 KB), 2 for rk 3 (115 KB) and rk 4 (219 KB, all that fits)
+                stages = std::min(stages, (rk >= 3 && rhsOut == nullptr) ? 2 : 3);
+                if (h->tmaStages > 1) stages = std::min(std::max(2, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))), h->tmaStages);
                 ta.nStages = stages;
                 const size_t sm = TD::smem_bytes(ta.nExtra, stages);
                 // (a 12-consumer-warp instantiation was measured: 152 registers per consumer spill the operator fragments,

@@ -373,3 +373,28 @@ def test_multi_partition_naca_transonic_dissipation_local_dt():
     assert np.array_equal(one.get_state(), q)
     for d in devs + [one]:
         d.close()
+
+
+def test_c1_naca_p0_full_run_residual_history():
+    """Config C1 as shipped (test_cases/Euler2D/SU2-naca12/input-base.yaml + runme.sh): NACA0012, N=0, Roe, local dt,
+    CFL 2, M=0.8, alpha=1.25, 2000 iterations.  Residual history every 100 iterations (what PrintUpdate prints,
+    euler.go:821-835) and the final field against the C restatement of the reference stage."""
+    from gocfd_b200 import lib
+    from oracle.c_oracle import COracleSolver
+    c = make(dict(PolynomialOrder=0, CFL=2.0, LocalTimeStepping=True, MaxIterations=2000, Minf=0.8, Alpha=1.25,
+                  Limiter="PerssonC0", Kappa=4.5, FinalTime=20.0), mesh_path("mesh_NACA0012_inv.su2"))
+    dev, ora = lib.Dfr2d(c.problem), COracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    worst = 0.0
+    for it in range(20):
+        a, b = dev.step(100), ora.step(100)
+        assert a["steps"] == b["steps"] == 100 * (it + 1)
+        ra, rb = np.array(dev.residual()), np.array(ora.residual())
+        np.testing.assert_allclose(ra, rb, rtol=1e-7, atol=1e-13)
+        worst = max(worst, rel_l2(dev.get_state(), ora.get_state()))
+    assert a["finished"] and b["finished"]
+    assert worst < TOL, worst
+    # the run converges: the density residual drops by orders of magnitude from its first value
+    assert max(0.0, rb[0]) < 1e-2
+    dev.close()
