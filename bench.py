@@ -342,7 +342,7 @@ def main():
     if t_elem:
         te = statistics.mean(t_elem) * 1e-3
         ach = b_elem * k_local / te / 1e9
-        roofline = {"bound": "hbm", "kernel": ("k_elem_tma<%d,8> (warp-specialised async-copy pipeline, FP64 DMMA contractions)" if n >= 4 else "k_elem<%d,false>") % n, "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": ("k_elem_tma<%d,8> (warp-specialised async-copy pipeline, FP64 DMMA contractions)" if n >= 2 else "k_elem<%d,false>") % n, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": b_elem * k_local, "avg_launch_ms": te * 1e3,
                     "edge_kernel": {"achieved": b_edge * k_local / (statistics.mean(t_edge) * 1e-3) / 1e9,

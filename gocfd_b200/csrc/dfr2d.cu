@@ -544,9 +544,10 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->pfTiles = 1;
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
     h->sms = sms;
-    // measured on B200 (profiles/r01c_*): the pipelined DMMA kernel wins at N = 4 (6.6 vs 8.1 ms), the row-per-thread DFMA kernel
-    // at N <= 3 (small operators: DMMA padding waste, fewer tiles per persistent CTA)
-    h->elemKernel = (N >= 4) ? 5 : 1;
+    // measured on B200 (profiles/r01h_*, r01i_*): the warp-specialised DMMA kernel wins at N >= 2 (N=4 8M: 5.2 vs 8.1 ms;
+    // N=3 2M: 0.92 vs 1.04 ms; N=2 2M: 0.63 vs 0.67 ms; N=2 200K: 71 vs 73 us); N <= 1 keeps the row-per-thread DFMA kernel
+    // (operators of 3 x 15 / 1 x 8 entries: the 8 x 8 x 4 tiles would be mostly padding)
+    h->elemKernel = (N >= 2) ? 5 : 1;
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
     if (const char *ev = getenv("DFR2D_TMA_STAGES")) h->tmaStages = atoi(ev);
     {
