@@ -195,6 +195,20 @@ func (s *Solver) Residual() (r [4]float64) {
 	return
 }
 
+// InitState evaluates Euler.InitializeSolution (euler.go:728-794) on the device instead of uploading c.Q.
+func (s *Solver) InitState(c *Euler2D.Euler) {
+	dfr := c.DFR
+	etov := make([]int32, 3*s.k)
+	for k := 0; k < s.k; k++ {
+		for v := 0; v < 3; v++ {
+			etov[3*k+v] = int32(dfr.Tris.EToV.At(k, v))
+		}
+	}
+	el := dfr.SolutionElement
+	s.check(C.dfr2d_init_state(s.h, C.int(c.Case), C.int64_t(dfr.VX.Len()), d(dfr.VX.DataP), d(dfr.VY.DataP), i32(etov),
+		d(el.R.DataP), d(el.S.DataP)), "dfr2d_init_state")
+}
+
 // PlotField is Euler.GetPlotField (plot.go:14-86) for the GetFlowFunction family, evaluated on the device:
 // flow function -> GraphInterp -> AverageGraphFieldVertices -> transpose -> float32, i.e. exactly the slice
 // AVSFieldWriter.saveField stores (DG2D/graphics_support.go:80-93).  The caller hands it to the writer instead of

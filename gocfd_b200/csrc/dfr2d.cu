@@ -1096,6 +1096,37 @@ extern "C" int dfr2d_get_field(dfr2d_handle *h, int which, double *out) {
     return 0;
 }
 
+extern "C" int dfr2d_init_state(dfr2d_handle *h, int init_case, int64_t nv, const double *VX, const double *VY,
+                                const int32_t *EToV, const double *R, const double *S) {
+    if (!h || !VX || !VY || !EToV || !R || !S || nv <= 0) return 1;
+    if (init_case < DFR2D_CASE_Freestream || init_case > DFR2D_CASE_ShockTube) { h->err = "unknown case type"; return 1; }
+    CK(cudaSetDevice(h->device));
+    double *vx = nullptr, *vy = nullptr, *rs = nullptr;
+    int *etov = nullptr;
+    int rc = 0;
+    cudaError_t e = cudaMalloc(&vx, (size_t)nv * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&vy, (size_t)nv * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&rs, (size_t)2 * h->NpInt * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&etov, (size_t)3 * std::max(h->K, 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vx, VX, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(vy, VY, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rs, R, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rs + h->NpInt, S, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(etov, EToV + 3 * h->k0, (size_t)3 * h->K * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        InitArgs ia{};
+        ia.K = h->K; ia.Kp = h->Kp; ia.npInt = h->NpInt; ia.initCase = init_case;
+        ia.vx = vx; ia.vy = vy; ia.etov = etov; ia.r = rs; ia.s = rs + h->NpInt; ia.q = h->q[0]; ia.ph = h->ph;
+        k_init_state<<<(h->K + 127) / 128, 128, 0, h->stream>>>(ia);
+        rc = launch_check(h, "k_init_state");
+        if (!rc) e = cudaStreamSynchronize(h->stream);
+        h->qfaceValid = false;
+    }
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
+    cudaFree(vx); cudaFree(vy); cudaFree(rs); cudaFree(etov);
+    return rc;
+}
+
 extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_interp, int np_graph, float *out) {
     if (!h || !graph_interp || !out) return 1;
     const int NG = 3 * (1 + h->NpEdge) + h->NpInt;

@@ -499,6 +499,43 @@ __global__ void __launch_bounds__(kPlotThreads) k_plot_field(PlotArgs a) {
     for (int t = threadIdx.x; t < nk * NG; t += kPlotThreads) dst[t] = sOut[(t / NG) * ST + (t % NG)];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Initial condition on the device: InitializeSolution (euler.go:728-794) -- InitializeFS and
+// InitializeIVortex (initialization.go:50-83), shock-tube split at x < 0.5 (euler.go:742-768) -- evaluated at the
+// solution points X = 0.5 (-(r+s) v0 + (1+r) v1 + (1+s) v2) (CalculateElementLocalGeometry), so that the host neither
+// builds nor uploads the [4][NpInt x K] state.  One thread per element.
+// ------------------------------------------------------------------------------------------------
+struct InitArgs {
+    int K, Kp, npInt, initCase;
+    const double *vx, *vy;     // [NV]
+    const int *etov;           // [K][3] own elements, global vertex ids
+    const double *r, *s;       // [NpInt] solution points of the reference element
+    double *q;                 // [4][NpInt][Kp]
+    Phys ph;
+};
+
+__global__ void k_init_state(InitArgs a) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const int v0 = a.etov[3 * (size_t)k], v1 = a.etov[3 * (size_t)k + 1], v2 = a.etov[3 * (size_t)k + 2];
+    const double ax = a.vx[v0], bx = a.vx[v1], cx = a.vx[v2], ay = a.vy[v0], by = a.vy[v1], cy = a.vy[v2];
+    const size_t plane = (size_t)a.npInt * a.Kp;
+    for (int i = 0; i < a.npInt; i++) {
+        const double r = a.r[i], s = a.s[i];
+        const double x = (((r + s) * -1.0) * ax + (r + 1.0) * bx + (s + 1.0) * cx) * 0.5;
+        const double y = (((r + s) * -1.0) * ay + (r + 1.0) * by + (s + 1.0) * cy) * 0.5;
+        double Q[4];
+        if (a.initCase == DFR2D_CASE_IVortex) {
+            ivortex_state(a.ph.vortex, 0.0, x, y, Q);
+        } else {
+            const dfr2d_freestream &f = (a.initCase == DFR2D_CASE_ShockTube) ? (x < 0.5 ? a.ph.fs[1] : a.ph.fs[2]) : a.ph.fs[0];
+            Q[0] = f.Qinf[0]; Q[1] = f.Qinf[1]; Q[2] = f.Qinf[2]; Q[3] = f.Qinf[3];
+        }
+#pragma unroll
+        for (int n = 0; n < 4; n++) a.q[n * plane + (size_t)i * a.Kp + k] = Q[n];
+    }
+}
+
 template <int N> static size_t elem_smem_diss() { return (size_t)12 * Dim<N>::NpInt * kElemsPerBlock * sizeof(double); }
 
 }  // namespace dfr2d

@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -81,6 +81,7 @@ def load():
     lib.dfr2d_set_register.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_get_register.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_get_field.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_init_state.argtypes = [H, C.c_int, C.c_int64, _dp, _dp, _ip, _dp, _dp]
     lib.dfr2d_plot_field.argtypes = [H, C.c_int, _dp, C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_set_stream.argtypes = [H, C.c_void_p]
     lib.dfr2d_partition_range.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -223,6 +224,16 @@ class Dfr2d:
         out = np.zeros(self.p.K)
         self._ck(self.lib.dfr2d_get_field(self.h, which, _d(out)))
         return out
+
+    def init_state(self, init_case, vx, vy, etov, r, s):
+        """InitializeSolution on the device (replaces building Q on the host + set_state)."""
+        vx = np.ascontiguousarray(vx, dtype=np.float64)
+        vy = np.ascontiguousarray(vy, dtype=np.float64)
+        etov = np.ascontiguousarray(etov, dtype=np.int32)
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        assert etov.shape == (self.p.K, 3) and r.shape == (self.p.NpInt,) and s.shape == (self.p.NpInt,)
+        self._ck(self.lib.dfr2d_init_state(self.h, int(init_case), len(vx), _d(vx), _d(vy), _i(etov), _d(r), _d(s)))
 
     def plot_field(self, flow_function, graph_interp, out=None):
         """GetPlotField on the device: float32 [K, NpGraph] (own rows of a multi-partition handle)."""

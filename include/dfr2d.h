@@ -142,6 +142,14 @@ int dfr2d_set_register(dfr2d_handle *h, int reg, const double *Q);
 int dfr2d_get_register(dfr2d_handle *h, int reg, double *Q);
 int dfr2d_get_field(dfr2d_handle *h, int which, double *out /* [K] */);
 
+/* Initial condition evaluated on the device instead of dfr2d_set_state: Euler.InitializeSolution (euler.go:728-794) --
+ * InitializeFS / InitializeIVortex (initialization.go:50-83; beta=5, x0=5, y0=0 as carried in dfr2d_problem.vortex) /
+ * the shock-tube split at x < 0.5 (euler.go:742-768, FSIn / FSOut) -- at the solution points of every own element,
+ * X = 0.5(-(r+s) v0 + (1+r) v1 + (1+s) v2).  VX, VY = [nv] vertex coordinates, EToV = [K x 3] (global), R, S = [NpInt]
+ * SolutionElement.R/S. */
+int dfr2d_init_state(dfr2d_handle *h, int init_case, int64_t nv, const double *VX, const double *VY, const int32_t *EToV,
+                     const double *R, const double *S);
+
 /* Field read-back for plots: Euler.GetPlotField (model_problems/Euler2D/plot.go:14-86) for the flow functions that go
  * through FreeStream.GetFlowFunction (fluids.go:209-223: Density=0 .. Entropy=13) evaluated on c.Q on the device:
  * node values -> DFR.GraphInterp product (DG2D/dfr_startup.go:62-63) -> AverageGraphFieldVertices
