@@ -350,7 +350,7 @@ def main():
                     "whole_stage": {"bytes_per_element": b_total,
                                     "achieved": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9,
                                     "frac": b_total * p.K * 5 * args.steps / (ms * 1e-3) / 1e9 / peak / world}}
-        prof = os.path.join(ROOT, "profiles", "r01h_traffic.json")
+        prof = os.path.join(ROOT, "profiles", "r01j_traffic.json")
         if os.path.exists(prof):
             try:
                 roofline["traffic"] = json.load(open(prof)).get("k_elem_N%d" % n)
