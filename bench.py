@@ -248,7 +248,7 @@ def main():
             sp, rp = dev.exchange_buffers(which)
             st = torch.as_tensor(_DevArray(sp, max(sum(sc), 1)), device="cuda")[:sum(sc)]
             rt = torch.as_tensor(_DevArray(rp, max(sum(rc), 1)), device="cuda")[:sum(rc)]
-            return lambda: dist.all_to_all_single(rt, st, rc, sc)
+            return lambda async_op=False: dist.all_to_all_single(rt, st, rc, sc, async_op=async_op)
         x_edge = exchange(dev.XCHG_EDGE)
         x_vtx = exchange(dev.XCHG_VERTEX) if diss else None
         x_diss = exchange(dev.XCHG_DISS) if diss else None
@@ -259,8 +259,10 @@ def main():
                     dev.stage_sensor(rk)
                     x_vtx()
                 dev.stage_prepare(rk)
-                x_edge()
-                dev.stage_edges(rk)
+                work = x_edge(async_op=True)         # NCCL stream; waits for the pack kernel, not for what follows
+                dev.stage_edges_interior(rk)         # interior-edge fluxes overlap the halo transfer
+                work.wait()                          # the compute stream waits for the halo (no host block)
+                dev.stage_edges(rk)                  # unpack + boundary and cut edges
                 if diss:
                     x_diss()
                     dev.stage_visc(rk)

@@ -58,6 +58,7 @@ struct dfr2d_handle {
     DevScalars *scHost = nullptr;     // pinned
     long long stageCounter = 0, stepIndex = 0, launches = 0;
     bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
+    bool interiorDone = false;        // the interior-edge kernel of the stage in flight has been launched (overlap with the halo)
     int edgeBlocks = 0;
     bool smemAttrSet = false;
     int pfTiles = 0;
@@ -324,6 +325,8 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
             c.ghCol = lMine ? led[s].r : led[s].l;
             c.ghNum = lMine ? p->edge_numR[e] : p->edge_numL[e];
             cuts.push_back(c);
+            pl.bndList.push_back(s);      // evaluated with the boundary edges after the halo exchange, so that the
+                                          // interior-edge kernel can run while the halo is in flight
         }
         std::stable_sort(cuts.begin(), cuts.end(), [](const Cut &a, const Cut &b) {
             return a.peer != b.peer ? a.peer < b.peer : a.ge < b.ge;
@@ -701,9 +704,11 @@ static int run_unpack_vertex(dfr2d_handle *h) {
     return launch_check(h, "k_vertex_unpack_max");
 }
 
-static int run_edges(dfr2d_handle *h, int rk) {
+// part: 1 = interior edges (no ghost column involved: may run while the halo is in flight), 2 = boundary + cut edges
+// (after the halo has been unpacked), 3 = both
+static int run_edges(dfr2d_handle *h, int rk, int part) {
     EdgeArgs a{};
-    a.ne = h->NE; a.NEp = h->NEp; a.Kp = h->Kp;
+    a.ne = h->NE; a.NEp = h->NEp; a.Kp = h->Kp; a.Kown = h->K;
     a.kL = h->ekL; a.kR = h->ekR; a.meta = h->emeta;
     a.nx = h->enx; a.ny = h->eny; a.oohk = h->eoohk;
     a.bpx = h->bpx; a.bpy = h->bpy;
@@ -720,7 +725,7 @@ static int run_edges(dfr2d_handle *h, int rk) {
     int ppt = h->edgePPT;
     if (ppt <= 0) ppt = (h->NE < 64 * h->sms * 256) ? 1 : h->N + 2;
     if ((h->N + 2) % ppt != 0) ppt = h->N + 2;
-    if (ppt != h->N + 2 && h->ph.localDT) CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
+    if (ppt != h->N + 2 && h->ph.localDT && (part & 1)) CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
     a.list = nullptr; a.nlist = 0;
 #define EDGE_LAUNCH(KERN)                                                                      \
     DISPATCH_N(h->N, {                                                                          \
@@ -732,6 +737,7 @@ static int run_edges(dfr2d_handle *h, int rk) {
     })
     if (h->edgeSplit) {
         const int ib = std::max(1, std::min(h->edgeBlocks * 2, (int)(((long long)h->NEp * ((h->N + 2) / ppt) + 255) / 256)));
+        if (part & 1) {
         switch (h->ph.fluxType) {
 #define KI_AVG(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_Average, P_><<<ib, 256, 0, h->stream>>>(a)
 #define KI_LAX(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_><<<ib, 256, 0, h->stream>>>(a)
@@ -743,14 +749,17 @@ static int run_edges(dfr2d_handle *h, int rk) {
             default: EDGE_LAUNCH(KI_RER); break;
         }
         if (int rc = launch_check(h, "k_edge_int")) return rc;
-        if (h->nBnd == 0) return 0;
+        }
+        if (!(part & 2) || h->nBnd == 0) return 0;
         a.list = h->bndList; a.nlist = h->nBnd;
         const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
 #define KB(NN_, P_) k_edge<NN_, P_><<<bb, 256, 0, h->stream>>>(a)
         EDGE_LAUNCH(KB);
         return launch_check(h, "k_edge(boundary)");
     }
+    if (!(part & 2)) return 0;          // single generic kernel: everything happens in the second part
 #define KG(NN_, P_) k_edge<NN_, P_><<<blocks, 256, 0, h->stream>>>(a)
+    a.Kown = 0x7fffffff;
     EDGE_LAUNCH(KG);
     (void)rk;
     return launch_check(h, "k_edge");
@@ -970,10 +979,21 @@ static int stage_prepare(dfr2d_handle *h, int rk) {
     return run_pack(h);
 }
 
+// interior edges only: independent of the halo, so a multi-GPU host calls it between posting the EDGE exchange and
+// waiting for it (north star: halo transfer overlapped with interior work); optional -- stage_edges catches up
+static int stage_edges_interior(dfr2d_handle *h, int rk) {
+    CK(cudaSetDevice(h->device));
+    if (h->interiorDone || !h->edgeSplit) return 0;
+    if (int rc = run_edges(h, rk, 1)) return rc;
+    h->interiorDone = true;
+    return 0;
+}
+
 static int stage_edges(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
     if (int rc = run_unpack(h)) return rc;
-    if (int rc = run_edges(h, rk)) return rc;
+    if (int rc = run_edges(h, rk, h->interiorDone ? 2 : 3)) return rc;
+    h->interiorDone = false;
     if (h->ph.dissipation) {
         if (int rc = run_diss_grad(h, rk)) return rc;
         return run_pack_diss(h);
@@ -1003,6 +1023,7 @@ static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
 
 extern "C" int dfr2d_stage_sensor(dfr2d_handle *h, int rk) { return h ? stage_sensor(h, rk) : 1; }
 extern "C" int dfr2d_stage_visc(dfr2d_handle *h, int rk) { return h ? stage_visc(h, rk) : 1; }
+extern "C" int dfr2d_stage_edges_interior(dfr2d_handle *h, int rk) { return h ? stage_edges_interior(h, rk) : 1; }
 extern "C" int dfr2d_stage_prepare(dfr2d_handle *h, int rk) { return h ? stage_prepare(h, rk) : 1; }
 extern "C" int dfr2d_stage_edges(dfr2d_handle *h, int rk) { return h ? stage_edges(h, rk) : 1; }
 extern "C" int dfr2d_stage_update(dfr2d_handle *h, int rk) { return h ? stage_update(h, rk, nullptr) : 1; }

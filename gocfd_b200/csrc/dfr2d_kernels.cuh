@@ -16,8 +16,9 @@ constexpr int kElemThreads = 4 * kElemsPerBlock; // one thread per (element, con
 
 struct EdgeArgs {
     int ne, NEp, Kp;
+    int Kown;                           // own columns; an edge with a column >= Kown (a ghost) is a cut edge, left to the list pass
     const int *kL, *kR, *meta;          // kR < 0: boundary edge, boundary-point slot = -1 - kR
-    const int *list;                    // optional: process only these edge slots (boundary edges)
+    const int *list;                    // optional: process only these edge slots (boundary and cut edges)
     int nlist;
     const double *nx, *ny, *oohk;
     const double *bpx, *bpy;            // [NBPloc][NpEdge]
@@ -180,8 +181,9 @@ __global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeA
         const int e = (int)(t % a.NEp), g = (int)(t / a.NEp);
         if (e >= a.ne) continue;
         const int kR = a.kR[e];
-        if (kR < 0) continue;
+        if (kR < 0 || kR >= a.Kown) continue;
         const int kL = a.kL[e], meta = a.meta[e];
+        if (kL >= a.Kown) continue;         // cut edge: needs the halo, evaluated after the exchange
         const int numL = meta & 3, numR = (meta >> 2) & 3;
         const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
         double wmax = -1.7976931348623157e308;

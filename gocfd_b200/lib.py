@@ -50,7 +50,7 @@ EXPORTS = [
     "dfr2d_residual", "dfr2d_rhs", "dfr2d_set_register", "dfr2d_get_register", "dfr2d_get_field",
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
-    "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc",
+    "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
@@ -91,7 +91,8 @@ def load():
     lib.dfr2d_exchange_counts.argtypes = [H, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.dfr2d_exchange_buffers.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.dfr2d_plan_vertices.argtypes = [H, C.POINTER(C.c_int64), _ip]
-    for name in ("dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update", "dfr2d_stage_sensor", "dfr2d_stage_visc"):
+    for name in ("dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update", "dfr2d_stage_sensor", "dfr2d_stage_visc",
+                 "dfr2d_stage_edges_interior"):
         getattr(lib, name).argtypes = [H, C.c_int]
     lib.dfr2d_step_finish.argtypes = [H, C.POINTER(StepInfo)]
     lib.dfr2d_launch_count.argtypes = [H]
@@ -284,6 +285,9 @@ class Dfr2d:
 
     def stage_sensor(self, rk):
         self._ck(self.lib.dfr2d_stage_sensor(self.h, rk))
+
+    def stage_edges_interior(self, rk):
+        self._ck(self.lib.dfr2d_stage_edges_interior(self.h, rk))
 
     def stage_visc(self, rk):
         self._ck(self.lib.dfr2d_stage_visc(self.h, rk))

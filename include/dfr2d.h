@@ -183,6 +183,10 @@ int dfr2d_stage_update(dfr2d_handle *h, int rk);  /* divergence, dt, SSP-RK upda
 enum { DFR2D_XCHG_EDGE = 0, DFR2D_XCHG_VERTEX = 1, DFR2D_XCHG_DISS = 2 };
 int dfr2d_stage_sensor(dfr2d_handle *h, int rk);
 int dfr2d_stage_visc(dfr2d_handle *h, int rk);
+/* Optional overlap hook: the numerical flux of the edges that touch no ghost column does not need the halo.  Call it
+ * after posting the EDGE exchange and before waiting for it; dfr2d_stage_edges then only unpacks and evaluates the
+ * boundary and cut edges.  Results are identical with or without this call. */
+int dfr2d_stage_edges_interior(dfr2d_handle *h, int rk);
 /* per-peer doubles (arrays of n_parts; every exchange is symmetric) and device buffers of exchange `which`;
  * which = DFR2D_XCHG_EDGE gives the same answers as dfr2d_halo_counts / dfr2d_halo_buffers */
 int dfr2d_exchange_counts(const dfr2d_handle *h, int which, int64_t *send_counts, int64_t *recv_counts);

@@ -255,8 +255,10 @@ def _multi_partition_step(devs, nsteps):
             for d in devs:
                 d.stage_sensor(rk)
             xv.run()
-            for d in devs:
+            for i, d in enumerate(devs):
                 d.stage_prepare(rk)
+                if (i + rk) % 2 == 0:
+                    d.stage_edges_interior(rk)       # optional overlap hook: results must not depend on it
             xe.run()
             for d in devs:
                 d.stage_edges(rk)
