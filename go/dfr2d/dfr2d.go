@@ -242,6 +242,8 @@ func (m *MultiSolver) Step() {
 		for _, s := range m.Parts {
 			s.check(C.dfr2d_stage_prepare(s.h, C.int(rk)), "dfr2d_stage_prepare")
 		}
+		// (an asynchronous Exchange would be posted here, dfr2d_stage_edges_interior called for every partition, and the
+		// exchange awaited before dfr2d_stage_edges: interior-edge fluxes do not need the halo)
 		m.Exchange(int(C.DFR2D_XCHG_EDGE))
 		for _, s := range m.Parts {
 			s.check(C.dfr2d_stage_edges(s.h, C.int(rk)), "dfr2d_stage_edges")
