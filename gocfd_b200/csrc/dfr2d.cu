@@ -1284,6 +1284,68 @@ extern "C" int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_
     return 0;
 }
 
+// ---- element renumbering for partition quality -------------------------------------------------
+// Reverse Cuthill-McKee over the element adjacency graph (elements sharing an edge).  PartitionMap.Split1D cuts the
+// element index range into contiguous pieces, so the cut size of a mesh is decided by its numbering: mesh-generator
+// numbering of the shipped NACA meshes is essentially random in space.  The host renumbers the elements with the
+// returned order BEFORE building the DG2D tables; nothing in the time loop changes.
+extern "C" int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
+                               int32_t *order) {
+    if (K <= 0 || NE < 0 || !edge_kL || !edge_kR || !edge_nconn || !order) { g_create_error = "bad rcm request"; return 1; }
+    std::vector<int> deg((size_t)K, 0), start((size_t)K + 1, 0), adj;
+    for (int64_t e = 0; e < NE; e++)
+        if (edge_nconn[e] == 2) { deg[edge_kL[e]]++; deg[edge_kR[e]]++; }
+    for (int64_t k = 0; k < K; k++) start[k + 1] = start[k] + deg[k];
+    adj.assign((size_t)start[K], 0);
+    {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int64_t e = 0; e < NE; e++)
+            if (edge_nconn[e] == 2) {
+                adj[fill[edge_kL[e]]++] = edge_kR[e];
+                adj[fill[edge_kR[e]]++] = edge_kL[e];
+            }
+    }
+    std::vector<char> seen((size_t)K, 0);
+    std::vector<int> level((size_t)K, -1), out, queue;
+    out.reserve((size_t)K);
+    auto bfs_far = [&](int root) {            // last node of a BFS from root with minimal degree in the last level
+        queue.assign(1, root);
+        std::vector<int> touched(1, root);
+        level[root] = 0;
+        int far = root;
+        for (size_t qi = 0; qi < queue.size(); qi++) {
+            const int u = queue[qi];
+            if (level[u] > level[far] || (level[u] == level[far] && deg[u] < deg[far])) far = u;
+            for (int t = start[u]; t < start[u + 1]; t++) {
+                const int w = adj[t];
+                if (!seen[w] && level[w] < 0) { level[w] = level[u] + 1; queue.push_back(w); touched.push_back(w); }
+            }
+        }
+        for (int t : touched) level[t] = -1;
+        return far;
+    };
+    for (int64_t s0 = 0; s0 < K; s0++) {
+        if (seen[s0]) continue;
+        int root = (int)s0;
+        for (int it = 0; it < 3; it++) root = bfs_far(root);       // pseudo-peripheral start node
+        const size_t first = out.size();
+        out.push_back(root);
+        seen[root] = 1;
+        std::vector<int> nb;
+        for (size_t qi = first; qi < out.size(); qi++) {
+            const int u = out[qi];
+            nb.clear();
+            for (int t = start[u]; t < start[u + 1]; t++)
+                if (!seen[adj[t]]) { seen[adj[t]] = 1; nb.push_back(adj[t]); }
+            std::sort(nb.begin(), nb.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
+            out.insert(out.end(), nb.begin(), nb.end());
+        }
+        std::reverse(out.begin() + (std::ptrdiff_t)first, out.end());
+    }
+    for (int64_t k = 0; k < K; k++) order[k] = out[(size_t)k];
+    return 0;
+}
+
 #ifdef DFR2D_PIPE_TIMING
 extern "C" int dfr2d_debug_pipe_clocks(unsigned long long out[8], int reset) {
     cudaMemcpyFromSymbol(out, g_pipe_clk, 8 * sizeof(unsigned long long));

@@ -41,6 +41,13 @@ class Mesh2D:
                         for k, v in bc_edges.items()}
 
 
+def renumber_elements(mesh, order):
+    """Mesh with element `new` = old element order[new] (vertices and boundary edges untouched)."""
+    order = np.asarray(order, dtype=np.int64)
+    assert sorted(order.tolist()) == list(range(mesh.K))
+    return Mesh2D(mesh.VX, mesh.VY, mesh.EToV[order], dict(mesh.BCEdges))
+
+
 def _su2_tokens(path):
     with open(path, "r") as f:
         for line in f:

@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -104,6 +104,7 @@ def load():
     lib.dfr2d_plan_sizes.argtypes = [H, lp]
     lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
     lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
+    lib.dfr2d_rcm_order.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _ip, _ip]
     _lib = lib
     return lib
 
@@ -151,6 +152,19 @@ def problem_struct(p):
         bp_edge=ii(p.bp_edge), bp_x=dd(p.bp_x), bp_y=dd(p.bp_y),
     )
     return s, keep
+
+
+def rcm_order(problem):
+    """order[new] = old element: reverse Cuthill-McKee over the element adjacency of `problem`'s edge table."""
+    lib = load()
+    order = np.zeros(problem.K, dtype=np.int32)
+    kl = np.ascontiguousarray(problem.edge_kL, dtype=np.int32)
+    kr = np.ascontiguousarray(problem.edge_kR, dtype=np.int32)
+    nc = np.ascontiguousarray(problem.edge_nconn, dtype=np.int32)
+    rc = lib.dfr2d_rcm_order(problem.K, problem.NE, _i(kl), _i(kr), _i(nc), _i(order))
+    if rc != 0:
+        raise Dfr2dError("dfr2d_rcm_order failed (%d): %s" % (rc, lib.dfr2d_last_error(None).decode()))
+    return order
 
 
 class Dfr2dError(RuntimeError):

@@ -212,6 +212,13 @@ int dfr2d_plan_halo(const dfr2d_plan *pl, int64_t *send_counts, int64_t *recv_co
  * per peer (2 per vertex: sigma, epsilon).  vertex_ids may be NULL to query the counts first. */
 int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_t *vertex_ids);
 
+/* Host-only helper for partition quality (no CUDA): reverse Cuthill-McKee order of the elements over the edge table
+ * (elements sharing an edge are adjacent).  order[new index] = old element.  Renumber the mesh with it before
+ * NewDFR2D so that the contiguous PartitionMap.Split1D ranges (utils/parallel_utils.go:172-192) are spatially compact;
+ * the reference wraps METIS for the same purpose in 3D only (DG3D/mesh/partitioner/mesh_partitioner.go). */
+int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
+                    int32_t *order);
+
 /* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
 int64_t dfr2d_launch_count(const dfr2d_handle *h);
 

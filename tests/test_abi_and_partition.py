@@ -190,3 +190,38 @@ def test_two_rank_gloo_dissipation_exchange():
     for pr, out in zip(procs, outs):
         assert pr.returncode == 0, out
         assert "OK" in out, out
+
+
+def test_rcm_renumbering_shrinks_the_cuts_of_an_unstructured_mesh():
+    """PartitionMap.Split1D cuts the element index range, so the halo size is decided by the mesh
+    numbering.  RCM order from the C ABI (host-only) on the shipped NACA0012 mesh, 8 partitions."""
+    from gocfd_b200 import lib
+    from gocfd_b200.host import readfiles as rf
+    mesh = rf.read_mesh(mesh_path("mesh_NACA0012_inv.su2"))
+    c = _case(1, mesh, InitType="Freestream")
+    p = c.problem
+    order = lib.rcm_order(p)
+    assert sorted(order.tolist()) == list(range(p.K))
+    c2 = _case(1, rf.renumber_elements(mesh, order), InitType="Freestream")
+    p2 = c2.problem
+    assert p2.K == p.K and p2.NE == p.NE and int((p2.edge_nconn == 1).sum()) == int((p.edge_nconn == 1).sum())
+
+    def cut_edges(prob, n_parts):
+        pm = PartitionMap(n_parts, prob.K)
+        sh = prob.edge_nconn == 2
+        bl = np.array([pm.get_bucket(int(k))[0] for k in prob.edge_kL[sh]])
+        br = np.array([pm.get_bucket(int(k))[0] for k in prob.edge_kR[sh]])
+        return int((bl != br).sum())
+
+    before, after = cut_edges(p, 8), cut_edges(p2, 8)
+    assert after < 0.5 * before, (before, after)
+    # bandwidth of the element adjacency: what RCM minimises
+    sh = p.edge_nconn == 2
+    bw0 = int(np.abs(p.edge_kL[sh].astype(np.int64) - p.edge_kR[sh]).max())
+    sh2 = p2.edge_nconn == 2
+    bw1 = int(np.abs(p2.edge_kL[sh2].astype(np.int64) - p2.edge_kR[sh2]).max())
+    assert bw1 < bw0
+    # and the plan of the renumbered mesh agrees: total halo of all partitions = 2 x cut edges
+    plans = [lib.Plan(p2, 8, r) for r in range(8)]
+    assert sum(pl.n_cut for pl in plans) == 2 * after
+    print("cut edges at 8 partitions: %d -> %d, adjacency bandwidth %d -> %d" % (before, after, bw0, bw1))

@@ -400,3 +400,36 @@ def test_c1_naca_p0_full_run_residual_history():
     # the run converges: the density residual drops by orders of magnitude from its first value
     assert max(0.0, rb[0]) < 1e-2
     dev.close()
+
+
+def test_rcm_renumbered_naca_multi_partition():
+    """the NACA mesh renumbered with dfr2d_rcm_order, 4 partitions: same physics as the original
+    numbering (solution permuted, differences only from edge-ownership round-off) and 1e-11 against the oracle."""
+    from gocfd_b200 import lib
+    from gocfd_b200.host import readfiles as rf
+    from oracle.euler2d_oracle import OracleSolver
+    kw = dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=100, Minf=0.5, Alpha=2.0)
+    mesh = rf.read_mesh(mesh_path("mesh_NACA0012_inv.su2"))
+    c0 = make(kw, mesh)
+    order = lib.rcm_order(c0.problem)
+    c1 = make(kw, rf.renumber_elements(mesh, order))
+    devs = [lib.Dfr2d(c1.problem, n_parts=4, part=r) for r in range(4)]
+    cut_rcm = sum(sum(d.halo_counts()[0]) for d in devs)
+    cut_orig = sum(sum(lib.Plan(c0.problem, 4, r).send_counts) for r in range(4))
+    assert cut_rcm < 0.5 * cut_orig
+    for d in devs:
+        d.set_state(c1.Q)
+    _multi_partition_step(devs, 5)
+    q1 = np.zeros_like(c1.Q)
+    for d in devs:
+        d.get_state(q1)
+    ora = OracleSolver(c1.problem)
+    ora.set_state(c1.Q)
+    ora.step(5)
+    assert rel_l2(q1, ora.get_state()) < TOL
+    one = lib.Dfr2d(c0.problem)
+    one.set_state(c0.Q)
+    one.step(5)
+    assert rel_l2(q1, one.get_state()[:, :, order]) < 1e-10
+    for d in devs + [one]:
+        d.close()
