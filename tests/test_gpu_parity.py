@@ -403,12 +403,14 @@ def test_c1_naca_p0_full_run_residual_history():
 
 
 def test_rcm_renumbered_naca_multi_partition():
-    """the NACA mesh renumbered with dfr2d_rcm_order, 4 partitions: same physics as the original
-    numbering (solution permuted, differences only from edge-ownership round-off) and 1e-11 against the oracle."""
+    """the NACA mesh renumbered with dfr2d_rcm_order, 4 partitions: 1e-11 against the oracle on the
+    same (renumbered) mesh.  Against the ORIGINAL numbering only the physics agrees: the reference's wave-speed
+    aggregate reads the owner side of each edge (edges.go:246-289) and ownership follows the numbering, so GlobalDT --
+    and with it the state after N steps -- moves at the 1e-7 level (SURVEY 8a parity hazard 3)."""
     from gocfd_b200 import lib
     from gocfd_b200.host import readfiles as rf
     from oracle.euler2d_oracle import OracleSolver
-    kw = dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=100, Minf=0.5, Alpha=2.0)
+    kw = dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=False, MaxIterations=100, Minf=0.5, Alpha=2.0, FinalTime=100.0)
     mesh = rf.read_mesh(mesh_path("mesh_NACA0012_inv.su2"))
     c0 = make(kw, mesh)
     order = lib.rcm_order(c0.problem)
@@ -430,6 +432,6 @@ def test_rcm_renumbered_naca_multi_partition():
     one = lib.Dfr2d(c0.problem)
     one.set_state(c0.Q)
     one.step(5)
-    assert rel_l2(q1, one.get_state()[:, :, order]) < 1e-10
+    assert rel_l2(q1, one.get_state()[:, :, order]) < 1e-5
     for d in devs + [one]:
         d.close()
