@@ -14,8 +14,11 @@
 #include "dfr2d_elem_mma.cuh"
 #include "dfr2d_elem_pipe.cuh"
 #include "dfr2d_elem_tma.cuh"
+#include "dfr2d_grad_mma.cuh"
 
 using namespace dfr2d;
+
+static bool grad_table_for(int N, const double *Div, const double *Bary, std::vector<double> &tb);
 
 static thread_local std::string g_create_error;
 
@@ -64,6 +67,9 @@ struct dfr2d_handle {
     int pfTiles = 0;
     int elemKernel = 4;               // 1: row-per-thread DFMA, 2: split-row DFMA, 3: DMMA, 4: pipelined DMMA (default)
     double *mmaFrags = nullptr;
+    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 2: DMMA k_grad_mma (DFR2D_GRAD_KERNEL)
+    double *gradTable = nullptr;
+    bool gradAttrSet = false;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
@@ -565,6 +571,12 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_upload(h, &h->mmaFrags, fr)) return rc;
     }
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
+    if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev);
+    if (ph.dissipation && h->gradKernel == 2) {
+        std::vector<double> tb;
+        grad_table_for(N, p->Div, p->Bary, tb);
+        if (int rc = dev_upload(h, &h->gradTable, tb)) return rc;
+    }
     CK(cudaDeviceSynchronize());
     return 0;
 }
@@ -931,6 +943,17 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
     ga.dissX = d.dissX; ga.dissY = d.dissY;
     ga.sc = h->sc; ga.par = (int)(h->stepIndex & 1); ga.stepIndex = h->stepIndex; ga.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->gradKernel == 2) {
+        DISPATCH_N(h->N, {
+            const size_t sm = GradMmaDim<NN>::kSmemBytes;
+            if (!h->gradAttrSet) {
+                cudaFuncSetAttribute(k_grad_mma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                h->gradAttrSet = true;
+            }
+            k_grad_mma<NN><<<blocks, kGradMmaThreads, sm, h->stream>>>(ga, h->gradTable);
+        });
+        return launch_check(h, "k_grad_mma");
+    }
     DISPATCH_N(h->N, {
         const size_t sm = (size_t)4 * (Dim<NN>::NpInt + Dim<NN>::NF3) * kElemsPerBlock * sizeof(double);
         k_grad<NN><<<blocks, kElemThreads, sm, h->stream>>>(ga);
@@ -1289,6 +1312,25 @@ extern "C" int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_
 // element index range into contiguous pieces, so the cut size of a mesh is decided by its numbering: mesh-generator
 // numbering of the shipped NACA meshes is essentially random in space.  The host renumbers the elements with the
 // returned order BEFORE building the DG2D tables; nothing in the time loop changes.
+static bool grad_table_for(int N, const double *Div, const double *Bary, std::vector<double> &tb) {
+    switch (N) {
+        case 0: build_grad_table<0>(Div, Bary, tb); return true;
+        case 1: build_grad_table<1>(Div, Bary, tb); return true;
+        case 2: build_grad_table<2>(Div, Bary, tb); return true;
+        case 3: build_grad_table<3>(Div, Bary, tb); return true;
+        case 4: build_grad_table<4>(Div, Bary, tb); return true;
+        default: return false;
+    }
+}
+
+extern "C" int64_t dfr2d_grad_mma_table(int N, const double *Div, const double *Bary, double *out, int64_t cap) {
+    std::vector<double> tb;
+    if (!Div || !Bary || !grad_table_for(N, Div, Bary, tb)) return -1;
+    if (out)
+        for (int64_t i = 0; i < cap && i < (int64_t)tb.size(); i++) out[i] = tb[i];
+    return (int64_t)tb.size();
+}
+
 extern "C" int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
                                int32_t *order) {
     if (K <= 0 || NE < 0 || !edge_kL || !edge_kR || !edge_nconn || !order) { g_create_error = "bad rcm request"; return 1; }

@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -105,6 +105,8 @@ def load():
     lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
     lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
     lib.dfr2d_rcm_order.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _ip, _ip]
+    lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
+    lib.dfr2d_grad_mma_table.restype = C.c_int64
     _lib = lib
     return lib
 
@@ -152,6 +154,19 @@ def problem_struct(p):
         bp_edge=ii(p.bp_edge), bp_x=dd(p.bp_x), bp_y=dd(p.bp_y),
     )
     return s, keep
+
+
+def grad_mma_table(problem):
+    """Operator table of the tensor-core gradient kernel for `problem`'s order (host-only; see include/dfr2d.h)."""
+    lib = load()
+    div = np.ascontiguousarray(problem.Div, dtype=np.float64)
+    bary = np.ascontiguousarray(problem.Bary, dtype=np.float64)
+    n = lib.dfr2d_grad_mma_table(problem.N, _d(div), _d(bary), None, 0)
+    if n < 0:
+        raise RuntimeError("dfr2d_grad_mma_table: bad request")
+    out = np.zeros(n)
+    lib.dfr2d_grad_mma_table(problem.N, _d(div), _d(bary), _d(out), n)
+    return out
 
 
 def rcm_order(problem):

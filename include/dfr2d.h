@@ -219,6 +219,13 @@ int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_t *vertex_i
 int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
                     int32_t *order);
 
+/* Host-only (no CUDA): the operator table the tensor-core gradient kernel (k_grad_mma, DFR2D_GRAD_KERNEL=2) stages in
+ * shared memory -- DFR.FluxElement.Div (raviart_thomas_element.go:249-297) cut to the rows and metric blocks that
+ * GetSolutionGradientUsingRTElement (euler.go:864-918) consumes, in DMMA.8x8x4 A-fragment lane order, followed by the
+ * Bary rows of those RT points.  Writes min(cap, needed) doubles to `out` and returns the needed count (<0: bad order).
+ * Exposed so that the layout can be checked on the CPU (tests/test_grad_mma_layout.py). */
+int64_t dfr2d_grad_mma_table(int N, const double *Div, const double *Bary, double *out, int64_t cap);
+
 /* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
 int64_t dfr2d_launch_count(const dfr2d_handle *h);
 

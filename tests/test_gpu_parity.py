@@ -169,9 +169,12 @@ def _smeared_sod_state(c, width=0.004):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4])
 @pytest.mark.parametrize("rk", [0, 2])
-def test_dissipation_rhs_parity(n, rk):
+@pytest.mark.parametrize("grad_kernel", [1, 2])
+def test_dissipation_rhs_parity(n, rk, grad_kernel, monkeypatch):
     """RHSQ with sensor, vertex merge, RT gradient, viscous edge flux, AddDissipation and the RHS
-    limiter; rk=2 also exercises the in-place limiting of the stage input (euler.go:605-609)."""
+    limiter; rk=2 also exercises the in-place limiting of the stage input (euler.go:605-609).
+    grad_kernel: 1 = constant-operand DFMA k_grad, 2 = tensor-core k_grad_mma (read at dfr2d_create)."""
+    monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
     c = _sod(n)
     assert c.problem.Dissipation
     q = _smeared_sod_state(c, 0.004 if n == 1 else 0.002)
@@ -187,8 +190,10 @@ def test_dissipation_rhs_parity(n, rk):
 
 
 @pytest.mark.parametrize("n", [2, 4])
-def test_sod_steps_with_dissipation(n):
+@pytest.mark.parametrize("grad_kernel", [1, 2])
+def test_sod_steps_with_dissipation(n, grad_kernel, monkeypatch):
     """Config C3: Sod tube, PerssonC0, global dt (incl. the viscous dt limit), 10 steps from a smeared front."""
+    monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
     c = _sod(n, CFL=2.0)
     c.Q = _smeared_sod_state(c)
     dev, ora = pair(c)
@@ -322,9 +327,11 @@ def test_multi_partition_naca_local_dt():
 
 
 @pytest.mark.parametrize("n_parts,n", [(2, 2), (3, 4), (4, 1)])
-def test_multi_partition_sod_with_dissipation(n_parts, n):
+@pytest.mark.parametrize("grad_kernel", [1, 2])
+def test_multi_partition_sod_with_dissipation(n_parts, n, grad_kernel, monkeypatch):
     """PerssonC0 across partitions -- shared-vertex max merge, Q_Face + ghost vertex epsilon,
     DissX/DissY edge rows.  Bitwise equal to the single-partition device run, 1e-11 against the oracle."""
+    monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
     from gocfd_b200 import lib
     from oracle.euler2d_oracle import OracleSolver
     c = _sod(n, CFL=2.0)

@@ -1,0 +1,76 @@
+"""A/B of the two RT-gradient kernels of the PerssonC0 path on one GPU (DFR2D_GRAD_KERNEL=1: constant-operand DFMA
+k_grad, =2: DMMA k_grad_mma): whole-step time, the stage_edges phase (k_edge + k_grad) per RK stage, and the
+relative L2 difference of the two states after the same number of steps.  One JSON line on stdout.
+
+    python tools/grad_kernel_ab.py [--nx 2000 --ny 500 --order 4 --steps 6]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nx", type=int, default=2000)
+    ap.add_argument("--ny", type=int, default=500)
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=6)
+    args = ap.parse_args()
+    import torch
+    import bench
+    from gocfd_b200 import lib
+    c = bench.build_case(args.nx, args.ny, args.order, dissipation=True)
+    p = c.problem
+    out = {"K": int(p.K), "N": int(p.N), "steps": args.steps}
+    states = {}
+    for gk in (1, 2):
+        os.environ["DFR2D_GRAD_KERNEL"] = str(gk)
+        dev = lib.Dfr2d(p)
+        dev.set_state(c.Q)
+        dev.step(2, sync=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        dev.step(args.steps, sync=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_step = e0.elapsed_time(e1) / args.steps
+        states[gk] = dev.get_state()
+        # phase timing of one more step through the stage API (single partition: no exchange in between)
+        ph = []
+        for rk in range(5):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+            ev[0].record()
+            dev.stage_sensor(rk)
+            ev[1].record()
+            dev.stage_prepare(rk)
+            ev[2].record()
+            dev.stage_edges(rk)
+            ev[3].record()
+            dev.stage_visc(rk)
+            ev[4].record()
+            dev.stage_update(rk)
+            ev[5].record()
+            ph.append(ev)
+        dev.step_finish(sync=True)
+        torch.cuda.synchronize()
+        names = ["sensor", "prepare", "edges+grad", "visc", "update"]
+        out["grad_kernel_%d" % gk] = {
+            "ms_per_step": ms_step, "ms_per_stage": ms_step / 5,
+            "phase_ms_mean": {nm: float(np.mean([e[i].elapsed_time(e[i + 1]) for e in ph])) for i, nm in enumerate(names)},
+            "finite": bool(np.isfinite(states[gk]).all()),
+        }
+        dev.close()
+    a, b = states[1], states[2]
+    out["rel_l2_state_2_vs_1"] = float(np.linalg.norm(a - b) / np.linalg.norm(a))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
