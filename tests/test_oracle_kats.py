@@ -334,3 +334,111 @@ def test_su2_reader_naca():
     m = read_su2(mesh_path("mesh_NACA0012_inv.su2"))
     assert m.K == 10216 and len(m.VX) == 5233
     assert {k: len(v) for k, v in m.BCEdges.items()} == {"wall": 200, "far": 50}
+
+
+# ---- DG2D/dfr_startup_test.go:224-247, :293-368 (TestDivergence) and :370-489 (TestGradient) ---------------------
+
+def _equi_tri_mesh(angle):
+    """CreateEquiTriMesh: one equilateral triangle of side 5, rotated by `angle` degrees."""
+    from gocfd_b200.host.readfiles import Mesh2D
+    scale = 5.0
+    y_height = scale * math.sin(math.pi * 60.0 / 180.0)
+    vx = np.array([-scale * 0.5, scale * 0.5, 0.0])
+    vy = np.array([-y_height / 3.0, -y_height / 3.0, 2.0 * y_height / 3.0])
+    ca, sa = math.cos(2.0 * math.pi * angle / 360.0), math.sin(2.0 * math.pi * angle / 360.0)
+    return Mesh2D(vx * ca + vy * sa, -vx * sa + vy * ca, [[0, 1, 2]], {})
+
+
+def _project_flux_onto_rt_space(dfr, fx, fy):
+    """ProjectFluxOntoRTSpace (DG2D/dfr_startup.go:316-358): [NpFlux, K]."""
+    rt = dfr.FluxElement
+    ni, ne = rt.NpInt, rt.NpEdge
+    ji, jd = dfr.Jinv, dfr.Jdet
+    ft0 = jd * (ji[:, 0] * fx + ji[:, 1] * fy)
+    ft1 = jd * (ji[:, 2] * fx + ji[:, 3] * fy)
+    fp = np.empty_like(fx)
+    fp[:ni] = ft0[:ni]
+    fp[ni:2 * ni] = ft1[ni:2 * ni]
+    e0 = 2 * ni
+    fp[e0:e0 + ne] = -ft1[e0:e0 + ne]
+    fp[e0 + ne:e0 + 2 * ne] = (1.0 / math.sqrt(2.0)) * (ft0[e0 + ne:e0 + 2 * ne] + ft1[e0 + ne:e0 + 2 * ne])
+    fp[e0 + 2 * ne:] = -ft0[e0 + 2 * ne:]
+    return fp
+
+
+def _divergence_check(dfr):
+    rt = dfr.FluxElement
+    ni, ne = rt.NpInt, rt.NpEdge
+    x, y = dfr.flux_xy()
+    for order in range(1, dfr.N + 1):
+        fx, fy = x ** order, y ** order
+        want = order * (x ** (order - 1) + y ** (order - 1))
+        tol = np.abs(fx).max() * 1.0e-9
+        fp = _project_flux_onto_rt_space(dfr, fx, fy)
+        assert np.abs(rt.Div @ fp / dfr.Jdet - want).max() <= tol
+        # SetNormalFluxOnEdges: physical unit normal scaled by ||n|| (IInII) on the edge rows, same divergence
+        for e in range(3):
+            rows = slice(2 * ni + e * ne, 2 * ni + (e + 1) * ne)
+            fp[rows] = dfr.IInII[e] * (dfr.FaceNorm[0, e] * fx[rows] + dfr.FaceNorm[1, e] * fy[rows])
+        assert np.abs(rt.Div @ fp / dfr.Jdet - want).max() <= tol
+
+
+@pytest.mark.parametrize("angle", [0, 15, 25, 45, 90, 180, 210, 270, 310])
+def test_rt_divergence_rotated_equilateral(angle):
+    """TestDivergence: RT divergence of (x^m, y^m), m = 1..4, is exact at N=4 on a rotated equilateral triangle,
+    through the Piola projection and through the IInII-scaled physical normals (tolerance 1e-9 max|Fx|)."""
+    _divergence_check(DFR2D(4, _equi_tri_mesh(angle)))
+
+
+def test_rt_divergence_test_tris_5():
+    _divergence_check(new_dfr2d(4, mesh_path("test_tris_5.neu")))
+
+
+def test_gradient_on_flux_points():
+    """TestGradient (N=3, test_tris_6.neu): d/dx, d/dy of x+y, x^2+y^2, x^3+y^3 at the RT points, (a) through
+    FluxDr/FluxDs + Jinv and (b) through the RT element, Div . (DXMetric (.) U) with U interpolated to the edges by
+    FluxEdgeInterp -- the operator chain of GetSolutionGradientUsingRTElement.  Tolerance 1e-6."""
+    dfr = new_dfr2d(3, mesh_path("test_tris_6.neu"))
+    assert dfr.K == 2
+    rt = dfr.FluxElement
+    ni = rt.NpInt
+    x, y = dfr.flux_xy()
+    dxm, dym = dfr.metrics()
+    for m in (1, 2, 3):
+        u_int = (x ** m + y ** m)[:ni]
+        dx_want, dy_want = m * x ** (m - 1), m * y ** (m - 1)
+        qr, qs = dfr.FluxDr @ u_int, dfr.FluxDs @ u_int
+        ji = dfr.Jinv
+        np.testing.assert_allclose(qr * ji[:, 0] + qs * ji[:, 2], dx_want, atol=1e-6)
+        np.testing.assert_allclose(qr * ji[:, 1] + qs * ji[:, 3], dy_want, atol=1e-6)
+        un = np.concatenate([u_int, u_int, dfr.FluxEdgeInterp @ u_int])
+        np.testing.assert_allclose(rt.Div @ (dxm * un), dx_want, atol=1e-6)
+        np.testing.assert_allclose(rt.Div @ (dym * un), dy_want, atol=1e-6)
+
+
+# ---- DG2D/raviart_thomas_element_test.go:17-163 (TestRTElement) -----------------------------------------------
+
+@pytest.mark.parametrize("p_rt", [1, 2, 3, 4, 5])
+def test_rt_element_polynomial_divergence(p_rt):
+    """DivergencePolynomialField_Test: for RT order P = N+1 the divergence operator `Div` applied to the DOF projection
+    of the three reference polynomial fields of order 0..P equals the analytic divergence at every RT point
+    (tolerance 1e-9 max|f1|, the reference's)."""
+    from gocfd_b200.host.dg2d.elements import RTElement
+    rt = RTElement(p_rt)
+    r, s = rt.R, rt.S
+    dof = np.asarray(rt.DOFVectors)
+    fields = [
+        (lambda p: ((r + s + 10) ** p, (10 * (r + s)) ** p),
+         lambda p: p * ((r + s + 10) ** (p - 1) + 10 * (10 * (r + s)) ** (p - 1)) if p > 0 else 0 * r),
+        (lambda p: (r ** p, s ** p),
+         lambda p: p * (r ** (p - 1) + s ** (p - 1)) if p > 0 else 0 * r),
+        (lambda p: ((s + 10) ** p, (10 * r) ** p),
+         lambda p: 0 * r),
+    ]
+    for f, div in fields:
+        for p in range(0, p_rt + 1):
+            f1, f2 = f(p)
+            proj = dof[:, 0] * f1 + dof[:, 1] * f2          # ProjectFunctionOntoDOF
+            max_f = np.abs(f1).max()
+            tol = 1e-9 * max_f if max_f >= 1e-9 else 1e-9
+            assert np.abs(rt.Div @ proj - div(p)).max() <= tol
