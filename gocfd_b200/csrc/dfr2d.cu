@@ -948,6 +948,7 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
             const size_t sm = GradMmaDim<NN>::kSmemBytes;
             if (!h->gradAttrSet) {
                 cudaFuncSetAttribute(k_grad_mma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaFuncSetAttribute(k_grad_mma<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
                 h->gradAttrSet = true;
             }
             k_grad_mma<NN><<<blocks, kGradMmaThreads, sm, h->stream>>>(ga, h->gradTable);

@@ -1,8 +1,9 @@
 /*
  * ORACLE -- test infrastructure, not product code.
  *
- * Plain C (OpenMP) restatement of the reference's INVISCID per-stage 2D Euler DFR right-hand
- * side and SSP-RK(5,4) step, organised the way the reference runs it on the CPU: the same
+ * Plain C (OpenMP) restatement of the reference's per-stage 2D Euler DFR right-hand side and
+ * SSP-RK(5,4) step -- the inviscid path and the PerssonC0 sensor / artificial-dissipation path --
+ * organised the way the reference runs it on the CPU: the same
  * phases with a barrier between them (StepWorker, model_problems/Euler2D/euler.go:420-653),
  * materialised Q_Face / EdgeStore / F_RT_DOF / RHSQ arrays, operator applications as
  * [m x n]·[n x K] products, threads standing in for the goroutine partitions.  It consumes the
@@ -12,8 +13,9 @@
  * are compared in tests/test_c_oracle.py); (2) the CPU baseline bench.py times on all host
  * cores ("port": the Go toolchain is absent, this is NOT the Go solver).
  * Parity status: pinned only through the numpy oracle and the reference KATs it passes
- * (tests/test_oracle_kats.py); see DESIGN.md section 5.  PerssonC0 dissipation is not restated
- * here (ora_create refuses it) -- the numpy oracle covers that path.
+ * (tests/test_oracle_kats.py); see DESIGN.md section 5.  The dissipation phases follow the Go
+ * data flow literally: materialised DXMetric/DYMetric, DOFX/DOFY, GradX/GradY, Epsilon, DissX/DissY,
+ * the viscous edge store and the DissDOF/DissDiv scratch (dissipation.go, edges.go:151-244).
  *
  * Reference citations are file:line under model_problems/Euler2D/ unless noted.
  */
@@ -38,6 +40,16 @@ typedef struct ora {
     double *EdgeFlux, *EdgeQ, *Agg; /* EdgeStore: [4][NE][NpEdge] x2, Aggregates [NE] */
     double Time, GlobalDT;
     long StepCount;
+    /* PerssonC0 dissipation (dissipation.go:90-217, dfr_shock_capturing.go:71-107) */
+    int diss;
+    long NV;
+    double *Div, *V, *Vinv, *Mass, *D, *P, *mf, *Bary, *edge_len, *nxk, *nyk;
+    int *EToV;
+    double *DXMetric, *DYMetric;            /* [NpFlux x K]  dfr_startup.go:213-254 */
+    double *Se, *SigmaScalar, *EpsilonScalar, *SigmaVertex, *EpsVertex, *Epsilon;
+    double *DissX, *DissY, *EdgeVisc, *AggV, *DTVisc;
+    double *LS0, *LS1, *LS2, *DOFX, *DOFY;  /* LScratch [NpInt x K] x3, DissDOF/DissDOF2 [NpFlux x K] */
+    double Kappa, Eps0;
 } ora;
 
 static double *dcopy(const double *s, long n) {
@@ -236,7 +248,6 @@ static void roe_er_flux(double gamma, const double *ql, const double *qr, double
 }
 
 ora *ora_create(const dfr2d_problem *p) {
-    if (p->dissipation) return NULL;
     ora *o = (ora *)calloc(1, sizeof(ora));
     o->p = *p;
     int N = p->N;
@@ -274,6 +285,57 @@ ora *ora_create(const dfr2d_problem *p) {
     o->EdgeFlux = (double *)calloc((size_t)(4L * NE * ne), sizeof(double));
     o->EdgeQ = (double *)calloc((size_t)(4L * NE * ne), sizeof(double));
     o->Agg = (double *)calloc((size_t)(NE > 0 ? NE : 1), sizeof(double));
+    o->diss = p->dissipation != 0;
+    if (o->diss) {
+        long NV = p->NV;
+        o->NV = NV;
+        o->Div = dcopy(p->Div, (long)nf * nf);
+        o->V = dcopy(p->V, (long)ni * ni); o->Vinv = dcopy(p->Vinv, (long)ni * ni);
+        o->Mass = dcopy(p->MassMatrix, (long)ni * ni); o->D = dcopy(p->D, (long)ni * ni); o->P = dcopy(p->P, (long)ni * ni);
+        o->mf = dcopy(p->ModeFilter, ni);
+        o->Bary = dcopy(p->Bary, 3L * nf);
+        o->edge_len = dcopy(p->edge_len, NE);
+        o->nxk = dcopy(p->FaceNormX, 3 * K); o->nyk = dcopy(p->FaceNormY, 3 * K);
+        o->EToV = icopy(p->EToV, 3 * K);
+        /* NewScalarDissipation: Kappa 5 unless given, Eps0 fixed before the override (dissipation.go:140-147) */
+        o->Kappa = 5.0;
+        o->Eps0 = o->Kappa / 1.5;
+        if (p->Kappa != 0.0) o->Kappa = p->Kappa;
+        /* CalculateRTBasedDerivativeMetrics, DG2D/dfr_startup.go:213-254 */
+        o->DXMetric = dcopy(NULL, (long)nf * K); o->DYMetric = dcopy(NULL, (long)nf * K);
+        for (long k = 0; k < K; k++) {
+            const double *ji = o->Jinv + 4 * k;
+            double oojd = 1.0 / o->Jdet[k];
+            for (int i = 0; i < ni; i++) {
+                o->DXMetric[(long)i * K + k] = ji[0]; o->DYMetric[(long)i * K + k] = ji[1];
+                o->DXMetric[(long)(i + ni) * K + k] = ji[2]; o->DYMetric[(long)(i + ni) * K + k] = ji[3];
+            }
+            for (int fn = 0; fn < 3; fn++) {
+                double iin = o->IInII[(long)fn * K + k];
+                for (int i = 0; i < ne; i++) {
+                    long r = 2 * ni + fn * ne + i;
+                    o->DXMetric[r * K + k] = oojd * o->nxk[(long)fn * K + k] * iin;
+                    o->DYMetric[r * K + k] = oojd * o->nyk[(long)fn * K + k] * iin;
+                }
+            }
+        }
+        o->Se = (double *)calloc((size_t)K, sizeof(double));
+        o->SigmaScalar = (double *)calloc((size_t)K, sizeof(double));
+        o->EpsilonScalar = (double *)calloc((size_t)K, sizeof(double));
+        o->SigmaVertex = (double *)calloc((size_t)(NV > 0 ? NV : 1), sizeof(double));
+        o->EpsVertex = (double *)calloc((size_t)(NV > 0 ? NV : 1), sizeof(double));
+        o->Epsilon = (double *)calloc((size_t)((long)nf * K), sizeof(double));
+        o->DissX = (double *)calloc((size_t)(4L * nf * K), sizeof(double));
+        o->DissY = (double *)calloc((size_t)(4L * nf * K), sizeof(double));
+        o->EdgeVisc = (double *)calloc((size_t)(4L * NE * ne), sizeof(double));
+        o->AggV = (double *)calloc((size_t)(NE > 0 ? NE : 1), sizeof(double));
+        o->DTVisc = (double *)calloc((size_t)K, sizeof(double));
+        o->LS0 = (double *)calloc((size_t)((long)ni * K), sizeof(double));
+        o->LS1 = (double *)calloc((size_t)((long)ni * K), sizeof(double));
+        o->LS2 = (double *)calloc((size_t)((long)ni * K), sizeof(double));
+        o->DOFX = (double *)calloc((size_t)((long)nf * K), sizeof(double));
+        o->DOFY = (double *)calloc((size_t)((long)nf * K), sizeof(double));
+    }
     return o;
 }
 
@@ -285,6 +347,13 @@ void ora_destroy(ora *o) {
     for (int r = 0; r < 5; r++) free(o->Q[r]);
     free(o->Residual); free(o->RHSQ); free(o->Q_Face); free(o->F_RT_DOF); free(o->DT);
     free(o->EdgeFlux); free(o->EdgeQ); free(o->Agg);
+    if (o->diss) {
+        free(o->Div); free(o->V); free(o->Vinv); free(o->Mass); free(o->D); free(o->P); free(o->mf); free(o->Bary);
+        free(o->edge_len); free(o->nxk); free(o->nyk); free(o->EToV); free(o->DXMetric); free(o->DYMetric);
+        free(o->Se); free(o->SigmaScalar); free(o->EpsilonScalar); free(o->SigmaVertex); free(o->EpsVertex);
+        free(o->Epsilon); free(o->DissX); free(o->DissY); free(o->EdgeVisc); free(o->AggV); free(o->DTVisc);
+        free(o->LS0); free(o->LS1); free(o->LS2); free(o->DOFX); free(o->DOFY);
+    }
     free(o);
 }
 
@@ -297,6 +366,9 @@ int ora_threads(void) {
 }
 
 void ora_set_state(ora *o, const double *Q) { memcpy(o->Q[0], Q, sizeof(double) * 4 * (size_t)o->NpInt * (size_t)o->K); }
+void ora_set_register(ora *o, int reg, const double *Q) {
+    if (reg >= 0 && reg < 5) memcpy(o->Q[reg], Q, sizeof(double) * 4 * (size_t)o->NpInt * (size_t)o->K);
+}
 void ora_get_state(ora *o, double *Q) { memcpy(Q, o->Q[0], sizeof(double) * 4 * (size_t)o->NpInt * (size_t)o->K); }
 void ora_residual(ora *o, double *maxR) {
     long n1 = (long)o->NpInt * o->K;
@@ -324,7 +396,193 @@ static void op_apply(const double *A, int m, int n, const double *X, double *Y, 
 
 #define BLK 256
 
-/* one RK stage: StepWorker euler.go:420-653 (inviscid branches) */
+/* ---- PerssonC0 dissipation phases --------------------------------------------------------------------------- */
+
+/* ModeAliasShockFinder.UpdateSeMoment, DG2D/dfr_shock_capturing.go:142-166 */
+static void update_se_moment(ora *o, const double *rho) {
+    const long K = o->K;
+    const int ni = o->NpInt;
+    op_apply(o->P, ni, ni, rho, o->LS0, K, 0, K);
+    op_apply(o->Mass, ni, ni, rho, o->LS1, K, 0, K);
+    op_apply(o->D, ni, ni, rho, o->LS2, K, 0, K);
+    for (long k = 0; k < K; k++) {
+        double num = 0.0, den = 0.0;
+        for (int i = 0; i < ni; i++) {
+            long ind = k + (long)i * K;
+            double di = o->LS2[ind];
+            num += di * o->LS0[ind];
+            den += rho[ind] * o->LS1[ind];
+        }
+        o->Se[k] = log10(num / den);
+    }
+}
+
+/* UpdateShockFinderSigma dissipation.go:491-518 (sigma lives outside the loop, as there) and
+ * CalculateElementViscosity :397-412 */
+static void update_sigma_and_viscosity(ora *o) {
+    const long K = o->K;
+    const double kappa = o->Kappa;
+    const double S0 = 4.0 / pow((double)(o->N + 1), 4.0);
+    const double left = S0 - kappa, right = S0 + kappa;
+    const double ookappa = 0.5 / kappa;
+    double sigma = 0.0;
+    for (long k = 0; k < K; k++) {
+        double se = o->Se[k];
+        if (se < left) sigma = 0.0;
+        else if (se >= left && se <= right) sigma = 0.5 * (1.0 + sin(M_PI * ookappa * (se - S0)));
+        else if (se > right) sigma = 1.0;
+        o->SigmaScalar[k] = sigma;
+    }
+    for (long k = 0; k < K; k++) o->EpsilonScalar[k] = o->Eps0 * o->hK[k] * o->SigmaScalar[k];
+}
+
+/* MergeElementScalarToVertices with Max, euler.go:1048-1065: the sorted (vertex, element) sweep resets a vertex at
+ * its first element and maxes over the rest -- i.e. the max over the incident elements; untouched vertices keep
+ * their value */
+static void merge_to_vertices(ora *o, const double *elem, double *vert, char *seen) {
+    memset(seen, 0, (size_t)(o->NV > 0 ? o->NV : 1));
+    for (long k = 0; k < o->K; k++)
+        for (int v = 0; v < 3; v++) {
+            int vv = o->EToV[3 * k + v];
+            if (!seen[vv]) { vert[vv] = elem[k]; seen[vv] = 1; }
+            else if (elem[k] > vert[vv]) vert[vv] = elem[k];
+        }
+}
+
+/* limitAndFilterSolution dissipation.go:606-622 on the columns [k0,k1) of one variable */
+static void limit_and_filter(ora *o, double *U, double *scratch, long k0, long k1) {
+    const long K = o->K;
+    const int ni = o->NpInt;
+    op_apply(o->Vinv, ni, ni, U, scratch, K, k0, k1);
+    for (int i = 1; i < ni; i++)
+        for (long k = k0; k < k1; k++) {
+            double alpha = sin(0.5 * M_PI * o->SigmaScalar[k]);
+            scratch[k + K * i] *= o->mf[i] * (1.0 - alpha);
+        }
+    op_apply(o->V, ni, ni, scratch, U, K, k0, k1);
+}
+
+/* EdgeStore.GetEdgeValues edges.go:93-113: slice of edge `e` as element k sees it and the sign (+1 owner, -1 not) */
+static inline int edge_sign(const ora *o, long e, long k) { return o->kL[e] == k ? 1 : -1; }
+
+/* CalculateEpsilonGradient dissipation.go:244-272 (C0) over GetSolutionGradientUsingRTElement euler.go:864-918 */
+static void calculate_epsilon_gradient(ora *o, const double *qqq) {
+    const long K = o->K, NE = o->NE;
+    const int ni = o->NpInt, ne = o->NpEdge, nf = o->NpFlux;
+    for (int n = 0; n < 4; n++) {
+        const double *Q = qqq + (long)n * ni * K;
+        for (long k = 0; k < K; k++)
+            for (int i = 0; i < ni; i++) {
+                long ind = k + (long)i * K, ind2 = k + (long)(i + ni) * K;
+                double Un = Q[ind];
+                o->DOFX[ind] = o->DXMetric[ind] * Un; o->DOFY[ind] = o->DYMetric[ind] * Un;
+                o->DOFX[ind2] = o->DXMetric[ind2] * Un; o->DOFY[ind2] = o->DYMetric[ind2] * Un;
+            }
+        for (long k = 0; k < K; k++)
+            for (int edgeNum = 0; edgeNum < 3; edgeNum++) {
+                long e = o->etoe[3 * k + edgeNum];
+                const double *edgeVals = o->EdgeQ + ((long)n * NE + e) * ne;
+                int sign = edge_sign(o, e, k);
+                int shift = edgeNum * ne;
+                for (int i = 0; i < ne; i++) {
+                    int ii = sign < 0 ? ne - 1 - i : i;
+                    long ind = k + (long)(2 * ni + i + shift) * K;
+                    double Un = edgeVals[ii];
+                    o->DOFX[ind] = o->DXMetric[ind] * Un;
+                    o->DOFY[ind] = o->DYMetric[ind] * Un;
+                }
+            }
+        double *GX = o->DissX + (long)n * nf * K, *GY = o->DissY + (long)n * nf * K;
+#pragma omp parallel for schedule(static)
+        for (long b = 0; b < (K + BLK - 1) / BLK; b++) {
+            long k0 = b * BLK, k1 = k0 + BLK < K ? k0 + BLK : K;
+            op_apply(o->Div, nf, nf, o->DOFX, GX, K, k0, k1);
+            op_apply(o->Div, nf, nf, o->DOFY, GY, K, k0, k1);
+        }
+        for (long x = 0; x < (long)nf * K; x++) { GX[x] *= o->Epsilon[x]; GY[x] *= o->Epsilon[x]; }
+    }
+}
+
+/* StoreEdgeViscousFlux edges.go:151-244 and the viscous half of StoreEdgeAggregates edges.go:274-286 */
+static void store_edge_viscous_flux(ora *o) {
+    const long K = o->K, NE = o->NE;
+    const int ni = o->NpInt, ne = o->NpEdge, nf = o->NpFlux;
+    const double Omega = 1.0 * (double)(o->N * o->N);
+#pragma omp parallel for schedule(static)
+    for (long e = 0; e < NE; e++) {
+        long kL = o->kL[e];
+        long kR = o->nconn[e] == 2 ? o->kR[e] : 0;   /* ConnectedTris[1] is 0 for one-tri edges (unused there) */
+        int shiftL = ne * o->numL[e], shiftR = ne * (o->nconn[e] == 2 ? o->numR[e] : 0);
+        double nxL = o->nxL[e], nyL = o->nyL[e];
+        double nxR = nxL, nyR = nyL;                 /* normalR := GetFaceNormal(kLGlobal, edgeNumberL), edges.go:175 */
+        double ooedgeLength = 1.0 / o->edge_len[e];
+        for (int n = 0; n < 4; n++) {
+            const double *DX = o->DissX + (long)n * nf * K, *DY = o->DissY + (long)n * nf * K;
+            double *vf = o->EdgeVisc + ((long)n * NE + e) * ne;
+            if (o->nconn[e] == 1) {
+                for (int i = 0; i < ne; i++) {
+                    long indL = kL + (long)(2 * ni + shiftL + i) * K;
+                    vf[i] = nxL * DX[indL] + nyL * DY[indL];
+                }
+            } else {
+                /* both GetEdgeValues calls of edges.go:225-228 return the one stored (owner-side) slice */
+                const double *edgeQL = o->EdgeQ + ((long)n * NE + e) * ne, *edgeQR = edgeQL;
+                for (int i = 0; i < ne; i++) {
+                    long indL = kL + (long)(2 * ni + shiftL + i) * K;
+                    long indR = kR + (long)(2 * ni + shiftR + ne - 1 - i) * K;
+                    double vFL = nxL * DX[indL] + nyL * DY[indL];
+                    double vFR = nxR * DX[indR] + nyR * DY[indR];
+                    vf[i] = 0.5 * (vFL + vFR);
+                    double LambdaAvg = 0.5 * (o->Epsilon[indL] + o->Epsilon[indR]);
+                    int ii = ne - 1 - i;
+                    vf[i] -= (Omega * LambdaAvg * ooedgeLength) * (edgeQL[i] - edgeQR[ii]);
+                }
+            }
+        }
+        double oohKVisc = 1.0 / o->hK[kL];
+        double m = -DBL_MAX;
+        for (int i = 0; i < ne; i++) {
+            double v = oohKVisc * oohKVisc * o->Epsilon[kL + (long)(2 * ni + shiftL + i) * K];
+            m = v > m ? v : m;
+        }
+        o->AggV[e] = m;
+    }
+}
+
+/* AddDissipation dissipation.go:274-346 for variable n on the columns [k0,k1): RHSQ += (1/Jdet) DivInt . DOF */
+static void add_dissipation(ora *o, int n, double *rhs, long k0, long k1) {
+    const long K = o->K, NE = o->NE;
+    const int ni = o->NpInt, ne = o->NpEdge, nf = o->NpFlux;
+    const double *DiX = o->DissX + (long)n * nf * K, *DiY = o->DissY + (long)n * nf * K;
+    double *DOF = o->DOFX, *DIV = o->LS0;        /* DissDOF / DissDiv scratch (column ranges are disjoint) */
+    for (long k = k0; k < k1; k++) {
+        double jd = o->Jdet[k];
+        const double *ji = o->Jinv + 4 * k;
+        for (int i = 0; i < ni; i++) {
+            long ind = k + K * i, ind2 = k + K * (i + ni);
+            DOF[ind] = jd * (ji[0] * DiX[ind] + ji[1] * DiY[ind]);
+            DOF[ind2] = jd * (ji[2] * DiX[ind] + ji[3] * DiY[ind]);
+        }
+        for (int edgeNum = 0; edgeNum < 3; edgeNum++) {
+            double IInII = o->IInII[k + K * edgeNum];
+            int shift = ne * edgeNum;
+            long e = o->etoe[3 * k + edgeNum];
+            const double *edgeFlux = o->EdgeVisc + ((long)n * NE + e) * ne;
+            int sign = edge_sign(o, e, k);
+            for (int i = 0; i < ne; i++) {
+                int ii = sign == -1 ? ne - 1 - i : i;
+                DOF[k + (long)(2 * ni + i + shift) * K] = edgeFlux[ii] * IInII * (double)sign;
+            }
+        }
+    }
+    op_apply(o->DivInt, ni, nf, DOF, DIV, K, k0, k1);
+    for (long k = k0; k < k1; k++) {
+        double oojd = 1.0 / o->Jdet[k];
+        for (int i = 0; i < ni; i++) rhs[k + (long)i * K] += oojd * DIV[k + (long)i * K];
+    }
+}
+
+/* one RK stage: StepWorker euler.go:420-653 */
 static void stage(ora *o, int rk) {
     const dfr2d_problem *p = &o->p;
     const long K = o->K, NE = o->NE;
@@ -332,6 +590,34 @@ static void stage(ora *o, int rk) {
     const double gamma = p->FSFar.Gamma;
     double *qqq = o->Q[rk];
     const long nblk = (K + BLK - 1) / BLK;
+
+    if (o->diss) {
+        /* euler.go:574-616: sensor, element viscosity, element->vertex max, vertex->element mean,
+         * InterpolateEpsilonSigma (dissipation.go:219-242), stage-2 limiter of the stage input */
+        update_se_moment(o, qqq);
+        update_sigma_and_viscosity(o);
+        char *seen = (char *)malloc((size_t)(o->NV > 0 ? o->NV : 1));
+        merge_to_vertices(o, o->SigmaScalar, o->SigmaVertex, seen);
+        merge_to_vertices(o, o->EpsilonScalar, o->EpsVertex, seen);
+        free(seen);
+        for (long k = 0; k < K; k++) {          /* MergeVertexScalarToElement(sum, div3), euler.go:1067-1086 */
+            double acc = 0.0;
+            for (int v = 0; v < 3; v++) acc = acc + o->SigmaVertex[o->EToV[v + 3 * k]];
+            o->SigmaScalar[k] = acc / 3.0;
+        }
+        for (long k = 0; k < K; k++) {
+            double v3[3] = {o->EpsVertex[o->EToV[3 * k]], o->EpsVertex[o->EToV[3 * k + 1]], o->EpsVertex[o->EToV[3 * k + 2]]};
+            for (int i = 0; i < nf; i++) {
+                const double *b = o->Bary + 3 * i;
+                double acc = b[0] * v3[0];
+                acc += b[1] * v3[1];
+                acc += b[2] * v3[2];
+                o->Epsilon[k + (long)i * K] = acc;
+            }
+        }
+        if (rk == 2)
+            for (int n = 0; n < 4; n++) limit_and_filter(o, qqq + (long)n * ni * K, o->LS2, 0, K);
+    }
 
     /* InterpolateSolutionToEdges, edges.go:485-491 */
 #pragma omp parallel for schedule(static)
@@ -397,21 +683,35 @@ static void stage(ora *o, int rk) {
         o->Agg[e] = amax;
     }
 
+    if (o->diss) {
+        calculate_epsilon_gradient(o, qqq);   /* euler.go:624-628 */
+        store_edge_viscous_flux(o);           /* euler.go:629-635 */
+    }
+
     /* CalcElementMaxWaveSpeed edges.go:291-323, InitializeDT euler.go:655-663 */
-    double gmax = -DBL_MAX;
-#pragma omp parallel for schedule(static) reduction(max : gmax)
+    double gmax = -DBL_MAX, gmaxv = -DBL_MAX;
+    const int diss = o->diss;
+#pragma omp parallel for schedule(static) reduction(max : gmax, gmaxv)
     for (long k = 0; k < K; k++) {
         double dt = rk == 0 ? -100.0 : o->DT[k];
         for (int e = 0; e < 3; e++) {
             double a = o->Agg[o->etoe[3 * k + e]];
             if (a > dt) dt = a;
             if (a > gmax) gmax = a;
+            if (diss) {
+                double av = o->AggV[o->etoe[3 * k + e]];
+                if (av > gmaxv) gmaxv = av;
+                o->DTVisc[k] = fmax(o->DTVisc[k], av);
+            }
         }
         o->DT[k] = dt;
     }
     /* calculateGlobalDT euler.go:945-971 / CalculateLocalDT :973-1002 */
+    const double NP12 = (double)((o->N + 1) * (o->N + 1));
+    const double C_diff = 1.0 / NP12;
     if (!p->local_time_stepping) {
         o->GlobalDT = p->CFL / fmax(0.0, gmax);
+        if (diss) o->GlobalDT = fmin(o->GlobalDT, C_diff / fmax(0.0, gmaxv));
         if (o->Time + o->GlobalDT > p->FinalTime) o->GlobalDT = p->FinalTime - o->Time;
     }
     const double gdt = o->GlobalDT;
@@ -426,6 +726,12 @@ static void stage(ora *o, int rk) {
     for (long b = 0; b < nblk; b++) {
         long k0 = b * BLK, k1 = k0 + BLK < K ? k0 + BLK : K;
         for (long k = k0; k < k1; k++) o->DT[k] = local ? cfl / o->DT[k] : gdt;
+        if (local && diss)
+            for (long k = k0; k < k1; k++)
+                if (o->DTVisc[k] > 1.e-9) {
+                    o->DTVisc[k] = C_diff / o->DTVisc[k];
+                    o->DT[k] = fmin(o->DT[k], o->DTVisc[k]);
+                }
         for (int i = 0; i < ni; i++)
             for (long k = k0; k < k1; k++) {
                 double q[4], fx[4], fy[4];
@@ -454,10 +760,15 @@ static void stage(ora *o, int rk) {
             double *rhs = o->RHSQ + n * reg1;
             op_apply(o->DivInt, ni, nf, o->F_RT_DOF + (long)n * nf * K, rhs, K, k0, k1);
             for (int i = 0; i < ni; i++)
+                for (long k = k0; k < k1; k++) rhs[(long)i * K + k] *= -(1.0 / o->Jdet[k]);
+            if (diss) {   /* euler.go:496-501 */
+                add_dissipation(o, n, rhs, k0, k1);
+                limit_and_filter(o, rhs, o->LS2, k0, k1);
+            }
+            for (int i = 0; i < ni; i++)
                 for (long k = k0; k < k1; k++) {
                     long x = n * reg1 + (long)i * K + k;
-                    double r = o->RHSQ[x] * (-(1.0 / o->Jdet[k]));
-                    o->RHSQ[x] = r;
+                    double r = o->RHSQ[x];
                     double dt_rhs = o->DT[k] * r;
                     switch (rk) {
                     case 0: q1[x] = q0[x] + RK_A * dt_rhs; break;
@@ -503,8 +814,11 @@ int ora_rhs(ora *o, int rk, double *out) {
     memcpy(sres, o->Residual, reg);
     memcpy(sdt, o->DT, sizeof(double) * (size_t)o->K);
     double gdt = o->GlobalDT;
+    double *sdv = NULL;
+    if (o->diss) { sdv = (double *)malloc(sizeof(double) * (size_t)o->K); memcpy(sdv, o->DTVisc, sizeof(double) * (size_t)o->K); }
     stage(o, rk);
     memcpy(out, o->RHSQ, reg);
+    if (sdv) { memcpy(o->DTVisc, sdv, sizeof(double) * (size_t)o->K); free(sdv); }
     for (int r = 0; r < 5; r++) { memcpy(o->Q[r], save[r], reg); free(save[r]); }
     memcpy(o->Residual, sres, reg); memcpy(o->DT, sdt, sizeof(double) * (size_t)o->K);
     o->GlobalDT = gdt;

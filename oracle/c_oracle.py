@@ -1,6 +1,6 @@
 """ORACLE -- test infrastructure, not product code.
 
-ctypes wrapper of oracle/c/liboracle.so, the C/OpenMP restatement of the inviscid stage
+ctypes wrapper of oracle/c/liboracle.so, the C/OpenMP restatement of the stage (inviscid and PerssonC0 paths)
 (oracle/c/euler2d_stage.c).  Same surface as OracleSolver / gocfd_b200.lib.Dfr2d.  Only tests/,
 __graft_entry__ and bench.py's CPU-baseline legs may import this.  The problem struct layout is
 the one of include/dfr2d.h, so the flattening helper of the ctypes binding is reused.
@@ -40,6 +40,7 @@ def load():
         lib.ora_residual.argtypes = [H, _dp]
         lib.ora_step.argtypes = [H, C.c_int, C.POINTER(StepInfo)]
         lib.ora_rhs.argtypes = [H, C.c_int, _dp]
+        lib.ora_set_register.argtypes = [H, C.c_int, _dp]
         _lib = lib
     return _lib
 
@@ -57,7 +58,7 @@ class COracleSolver:
         self.h = self.lib.ora_create(C.byref(s))
         del keep
         if not self.h:
-            raise ValueError("the C oracle restates the inviscid stage only (dissipation requested)")
+            raise ValueError("ora_create failed")
 
     def close(self):
         if self.h:
@@ -74,6 +75,11 @@ class COracleSolver:
         q = np.ascontiguousarray(q, dtype=np.float64)
         assert q.shape == self.shape
         self.lib.ora_set_state(self.h, q.ctypes.data_as(_dp))
+
+    def set_register(self, reg, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        assert q.shape == self.shape
+        self.lib.ora_set_register(self.h, reg, q.ctypes.data_as(_dp))
 
     def get_state(self):
         q = np.zeros(self.shape)
