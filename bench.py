@@ -338,7 +338,7 @@ def main():
     if diss:
         bv = algorithmic_bytes_visc(n)
         ach = bv * p.K * 5 * args.steps / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad, k_visc_edge, k_elem<N,true>)",
+        roofline = {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad_pipe [DMMA], k_visc_edge, k_elem<N,true>)",
                     "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
                     "peak_source": peak_src, "bytes_per_element_stage": bv}
     if t_elem:

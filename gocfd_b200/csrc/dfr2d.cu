@@ -67,8 +67,11 @@ struct dfr2d_handle {
     int pfTiles = 0;
     int elemKernel = 4;               // 1: row-per-thread DFMA, 2: split-row DFMA, 3: DMMA, 4: pipelined DMMA (default)
     double *mmaFrags = nullptr;
-    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 2: DMMA k_grad_mma (DFR2D_GRAD_KERNEL)
-    double *gradTable = nullptr;
+    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 2: DMMA k_grad_mma, 3: pipelined persistent DMMA
+                                      // k_grad_pipe (DFR2D_GRAD_KERNEL)
+    double *gradTable = nullptr, *gradMxy = nullptr;
+    int gradMG = 3;                   // m-tiles per accumulation group of k_grad_pipe (DFR2D_GRAD_MG = 2 | 3)
+    int gradSkewNs = 0;               // start delay of k_grad_pipe's second warp group (DFR2D_GRAD_SKEW_NS)
     bool gradAttrSet = false;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
@@ -571,11 +574,30 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_upload(h, &h->mmaFrags, fr)) return rc;
     }
     if (const char *ev = getenv("DFR2D_PREFETCH_TILES")) h->pfTiles = atoi(ev);
+    // measured on B200, 2M triangles (profiles/r01p_grad_ab_N*.json): the pipelined tensor-core gradient kernel wins at
+    // N = 4 (k_edge + gradient 3.86 -> 2.74 ms), N = 3 (2.32 -> 2.15) and N = 2 (1.56 -> 1.43).  N = 1 keeps the DFMA
+    // kernel: its operators are 15 x 15, and its summation order is the one the 1e-11 parity bar at N = 1 relies on
+    // (the RT2 divergence operator is ill conditioned, tests/test_noise_floor.py)
+    h->gradKernel = (N >= 2) ? 3 : 1;
     if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev);
-    if (ph.dissipation && h->gradKernel == 2) {
+    if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
+    if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
+    if (ph.dissipation && h->gradKernel >= 2) {
         std::vector<double> tb;
         grad_table_for(N, p->Div, p->Bary, tb);
         if (int rc = dev_upload(h, &h->gradTable, tb)) return rc;
+        // (x, y) metric of the RT points of edge 0, 1, 2 (DXMetric / DYMetric edge rows, DG2D/dfr_startup.go:213-254)
+        // as plain rows [mx0, my0, mx1, my1, mx2, my2][Kp], same operation order as k_grad
+        std::vector<double> mxy((size_t)6 * Kp, 0.0);
+        for (int k = 0; k < K; k++) {
+            const double oojd = 1.0 / pl.Jdet[k];
+            for (int le = 0; le < 3; le++) {
+                const double iin = pl.IInII[(size_t)le * Kp + k];
+                mxy[(size_t)(2 * le) * Kp + k] = oojd * p->FaceNormX[(k0 + k) + p->K * le] * iin;
+                mxy[(size_t)(2 * le + 1) * Kp + k] = oojd * p->FaceNormY[(k0 + k) + p->K * le] * iin;
+            }
+        }
+        if (int rc = dev_upload(h, &h->gradMxy, mxy)) return rc;
     }
     CK(cudaDeviceSynchronize());
     return 0;
@@ -943,6 +965,24 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
     ga.dissX = d.dissX; ga.dissY = d.dissY;
     ga.sc = h->sc; ga.par = (int)(h->stepIndex & 1); ga.stepIndex = h->stepIndex; ga.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->gradKernel == 3) {
+        DISPATCH_N(h->N, {
+            using PD = GradPipeDim<NN>;
+            if (!h->gradAttrSet) {
+                cudaFuncSetAttribute(k_grad_pipe<NN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD::kSmemBytes);
+                cudaFuncSetAttribute(k_grad_pipe<NN, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k_grad_pipe<NN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD::kSmemBytes);
+                cudaFuncSetAttribute(k_grad_pipe<NN, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                h->gradAttrSet = true;
+            }
+            GradPipeArgs pa{};
+            pa.a = ga; pa.table = h->gradTable; pa.mxy = h->gradMxy; pa.nTiles = blocks; pa.skewNs = h->gradSkewNs;
+            const int grid = std::max(1, std::min(h->sms, (blocks + PD::kGroups - 1) / PD::kGroups));
+            if (h->gradMG == 2) k_grad_pipe<NN, 2><<<grid, PD::kThreads, PD::kSmemBytes, h->stream>>>(pa);
+            else k_grad_pipe<NN, 3><<<grid, PD::kThreads, PD::kSmemBytes, h->stream>>>(pa);
+        });
+        return launch_check(h, "k_grad_pipe");
+    }
     if (h->gradKernel == 2) {
         DISPATCH_N(h->N, {
             const size_t sm = GradMmaDim<NN>::kSmemBytes;

@@ -18,6 +18,7 @@
 #pragma once
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
+#include "dfr2d_elem_tma.cuh"
 
 namespace dfr2d {
 
@@ -196,6 +197,279 @@ template <int N> void build_grad_table(const double *Div, const double *Bary, st
                 }
     for (int m = 0; m < GD::NOUT; m++)
         for (int c = 0; c < 3; c++) out[GD::kFragDoubles + m * 3 + c] = Bary[(size_t)GD::out_row(m) * 3 + c];
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// k_grad_pipe<N> (DFR2D_GRAD_KERNEL=3): k_grad_mma as a persistent, software-pipelined kernel.
+//
+// Measured on B200 (profiles/r01l_grad_ab.json): k_grad_mma is only 10 % faster than the DFMA kernel although its
+// tensor-pipe floor is ~1 ms for 2M elements at N=4 -- a CTA loads its tile (three dependent global loads deep:
+// etoe -> edge table -> Q_Face), synchronises, computes, stores; nothing overlaps and the operator table is re-read
+// from L2 by every 32-element tile.  Here one CTA per SM holds the table for its lifetime and runs two independent
+// groups of 8 warps; each group walks its own tiles through a two-stage shared-memory ring:
+//   * every byte of tile t+1 (solution rows, gathered edge values, metric rows, vertex epsilon) is moved by cp.async
+//     issued BEFORE the DMMA work of tile t, so it lands underneath it and never occupies a register;
+//   * the index chain is pipelined one level per iteration: etoe of tile t+3 and the edge-table entries of tile t+2 are
+//     plain loads whose results are first used one iteration later;
+//   * per-edge metrics n_e IInII_e / Jdet are precomputed once at create ([6][Kp]) so they are plain rows as well;
+//   * the two groups synchronise only among themselves (named barriers), so one group's epilogue stores overlap the
+//     other's tensor work.
+// ------------------------------------------------------------------------------------------------------------------
+template <int N> struct GradPipeDim {
+    using GD = GradMmaDim<N>;
+    static constexpr int E = kElemsPerBlock;
+    static constexpr int kGroups = 2, kGroupThreads = 8 * E, kThreads = kGroups * kGroupThreads;
+    static constexpr int kUDoubles = 4 * GD::UROWS * GD::SE;
+    static constexpr int kStageDoubles = kUDoubles + 10 * E + 3 * E;      // U, metric rows, vertex epsilon
+    static constexpr size_t kSmemBytes = (size_t)(GD::kTableDoubles + 2 * kGroups * kStageDoubles) * sizeof(double);
+};
+
+struct GradPipeArgs {
+    GradArgs a;
+    const double *table;     // build_grad_table
+    const double *mxy;       // [6][Kp]: (x, y) metric of the points of edge 0, 1, 2
+    int nTiles;
+    int skewNs;              // start delay of group 1: keeps the two groups' tensor phases out of step
+};
+
+__device__ __forceinline__ void group_bar(int group) {
+    if (group == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+// One metric block of the contraction for the m-tiles [M0, M0+MG) and this warp's two n-tiles: S = Div_block . U_block
+// (NKS k-steps of DMMA), then g += metric (.) S.  pUb / pAb / pMb point at the block's first B row, A fragment and
+// metric row pair.  Called from ROLLED loops over the blocks: with the whole tile body unrolled, ptxas batches the
+// shared-memory loads of many k-steps ahead of the DMMA stream and spills them.
+template <int N, int MG, int M0, int NKS>
+__device__ __forceinline__ void grad_block(const double *pUb, const double *pAb, const double *pMb, double (&gx)[MG][2][2],
+                                           double (&gy)[MG][2][2]) {
+    using GD = GradMmaDim<N>;
+    constexpr int E = kElemsPerBlock, SE = GD::SE, KS = GD::KS, MT = GD::MT;
+    double S[MG][2][2];
+#pragma unroll
+    for (int mt = 0; mt < MG; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < NKS; ks++) {
+        double b[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) b[nt] = pUb[4 * ks * SE + 8 * nt];
+#pragma unroll
+        for (int mt = 0; mt < MG; mt++)
+            if (M0 + mt < MT) {
+                const double av = pAb[((M0 + mt) * KS + ks) * 32];
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) dmma884(S[mt][nt][0], S[mt][nt][1], av, b[nt]);
+            }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++) {
+        const double2 mX = *reinterpret_cast<const double2 *>(&pMb[8 * nt]);
+        const double2 mY = *reinterpret_cast<const double2 *>(&pMb[E + 8 * nt]);
+#pragma unroll
+        for (int mt = 0; mt < MG; mt++)
+            if (M0 + mt < MT) {
+                gx[mt][nt][0] = fma(mX.x, S[mt][nt][0], gx[mt][nt][0]);
+                gx[mt][nt][1] = fma(mX.y, S[mt][nt][1], gx[mt][nt][1]);
+                gy[mt][nt][0] = fma(mY.x, S[mt][nt][0], gy[mt][nt][0]);
+                gy[mt][nt][1] = fma(mY.y, S[mt][nt][1], gy[mt][nt][1]);
+            }
+    }
+}
+
+// Rows [M0, M0+MG) of one tile: all five blocks, Epsilon product, stores.
+template <int N, int MG, int M0>
+__device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU, const double *pA, const double *pM,
+                                            const double *pB, int n, int fr, int fc, int nt0, int k0, size_t KpL) {
+    using GD = GradMmaDim<N>;
+    constexpr int E = kElemsPerBlock, SE = GD::SE, KI = GD::KI, KE = GD::KE, MT = GD::MT, NF = GD::NF;
+    double gx[MG][2][2], gy[MG][2][2];
+#pragma unroll
+    for (int mt = 0; mt < MG; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 2; nt++) gx[mt][nt][0] = gx[mt][nt][1] = gy[mt][nt][0] = gy[mt][nt][1] = 0.0;
+#pragma unroll 1
+    for (int r = 0; r < 2; r++)                 // the two interior blocks share the B rows
+        grad_block<N, MG, M0, KI>(pU, pA + r * KI * 32, pM + 2 * r * E, gx, gy);
+#pragma unroll 1
+    for (int le = 0; le < 3; le++)              // points of edge le
+        grad_block<N, MG, M0, KE>(pU + (4 * KI + le * 4 * KE) * SE, pA + (2 * KI + le * KE) * 32, pM + (4 + 2 * le) * E, gx, gy);
+    // vertex epsilon of this lane's element pairs (rows 10..12 of the metric block)
+    double2 ev[2][3];
+#pragma unroll
+    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+        for (int v = 0; v < 3; v++) ev[nt][v] = *reinterpret_cast<const double2 *>(&pM[(10 + v) * E + 8 * nt]);
+#pragma unroll
+    for (int mt = 0; mt < MG; mt++) {
+        const int m = 8 * (M0 + mt) + fr;
+        if (M0 + mt < MT && m < GD::NOUT) {
+            const int row = GD::out_row(m);
+            const double b0 = pB[8 * (M0 + mt) * 3], b1 = pB[8 * (M0 + mt) * 3 + 1], b2 = pB[8 * (M0 + mt) * 3 + 2];
+#pragma unroll
+            for (int nt = 0; nt < 2; nt++) {
+                const int e0 = 8 * (nt0 + nt) + 2 * fc;
+                const double epsA = b0 * ev[nt][0].x + b1 * ev[nt][1].x + b2 * ev[nt][2].x;
+                const double epsB = b0 * ev[nt][0].y + b1 * ev[nt][1].y + b2 * ev[nt][2].y;
+                const size_t o = ((size_t)n * NF + row) * KpL + k0 + e0;
+                if (k0 + e0 + 1 < a.K) {
+                    *reinterpret_cast<double2 *>(a.dissX + o) = make_double2(gx[mt][nt][0] * epsA, gx[mt][nt][1] * epsB);
+                    *reinterpret_cast<double2 *>(a.dissY + o) = make_double2(gy[mt][nt][0] * epsA, gy[mt][nt][1] * epsB);
+                } else if (k0 + e0 < a.K) {
+                    a.dissX[o] = gx[mt][nt][0] * epsA;
+                    a.dissY[o] = gy[mt][nt][0] * epsA;
+                }
+            }
+        }
+    }
+}
+
+template <int N, int MG>      // MG: m-tiles accumulated at a time (2 or 3)
+__global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradPipeArgs args) {
+    using GD = GradMmaDim<N>;
+    using PD = GradPipeDim<N>;
+    constexpr int NI = GD::NI, NEd = GD::NEd, NF = GD::NF, NF3 = GD::NF3, E = kElemsPerBlock, SE = GD::SE;
+    constexpr int MT = GD::MT, KI = GD::KI, KE = GD::KE, UROWS = GD::UROWS;
+    const GradArgs &a = args.a;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    extern __shared__ double smem[];
+    double *sT = smem;                                              // operator table, whole CTA
+    const int group = threadIdx.x / PD::kGroupThreads, tg = threadIdx.x % PD::kGroupThreads;
+    double *sStage = sT + GD::kTableDoubles + (size_t)group * 2 * PD::kStageDoubles;   // this group's two stages
+    const int lane = tg & 31, wg = tg >> 5, n = wg & 3, half = wg >> 2;
+    const size_t Kp = a.Kp;
+    const int nTiles = args.nTiles;
+    const int stride = gridDim.x * PD::kGroups;
+    const int tile0 = blockIdx.x * PD::kGroups + group;
+
+    for (int t = threadIdx.x; t < GD::kTableDoubles; t += PD::kThreads) sT[t] = args.table[t];
+    // padding rows of both stages are zeroed once; the copies only ever write the real rows
+    for (int st = 0; st < 2; st++) {
+        double *u = sStage + (size_t)st * PD::kStageDoubles + (size_t)n * UROWS * SE;
+        for (int r = half; r < UROWS; r += 2) {
+            const bool pad = (r < 4 * KI) ? (r >= NI) : (((r - 4 * KI) % (4 * KE)) >= NEd);
+            if (pad) u[r * SE + lane] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    // ---- pipeline registers ---------------------------------------------------------------------------------------
+    int sIdx[3];                 // etoe of the tile three ahead
+    int eKL[3], eMeta[3];        // raw edge-table entries of the tile two ahead (owner column, meta); decoded at issue
+                                 // time, one iteration after the loads were posted, so that nothing waits on them
+    int eKc = 0;                 // this lane's (clamped) element of that tile
+    unsigned evIdx = 0;          // vertex of this lane's element (warps 5..7 of the group: vertex wg - 5)
+
+    auto elem_of = [&](int tile) {
+        const int tc = tile < nTiles ? tile : nTiles - 1;
+        const int k = tc * E + lane;
+        return k < a.K ? k : a.K - 1;
+    };
+    auto load_s = [&](int tile) {
+        const int kc = elem_of(tile);
+#pragma unroll
+        for (int le = 0; le < 3; le++) sIdx[le] = a.etoe[(size_t)le * Kp + kc];
+    };
+    auto load_l2 = [&](int tile) {          // consumes sIdx (loaded one iteration earlier)
+        eKc = elem_of(tile);
+#pragma unroll
+        for (int le = 0; le < 3; le++) {
+            const int s = sIdx[le];
+            eKL[le] = -1;
+            eMeta[le] = 0;
+            if (s < 0) {
+                eKL[le] = a.ekL[-1 - s];
+                eMeta[le] = a.emeta[-1 - s];
+            }
+        }
+        if (wg >= 5) evIdx = (unsigned)a.etov[(size_t)(wg - 5) * Kp + eKc];
+    };
+    auto issue = [&](int tile, int st) {    // every byte of `tile` -> stage st, asynchronously
+        if (tile < nTiles) {
+            const int k0 = tile * E;
+            double *base = sStage + (size_t)st * PD::kStageDoubles;
+            unsigned uB = smem_u32(base);
+            size_t KpL = Kp;
+            // keep ptxas from hoisting (and spilling) every loop-invariant address of the unrolled copy lists
+            asm volatile("" : "+r"(uB), "+l"(KpL));
+            // solution rows: 4 NI rows of 256 B as 16-byte chunks
+            for (int c = tg; c < 4 * NI * 16; c += PD::kGroupThreads) {
+                const int row = c >> 4, ch = c & 15, var = row / NI, i = row - var * NI;
+                cp_async16_u32(uB + (unsigned)(((var * UROWS + i) * SE + 2 * ch) * sizeof(double)),
+                               a.q + ((size_t)var * NI + i) * KpL + k0 + 2 * ch);
+            }
+            // edge values of this lane's element, variable n, rows of parity `half`
+            const double *qf = a.qface + (size_t)(n * NF3) * KpL;
+#pragma unroll
+            for (int le = 0; le < 3; le++) {
+                // owner: own edge rows; neighbour: the owner's rows, points reversed (euler.go:896-912)
+                const bool rev = eKL[le] >= 0;
+                const double *src = qf + (rev ? (size_t)((eMeta[le] & 3) * NEd) * KpL + eKL[le] : (size_t)(le * NEd) * KpL + eKc);
+#pragma unroll
+                for (int i = 0; i < NEd; i++)
+                    if ((i & 1) == half)
+                        cp_async8_u32(uB + (unsigned)(((n * UROWS + 4 * KI + le * 4 * KE + i) * SE + lane) * sizeof(double)),
+                                      src + (size_t)(rev ? NEd - 1 - i : i) * KpL);
+            }
+            // metric rows: Jinv[4][Kp], mxy[6][Kp]
+            if (tg < 160) {
+                const int row = tg >> 4, ch = tg & 15;
+                const double *src = (row < 4 ? a.Jinv + (size_t)row * KpL : args.mxy + (size_t)(row - 4) * KpL) + k0 + 2 * ch;
+                cp_async16_u32(uB + (unsigned)((PD::kUDoubles + row * E + 2 * ch) * sizeof(double)), src);
+            } else {
+                cp_async8_u32(uB + (unsigned)((PD::kUDoubles + 10 * E + (wg - 5) * E + lane) * sizeof(double)), a.epsV + evIdx);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    // ---- prologue -----------------------------------------------------------------------------------------------------
+    // Both groups run the same instruction stream on the same amount of work, so started together they stay in lock
+    // step: both in the DMMA phase (fighting for the one FP64/tensor pipe of the SM), then both in the epilogue with the
+    // pipe idle.  Delaying group 1 by about half a tile time interleaves the phases.
+    if (group == 1 && args.skewNs > 0) __nanosleep((unsigned)args.skewNs);
+    load_s(tile0);
+    load_l2(tile0);
+    issue(tile0, 0);
+    load_s(tile0 + stride);
+    load_l2(tile0 + stride);
+    load_s(tile0 + 2 * stride);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    group_bar(group);
+
+    const int fr = lane >> 2, fc = lane & 3;
+    const int nt0 = 2 * half;
+    // Shared-memory addressing of the steady state: every read is smem[opaque per-iteration offset + compile-time
+    // constant], i.e. LDS [R + imm].  Left alone, the compiler hoists the ~200 per-fragment addresses of the unrolled
+    // body out of the tile loop and spills them (1 KB of local memory per thread); laundering a POINTER instead turns
+    // the loads into generic LD (long-scoreboard stalls, profiles/r01n).
+    const unsigned groupOff = (unsigned)(GD::kTableDoubles + group * 2 * PD::kStageDoubles);
+    const unsigned laneU = (unsigned)(n * UROWS * SE + fc * SE + fr + 8 * nt0);          // B fragments
+    const unsigned laneM = (unsigned)(PD::kUDoubles + 8 * nt0 + 2 * fc);                 // metric / vertex-eps pairs
+    const unsigned laneB = (unsigned)(GD::kFragDoubles + fr * 3);                        // Bary rows
+    int st = 0;
+    for (int tile = tile0; tile < nTiles; tile += stride, st ^= 1) {
+        issue(tile + stride, st ^ 1);              // uses eKL / eMeta / eKc / evIdx of tile + stride
+        load_l2(tile + 2 * stride);                // uses sIdx of tile + 2 stride
+        load_s(tile + 3 * stride);
+
+        const int k0 = tile * E;
+        unsigned oU = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles + laneU;
+        unsigned oM = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles + laneM;
+        unsigned oA = (unsigned)lane, oB = laneB;
+        size_t KpL = Kp;
+        asm volatile("" : "+r"(oU), "+r"(oM), "+r"(oA), "+r"(oB), "+l"(KpL));
+        const double *pU = smem + oU, *pM = smem + oM, *pA = smem + oA, *pB = smem + oB;
+        grad_mgroup<N, MG, 0>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+        if (MG < MT) grad_mgroup<N, MG, MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+        if (2 * MG < MT) grad_mgroup<N, MG, 2 * MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+        static_assert(3 * MG >= MT, "m-groups");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        group_bar(group);          // stage st^1 is complete and every warp of the group has finished reading stage st
+    }
 }
 
 }  // namespace dfr2d

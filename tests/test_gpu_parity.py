@@ -169,11 +169,13 @@ def _smeared_sod_state(c, width=0.004):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4])
 @pytest.mark.parametrize("rk", [0, 2])
-@pytest.mark.parametrize("grad_kernel", [1, 2])
+@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
 def test_dissipation_rhs_parity(n, rk, grad_kernel, monkeypatch):
     """RHSQ with sensor, vertex merge, RT gradient, viscous edge flux, AddDissipation and the RHS
     limiter; rk=2 also exercises the in-place limiting of the stage input (euler.go:605-609).
-    grad_kernel: 1 = constant-operand DFMA k_grad, 2 = tensor-core k_grad_mma (read at dfr2d_create)."""
+    grad_kernel: 1 = constant-operand DFMA k_grad, 2 = tensor-core k_grad_mma, 3 = pipelined k_grad_pipe (read at
+    dfr2d_create).  The tensor-core kernels sum the Div contraction block-wise; at N=1 that order differs from the dense
+    one by the operator's own float64 noise floor (3e-11, tests/test_noise_floor.py), hence 2e-10 there."""
     monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
     c = _sod(n)
     assert c.problem.Dissipation
@@ -183,14 +185,14 @@ def test_dissipation_rhs_parity(n, rk, grad_kernel, monkeypatch):
     ora.Q[rk][...] = q
     a, b = dev.rhs(rk), ora.rhs(rk)
     assert ora.SigmaScalar.max() > 0.05, "test state must trigger the sensor"
-    assert rel_l2(a, b) < TOL
+    assert rel_l2(a, b) < (2e-10 if (n == 1 and grad_kernel != 1) else TOL)
     np.testing.assert_allclose(dev.get_field(3)[np.isfinite(ora.Se)], ora.Se[np.isfinite(ora.Se)], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(dev.get_field(1), ora.SigmaScalar, rtol=1e-9, atol=1e-12)
     dev.close()
 
 
 @pytest.mark.parametrize("n", [2, 4])
-@pytest.mark.parametrize("grad_kernel", [1, 2])
+@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
 def test_sod_steps_with_dissipation(n, grad_kernel, monkeypatch):
     """Config C3: Sod tube, PerssonC0, global dt (incl. the viscous dt limit), 10 steps from a smeared front."""
     monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
@@ -327,7 +329,7 @@ def test_multi_partition_naca_local_dt():
 
 
 @pytest.mark.parametrize("n_parts,n", [(2, 2), (3, 4), (4, 1)])
-@pytest.mark.parametrize("grad_kernel", [1, 2])
+@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
 def test_multi_partition_sod_with_dissipation(n_parts, n, grad_kernel, monkeypatch):
     """PerssonC0 across partitions -- shared-vertex max merge, Q_Face + ghost vertex epsilon,
     DissX/DissY edge rows.  Bitwise equal to the single-partition device run, 1e-11 against the oracle."""
