@@ -124,6 +124,7 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
 
+DISS_SAMPLE_NX = 600     # 600x150x2 = 180,000 triangles for the (slower, partly serial) PerssonC0 path of the port
 CPU_SAMPLE_NX = 500      # 500x500x2 = 500,000 triangles: state >> CPU caches, one RK step ~1 s on 8 cores at N=4
 
 
@@ -137,13 +138,14 @@ def _cpu_model():
     return "unknown CPU"
 
 
-def cpu_run(n, steps=None, warmup=1, seconds_target=12.0, nx=CPU_SAMPLE_NX):
+def cpu_run(n, steps=None, warmup=1, seconds_target=12.0, nx=CPU_SAMPLE_NX, dissipation=False):
     """The CPU arm: oracle/c (C + OpenMP restatement of the reference's stage, phase structure and
     materialised arrays of the Go solver, all host threads) on a bounded sample of the same workload:
     same vortex set-up, order, flux and dt mode on an nx x nx x 2 mesh.  Runs `steps` RK steps, or as
     many as fit in seconds_target when steps is None.  The Go toolchain is absent, so this is a port."""
     from oracle.c_oracle import COracleSolver, threads
-    c = build_case(nx, nx, n)
+    ny = max(1, nx // 4) if dissipation else nx          # the Sod tube keeps its 4:1 aspect
+    c = build_case(nx, ny, n, dissipation=dissipation)
     o = COracleSolver(c.problem)
     o.set_state(c.Q)
     o.step(max(1, warmup))
@@ -157,13 +159,13 @@ def cpu_run(n, steps=None, warmup=1, seconds_target=12.0, nx=CPU_SAMPLE_NX):
     dof = 4 * c.problem.NpInt * c.problem.K * 5 * done
     return {"value": dof / el, "unit": "DOF-stage-updates/s", "cores": threads(), "kind": "port",
             "us_per_element_iteration": el * 1e6 / done / c.problem.K, "ms_per_step": el * 1e3 / done,
-            "sample": "C/OpenMP restatement of the Go stage (oracle/c), %d threads on %s; %dx%dx2=%d triangles, N=%d, "
+            "sample": "C/OpenMP restatement of the Go stage (oracle/c%s), %d threads on %s; %dx%dx2=%d triangles, N=%d, "
                       "%d RK steps in %.1f s; not the Go solver (no Go toolchain)"
-                      % (threads(), _cpu_model(), nx, nx, c.problem.K, n, done, el)}
+                      % (", PerssonC0 path" if dissipation else "", threads(), _cpu_model(), nx, ny, c.problem.K, n, done, el)}
 
 
-def cpu_baseline(n):
-    return cpu_run(n)
+def cpu_baseline(n, dissipation=False):
+    return cpu_run(n, nx=DISS_SAMPLE_NX if dissipation else CPU_SAMPLE_NX, dissipation=dissipation)
 
 
 def run_reference(args, rank):
@@ -173,15 +175,18 @@ def run_reference(args, rank):
     if args.order >= 0:
         n = args.order
     t_all = time.perf_counter()
-    base = cpu_run(n, steps=args.steps, warmup=args.warmup, nx=min(CPU_SAMPLE_NX, nx))
+    diss = args.workload in DISSIPATION_WORKLOADS
+    sample_nx = min(DISS_SAMPLE_NX if diss else CPU_SAMPLE_NX, nx)
+    base = cpu_run(n, steps=args.steps, warmup=args.warmup, nx=sample_nx, dissipation=diss)
     line = {
         "impl": "reference", "metric": "DOF-stage-updates/s", "value": base["value"], "unit": "DOF-stage-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: isentropic vortex, %dx%dx2 triangles, N=%d, Roe, global dt (the CPU arm steps a bounded "
+        "config": {"workload": "%s: %s, %dx%dx2 triangles, N=%d, Roe, global dt (the CPU arm steps a bounded "
                                "%dx%dx2 sample of it; throughput is size-independent once the state exceeds the caches)"
-                               % (args.workload, nx, ny, n, min(CPU_SAMPLE_NX, nx), min(CPU_SAMPLE_NX, nx))},
+                               % (args.workload, "Sod shock tube with PerssonC0 dissipation" if diss else "isentropic vortex",
+                                  nx, ny, n, sample_nx, max(1, sample_nx // 4) if diss else sample_nx)},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "DOF-stage-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -412,8 +417,8 @@ def main():
             "us_per_element_iteration": ms * 1e3 / args.steps / p.K,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
-        if not args.no_cpu_baseline and world == 1 and not diss:
-            line["cpu_baseline"] = cpu_baseline(n)
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(n, dissipation=diss)
         print(json.dumps(line))
     dev.close()
     if world > 1:

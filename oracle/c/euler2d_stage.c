@@ -402,9 +402,14 @@ static void op_apply(const double *A, int m, int n, const double *X, double *Y, 
 static void update_se_moment(ora *o, const double *rho) {
     const long K = o->K;
     const int ni = o->NpInt;
-    op_apply(o->P, ni, ni, rho, o->LS0, K, 0, K);
-    op_apply(o->Mass, ni, ni, rho, o->LS1, K, 0, K);
-    op_apply(o->D, ni, ni, rho, o->LS2, K, 0, K);
+#pragma omp parallel for schedule(static)
+    for (long b = 0; b < (K + BLK - 1) / BLK; b++) {
+        long k0 = b * BLK, k1 = k0 + BLK < K ? k0 + BLK : K;
+        op_apply(o->P, ni, ni, rho, o->LS0, K, k0, k1);
+        op_apply(o->Mass, ni, ni, rho, o->LS1, K, k0, k1);
+        op_apply(o->D, ni, ni, rho, o->LS2, K, k0, k1);
+    }
+#pragma omp parallel for schedule(static)
     for (long k = 0; k < K; k++) {
         double num = 0.0, den = 0.0;
         for (int i = 0; i < ni; i++) {
@@ -471,6 +476,7 @@ static void calculate_epsilon_gradient(ora *o, const double *qqq) {
     const int ni = o->NpInt, ne = o->NpEdge, nf = o->NpFlux;
     for (int n = 0; n < 4; n++) {
         const double *Q = qqq + (long)n * ni * K;
+#pragma omp parallel for schedule(static)
         for (long k = 0; k < K; k++)
             for (int i = 0; i < ni; i++) {
                 long ind = k + (long)i * K, ind2 = k + (long)(i + ni) * K;
@@ -478,6 +484,7 @@ static void calculate_epsilon_gradient(ora *o, const double *qqq) {
                 o->DOFX[ind] = o->DXMetric[ind] * Un; o->DOFY[ind] = o->DYMetric[ind] * Un;
                 o->DOFX[ind2] = o->DXMetric[ind2] * Un; o->DOFY[ind2] = o->DYMetric[ind2] * Un;
             }
+#pragma omp parallel for schedule(static)
         for (long k = 0; k < K; k++)
             for (int edgeNum = 0; edgeNum < 3; edgeNum++) {
                 long e = o->etoe[3 * k + edgeNum];
@@ -499,6 +506,7 @@ static void calculate_epsilon_gradient(ora *o, const double *qqq) {
             op_apply(o->Div, nf, nf, o->DOFX, GX, K, k0, k1);
             op_apply(o->Div, nf, nf, o->DOFY, GY, K, k0, k1);
         }
+#pragma omp parallel for schedule(static)
         for (long x = 0; x < (long)nf * K; x++) { GX[x] *= o->Epsilon[x]; GY[x] *= o->Epsilon[x]; }
     }
 }
@@ -600,11 +608,13 @@ static void stage(ora *o, int rk) {
         merge_to_vertices(o, o->SigmaScalar, o->SigmaVertex, seen);
         merge_to_vertices(o, o->EpsilonScalar, o->EpsVertex, seen);
         free(seen);
+#pragma omp parallel for schedule(static)
         for (long k = 0; k < K; k++) {          /* MergeVertexScalarToElement(sum, div3), euler.go:1067-1086 */
             double acc = 0.0;
             for (int v = 0; v < 3; v++) acc = acc + o->SigmaVertex[o->EToV[v + 3 * k]];
             o->SigmaScalar[k] = acc / 3.0;
         }
+#pragma omp parallel for schedule(static)
         for (long k = 0; k < K; k++) {
             double v3[3] = {o->EpsVertex[o->EToV[3 * k]], o->EpsVertex[o->EToV[3 * k + 1]], o->EpsVertex[o->EToV[3 * k + 2]]};
             for (int i = 0; i < nf; i++) {
@@ -615,8 +625,13 @@ static void stage(ora *o, int rk) {
                 o->Epsilon[k + (long)i * K] = acc;
             }
         }
-        if (rk == 2)
-            for (int n = 0; n < 4; n++) limit_and_filter(o, qqq + (long)n * ni * K, o->LS2, 0, K);
+        if (rk == 2) {
+#pragma omp parallel for schedule(static)
+            for (long b = 0; b < nblk; b++) {
+                long k0 = b * BLK, k1 = k0 + BLK < K ? k0 + BLK : K;
+                for (int n = 0; n < 4; n++) limit_and_filter(o, qqq + (long)n * ni * K, o->LS2, k0, k1);
+            }
+        }
     }
 
     /* InterpolateSolutionToEdges, edges.go:485-491 */
