@@ -15,6 +15,7 @@
 #include "dfr2d_elem_pipe.cuh"
 #include "dfr2d_elem_tma.cuh"
 #include "dfr2d_grad_mma.cuh"
+#include "dfr2d_elem_mma_diss.cuh"
 
 using namespace dfr2d;
 
@@ -71,6 +72,10 @@ struct dfr2d_handle {
                                       // k_grad_pipe (DFR2D_GRAD_KERNEL)
     double *gradTable = nullptr, *gradMxy = nullptr;
     int gradMG = 3;                   // m-tiles per accumulation group of k_grad_pipe (DFR2D_GRAD_MG = 2 | 3)
+    int dissElemKernel = 1;           // element kernel of the PerssonC0 path: 1 = k_elem<N,true> (DFMA), 3 = k_elem_mma_diss
+                                      // (DMMA, opt-in until measured; DFR2D_DISS_ELEM_KERNEL)
+    double *mmaDissFrags = nullptr;
+    int mmaDissGrid = 0;
     int gradSkewNs = 0;               // start delay of k_grad_pipe's second warp group (DFR2D_GRAD_SKEW_NS)
     bool gradAttrSet = false;
     int sms = 148, mmaGrid = 148;
@@ -582,6 +587,17 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev);
     if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
+    if (const char *ev = getenv("DFR2D_DISS_ELEM_KERNEL")) h->dissElemKernel = atoi(ev);
+    if (ph.dissipation && h->dissElemKernel == 3) {
+        std::vector<double> fr;
+        switch (N) {
+            case 1: build_mma_diss_frags<1>(p->DivInt, p->Vinv, p->V, fr); break;
+            case 2: build_mma_diss_frags<2>(p->DivInt, p->Vinv, p->V, fr); break;
+            case 3: build_mma_diss_frags<3>(p->DivInt, p->Vinv, p->V, fr); break;
+            default: build_mma_diss_frags<4>(p->DivInt, p->Vinv, p->V, fr); break;
+        }
+        if (int rc = dev_upload(h, &h->mmaDissFrags, fr)) return rc;
+    }
     if (ph.dissipation && h->gradKernel >= 2) {
         std::vector<double> tb;
         grad_table_for(N, p->Div, p->Bary, tb);
@@ -822,6 +838,24 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     a.stepIndex = h->stepIndex;
     a.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->ph.dissipation && h->dissElemKernel == 3) {
+        ElemMmaArgs ma{};
+        ma.a = a;
+        ma.frags = h->mmaDissFrags;
+        ma.nTiles = blocks;
+        DISPATCH_N(h->N, {
+            const size_t sm = MmaDissDim<NN>::kSmemBytes;
+            if (h->mmaDissGrid == 0) {
+                cudaFuncSetAttribute(k_elem_mma_diss<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                cudaFuncSetAttribute(k_elem_mma_diss<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                int occ = 1;
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem_mma_diss<NN>, kElemThreads, sm);
+                h->mmaDissGrid = h->sms * std::max(occ, 1);
+            }
+            k_elem_mma_diss<NN><<<std::min(blocks, h->mmaDissGrid), kElemThreads, sm, h->stream>>>(ma);
+        });
+        return launch_check(h, "k_elem_mma_diss");
+    }
     if (h->ph.dissipation) {
         DISPATCH_N(h->N, {
             const size_t sm = elem_smem_diss<NN>();
