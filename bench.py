@@ -332,6 +332,28 @@ def main():
         torch.cuda.synchronize()
         t_edge = [a.elapsed_time(b) for a, b, _ in evs]
         t_elem = [b.elapsed_time(cc) for _, b, cc in evs]
+    phases = None
+    if world == 1 and diss:
+        # the five launches groups of a PerssonC0 stage through the stage API (single partition: nothing to exchange)
+        names = ["k_sensor", "k_diss_prepare", "k_edge + RT gradient", "k_visc_edge", "k_elem<N,true>"]
+        evs = []
+        for _ in range(2):
+            for rk in range(5):
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                ev[0].record(stream)
+                dev.stage_sensor(rk)
+                ev[1].record(stream)
+                dev.stage_prepare(rk)
+                ev[2].record(stream)
+                dev.stage_edges(rk)
+                ev[3].record(stream)
+                dev.stage_visc(rk)
+                ev[4].record(stream)
+                dev.stage_update(rk)
+                ev[5].record(stream)
+                evs.append(ev)
+        torch.cuda.synchronize()
+        phases = {nm: statistics.mean(e[i].elapsed_time(e[i + 1]) for e in evs) for i, nm in enumerate(names)}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -345,7 +367,7 @@ def main():
         ach = bv * p.K * 5 * args.steps / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad_pipe [DMMA], k_visc_edge, k_elem<N,true>)",
                     "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
-                    "peak_source": peak_src, "bytes_per_element_stage": bv}
+                    "peak_source": peak_src, "bytes_per_element_stage": bv, "phase_ms": phases}
     if t_elem:
         te = statistics.mean(t_elem) * 1e-3
         ach = b_elem * k_local / te / 1e9

@@ -282,8 +282,9 @@ class Euler:
         return p
 
     # ---- time loop (euler.go:138-220) -------------------------------------------------
-    def Solve(self, solver, print_every=100, out=print):
-        """`solver` implements set_state/step/residual/get_state (the device library or the oracle)."""
+    def Solve(self, solver, print_every=100, out=print, output_dir=None, mesh_file=""):
+        """`solver` implements set_state/step/residual/get_state (the device library or the oracle).  With `output_dir`
+        the files of `OutputFinal` (euler.go:219-318) are written after the last step, as the reference does."""
         solver.set_state(self.Q)
         out(self.print_initialization())
         steps, finished = 0, False
@@ -300,6 +301,9 @@ class Euler:
         self.Q = solver.get_state()
         rate = elapsed * 1e6 / float(self.DFR.K * max(steps, 1))
         out("\nRate of execution = %8.5f us/(element*iteration) over %d iterations" % (rate, steps))
+        if output_dir is not None:
+            from .output_final import output_final
+            output_final(self, self.Q, mesh_file=mesh_file, outdir=output_dir, out=out)
         return steps, elapsed
 
     def check_if_finished(self, t, steps):

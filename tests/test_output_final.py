@@ -134,3 +134,20 @@ def test_output_final_shocktube_files(tmp_path):
     paths = of.output_final(c, c.Q, mesh_file="sod-aligned-100pts.su2", outdir=str(tmp_path))
     assert [p.split("/")[-1] for p in paths] == ["shocktube.dat", "shocktube_analytic.dat"]
     assert open(paths[0]).readline() == "Meshfile: sod-aligned-100pts.su2\n"
+
+
+def test_solve_writes_output_final(tmp_path):
+    """Euler.Solve(..., output_dir=...) ends like the reference's Solve: PrintFinal, then OutputFinal (euler.go:217-219).
+    Driven by the oracle here (CPU); the device library has the same solver surface."""
+    from oracle.euler2d_oracle import OracleSolver
+    ip = InputParameters2D(CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=1, FinalTime=0.2,
+                           MaxIterations=3, Gamma=1.4, Limiter="persson c0", Kappa=5.0)
+    c = Euler(ip, mesh_path("sod-aligned-100pts.su2"))
+    lines = []
+    steps, _ = c.Solve(OracleSolver(c.problem), out=lines.append, output_dir=str(tmp_path), mesh_file="sod-aligned-100pts.su2")
+    assert steps == 3
+    rows = open(tmp_path / "shocktube.dat").read().splitlines()
+    assert rows[0] == "Meshfile: sod-aligned-100pts.su2" and len(rows) == 2 + 4 * c.DFR.K // 5
+    vals = np.array([[float(v) for v in r.split("\t")] for r in rows[2:]])
+    assert vals[0, 1] == pytest.approx(1.0, abs=1e-6) and vals[-1, 1] == pytest.approx(0.125, abs=1e-6)
+    assert (tmp_path / "shocktube_analytic.dat").exists()
