@@ -1,4 +1,5 @@
-"""A/B of the two RT-gradient kernels of the PerssonC0 path on one GPU (DFR2D_GRAD_KERNEL=1: constant-operand DFMA
+"""A/B of the kernel variants of the PerssonC0 path on one GPU (variant 9 = tensor-core element kernel k_elem_mma_diss;
+the rest are the RT-gradient kernels) (DFR2D_GRAD_KERNEL=1: constant-operand DFMA
 k_grad, =2: DMMA k_grad_mma, =3: pipelined persistent DMMA k_grad_pipe with DFR2D_GRAD_MG=3|2): whole-step time, the stage_edges phase (k_edge + k_grad) per RK stage, and the
 relative L2 difference of the two states after the same number of steps.  One JSON line on stdout.
 
@@ -21,7 +22,7 @@ def main():
     ap.add_argument("--ny", type=int, default=500)
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--variants", default="1,2,3,4,5,6,7,8", help="subset of the variant labels to run (1 is the reference state)")
+    ap.add_argument("--variants", default="1,3,9", help="subset of the variant labels to run (1 is the reference state)")
     args = ap.parse_args()
     import torch
     import bench
@@ -30,12 +31,14 @@ def main():
     p = c.problem
     out = {"K": int(p.K), "N": int(p.N), "steps": args.steps}
     states = {}
-    # label -> (DFR2D_GRAD_KERNEL, DFR2D_GRAD_MG, DFR2D_GRAD_SKEW_NS)
-    variants = {1: ("1", "3", "0"), 2: ("2", "3", "0"), 3: ("3", "3", "0"), 4: ("3", "2", "0"),
-                5: ("3", "3", "1500"), 6: ("3", "3", "3000"), 7: ("3", "3", "5000"), 8: ("3", "2", "3000")}
+    # label -> (DFR2D_GRAD_KERNEL, DFR2D_GRAD_MG, DFR2D_GRAD_SKEW_NS, DFR2D_DISS_ELEM_KERNEL)
+    variants = {1: ("1", "3", "0", "1"), 2: ("2", "3", "0", "1"), 3: ("3", "3", "0", "1"), 4: ("3", "2", "0", "1"),
+                5: ("3", "3", "1500", "1"), 6: ("3", "3", "3000", "1"), 7: ("3", "3", "5000", "1"), 8: ("3", "2", "3000", "1"),
+                9: ("3", "3", "0", "3")}
     variants = {k: v for k, v in variants.items() if str(k) in args.variants.split(",")}
     for gk in variants:
-        os.environ["DFR2D_GRAD_KERNEL"], os.environ["DFR2D_GRAD_MG"], os.environ["DFR2D_GRAD_SKEW_NS"] = variants[gk]
+        (os.environ["DFR2D_GRAD_KERNEL"], os.environ["DFR2D_GRAD_MG"], os.environ["DFR2D_GRAD_SKEW_NS"],
+         os.environ["DFR2D_DISS_ELEM_KERNEL"]) = variants[gk]
         dev = lib.Dfr2d(p)
         dev.set_state(c.Q)
         dev.step(2, sync=True)
@@ -72,7 +75,7 @@ def main():
             "finite": bool(np.isfinite(states[gk]).all()),
         }
         dev.close()
-    out["variants"] = {"grad_kernel_%d" % k: "DFR2D_GRAD_KERNEL=%s DFR2D_GRAD_MG=%s DFR2D_GRAD_SKEW_NS=%s" % v for k, v in variants.items()}
+    out["variants"] = {"grad_kernel_%d" % k: "DFR2D_GRAD_KERNEL=%s DFR2D_GRAD_MG=%s DFR2D_GRAD_SKEW_NS=%s DFR2D_DISS_ELEM_KERNEL=%s" % v for k, v in variants.items()}
     for k in [k for k in variants if k != 1 and 1 in variants]:
         out["rel_l2_state_%d_vs_1" % k] = float(np.linalg.norm(states[1] - states[k]) / np.linalg.norm(states[1]))
     print(json.dumps(out))
