@@ -53,6 +53,11 @@ func fs(f *Euler2D.FreeStream) (o C.dfr2d_freestream) {
 // New mirrors the tail of NewEuler + NewRungeKuttaSSP (euler.go:98-117, :343-406).
 // kappa is ip.Kappa as parsed; device is the CUDA ordinal.
 func New(c *Euler2D.Euler, kappa float64, device int) *Solver {
+	return newPartition(c, kappa, 1, 0, device)
+}
+
+// newPartition builds partition `part` of `nParts` (PartitionMap.Split1D element ranges) on CUDA device `device`.
+func newPartition(c *Euler2D.Euler, kappa float64, nParts, part, device int) *Solver {
 	var (
 		dfr    = c.DFR
 		rt     = dfr.FluxElement
@@ -152,7 +157,7 @@ func New(c *Euler2D.Euler, kappa float64, device int) *Solver {
 		unsafe.Pointer(p.edge_len), unsafe.Pointer(p.bp_edge), unsafe.Pointer(p.bp_x), unsafe.Pointer(p.bp_y)} {
 		pin.Pin(ptr)
 	}
-	if rc := C.dfr2d_create(&p, 1, 0, C.int(device), &s.h); rc != 0 {
+	if rc := C.dfr2d_create(&p, C.int(nParts), C.int(part), C.int(device), &s.h); rc != 0 {
 		panic(fmt.Errorf("dfr2d_create: %s", C.GoString(C.dfr2d_last_error(nil))))
 	}
 	s.SetState(c)
@@ -223,41 +228,52 @@ func (s *Solver) PlotField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []float32 
 
 func (s *Solver) Close() { C.dfr2d_destroy(s.h); s.h = nil }
 
-// MultiSolver drives one handle per GPU from a single Go process: the per-stage protocol of include/dfr2d.h
-// (sensor / prepare / edges / visc / update with three exchange points and one MAX reduction), the halo bytes
-// moved by the caller-supplied functions (cudaMemcpyPeerAsync or NCCL bindings).  bench.py runs the same protocol
-// with one process per GPU over torch.distributed.
+// MultiSolver drives one handle per GPU from a single Go process -- the shape of the reference's controller goroutine
+// (euler.go:408-412): dfr2d_multi_step runs the per-stage protocol of include/dfr2d.h over all partitions, moving the
+// halo bytes with cudaMemcpyPeerAsync ordered by CUDA events and taking the wave-speed maximum with a peer-reading
+// kernel; nothing synchronises with the host inside the call.  (One process per GPU with NCCL, as bench.py does it
+// through torch.distributed, uses the dfr2d_stage_* / dfr2d_exchange_* calls instead.)
 type MultiSolver struct {
-	Parts    []*Solver
-	Exchange func(which int) // moves every partition's send buffer of exchange `which` into its peers' receive buffers
-	MaxWave  func()          // MAX-allreduce of dfr2d_wavespeed_buffer (two doubles) over the partitions
+	Parts []*Solver
 }
 
-func (m *MultiSolver) Step() {
-	for rk := 0; rk < 5; rk++ {
+// NewMulti creates one partition per device (devices[g] may repeat: several partitions per GPU).
+func NewMulti(c *Euler2D.Euler, kappa float64, devices []int) *MultiSolver {
+	m := &MultiSolver{}
+	for g, dev := range devices {
+		m.Parts = append(m.Parts, newPartition(c, kappa, len(devices), g, dev))
+	}
+	return m
+}
+
+// Step runs nsteps x {RK.Step; Time += GlobalDT; StepCount++} over all partitions.
+func (m *MultiSolver) Step(nsteps int) (time, dt float64, steps int, finished bool) {
+	hs := make([]*C.dfr2d_handle, len(m.Parts))
+	for g, s := range m.Parts {
+		hs[g] = s.h
+	}
+	var info C.dfr2d_step_info
+	if rc := C.dfr2d_multi_step(&hs[0], C.int(len(hs)), C.int(nsteps), &info); rc != 0 {
 		for _, s := range m.Parts {
-			s.check(C.dfr2d_stage_sensor(s.h, C.int(rk)), "dfr2d_stage_sensor")
-		}
-		m.Exchange(int(C.DFR2D_XCHG_VERTEX))
-		for _, s := range m.Parts {
-			s.check(C.dfr2d_stage_prepare(s.h, C.int(rk)), "dfr2d_stage_prepare")
-		}
-		// (an asynchronous Exchange would be posted here, dfr2d_stage_edges_interior called for every partition, and the
-		// exchange awaited before dfr2d_stage_edges: interior-edge fluxes do not need the halo)
-		m.Exchange(int(C.DFR2D_XCHG_EDGE))
-		for _, s := range m.Parts {
-			s.check(C.dfr2d_stage_edges(s.h, C.int(rk)), "dfr2d_stage_edges")
-		}
-		m.Exchange(int(C.DFR2D_XCHG_DISS))
-		for _, s := range m.Parts {
-			s.check(C.dfr2d_stage_visc(s.h, C.int(rk)), "dfr2d_stage_visc")
-		}
-		m.MaxWave()
-		for _, s := range m.Parts {
-			s.check(C.dfr2d_stage_update(s.h, C.int(rk)), "dfr2d_stage_update")
+			s.check(rc, "dfr2d_multi_step")
 		}
 	}
+	return float64(info.time), float64(info.dt), int(info.steps), info.finished != 0
+}
+
+// GetState gathers every partition's columns into c.Q4 (each handle writes only its own element range).
+func (m *MultiSolver) GetState(c *Euler2D.Euler) {
 	for _, s := range m.Parts {
-		s.check(C.dfr2d_step_finish(s.h, nil), "dfr2d_step_finish")
+		s.check(C.dfr2d_get_state(s.h, d(m.Parts[0].global)), "dfr2d_get_state")
+	}
+	g := m.Parts[0]
+	for n := 0; n < 4; n++ {
+		copy(c.Q4[n].DataP, g.global[n*g.np*g.k:(n+1)*g.np*g.k])
+	}
+}
+
+func (m *MultiSolver) Close() {
+	for _, s := range m.Parts {
+		s.Close()
 	}
 }

@@ -62,6 +62,7 @@ struct dfr2d_handle {
     DevScalars *scHost = nullptr;     // pinned
     long long stageCounter = 0, stepIndex = 0, launches = 0;
     bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
+    cudaEvent_t evXchg = nullptr, evWave = nullptr;   // dfr2d_multi_step: "my sends are posted", "my edge phase is done"
     bool interiorDone = false;        // the interior-edge kernel of the stage in flight has been launched (overlap with the halo)
     int edgeBlocks = 0;
     bool smemAttrSet = false;
@@ -169,6 +170,8 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->evXchg) cudaEventDestroy(h->evXchg);
+    if (h->evWave) cudaEventDestroy(h->evWave);
     for (void *p : h->allocs) cudaFree(p);
     if (h->scHost) cudaFreeHost(h->scHost);
     if (g_ops_owner == h) g_ops_owner = nullptr;
@@ -1162,6 +1165,154 @@ extern "C" int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info) {
     }
     int rc = dfr2d_step_finish(h, info);
     if (info && h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) info->finished = 1;
+    return rc;
+}
+
+// ---- single-process multi-GPU driver ------------------------------------------------------------------------------
+struct PeerSlots {
+    const unsigned long long *p[32];
+    int n;
+};
+
+// {max wave speed, max viscous wave speed} over all partitions: bit patterns of non-negative doubles order like the
+// doubles.  A peer may be updating its own slot while it is read here; the slot only ever grows towards the global
+// maximum, so either value is a valid contribution.
+__global__ void k_wave_max_peers(unsigned long long *mine, PeerSlots peers) {
+    const int t = threadIdx.x;
+    if (t < 2) {
+        unsigned long long v = mine[t];
+        for (int i = 0; i < peers.n; i++) {
+            const unsigned long long w = *(const volatile unsigned long long *)(peers.p[i] + t);
+            v = w > v ? w : v;
+        }
+        mine[t] = v;
+    }
+}
+
+static int multi_prepare(dfr2d_handle **hs, int n) {
+    for (int i = 0; i < n; i++) {
+        dfr2d_handle *h = hs[i];
+        if (!h || h->nParts != n || h->part != i) return 1;
+        CK(cudaSetDevice(h->device));
+        if (!h->evXchg) {
+            CK(cudaEventCreateWithFlags(&h->evXchg, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->evWave, cudaEventDisableTiming));
+            for (int j = 0; j < n; j++)
+                if (hs[j] && hs[j]->device != h->device) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, h->device, hs[j]->device);
+                    if (!can) { h->err = "dfr2d_multi_step needs peer access between the devices"; return 2; }
+                    cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return 2; }
+                    cudaGetLastError();
+                }
+        }
+    }
+    return 0;
+}
+
+static const std::vector<int64_t> &xchg_counts(const dfr2d_handle *h, int which) {
+    return which == DFR2D_XCHG_EDGE ? h->sendCounts : (which == DFR2D_XCHG_VERTEX ? h->vtxCounts : h->dissCounts);
+}
+
+// segment j of partition i's send buffer -> segment i of partition j's receive buffer (all_to_all semantics; counts are
+// symmetric).  Copies run on the sender's stream behind its pack kernel; receivers wait for the senders' events.  The
+// receive buffer of the previous stage has been consumed by then: every stage ends in multi_wave_max, where each stream
+// waits for all others' edge phase.
+static int multi_exchange(dfr2d_handle **hs, int n, int which) {
+    bool any = false;
+    for (int i = 0; i < n; i++) {
+        dfr2d_handle *h = hs[i];
+        const std::vector<int64_t> &ci = xchg_counts(h, which);
+        if ((int)ci.size() < n) continue;
+        const double *sb = which == DFR2D_XCHG_EDGE ? h->sendBuf : (which == DFR2D_XCHG_VERTEX ? h->vSendBuf : h->dSendBuf);
+        CK(cudaSetDevice(h->device));
+        int64_t so = 0;
+        bool sent = false;
+        for (int j = 0; j < n; j++) {
+            const int64_t cnt = ci[j];
+            if (j != i && cnt > 0) {
+                dfr2d_handle *d = hs[j];
+                const std::vector<int64_t> &cj = xchg_counts(d, which);
+                int64_t ro = 0;
+                for (int k = 0; k < i; k++) ro += cj[k];
+                double *rb = which == DFR2D_XCHG_EDGE ? d->recvBuf : (which == DFR2D_XCHG_VERTEX ? d->vRecvBuf : d->dRecvBuf);
+                CK(cudaMemcpyPeerAsync(rb + ro, d->device, sb + so, h->device, (size_t)cnt * sizeof(double), h->stream));
+                sent = true;
+            }
+            so += cnt;
+        }
+        if (sent) { CK(cudaEventRecord(h->evXchg, h->stream)); any = true; }
+    }
+    if (!any) return 0;
+    for (int j = 0; j < n; j++) {
+        dfr2d_handle *d = hs[j], *h = d;       // (CK reports into h)
+        const std::vector<int64_t> &cj = xchg_counts(d, which);
+        if ((int)cj.size() < n) continue;
+        CK(cudaSetDevice(d->device));
+        for (int i = 0; i < n; i++)
+            if (i != j && cj[i] > 0 && !(hs[i]->device == d->device && hs[i]->stream == d->stream))
+                CK(cudaStreamWaitEvent(d->stream, hs[i]->evXchg, 0));
+    }
+    return 0;
+}
+
+static int multi_wave_max(dfr2d_handle **hs, int n) {
+    for (int i = 0; i < n; i++) {
+        dfr2d_handle *h = hs[i];
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventRecord(h->evWave, h->stream));
+    }
+    for (int j = 0; j < n; j++) {
+        dfr2d_handle *d = hs[j], *h = d;
+        CK(cudaSetDevice(d->device));
+        PeerSlots ps{};
+        for (int i = 0; i < n; i++)
+            if (i != j) {
+                if (!(hs[i]->device == d->device && hs[i]->stream == d->stream)) CK(cudaStreamWaitEvent(d->stream, hs[i]->evWave, 0));
+                ps.p[ps.n++] = &hs[i]->sc->wave[hs[i]->stageCounter & 1][0];
+            }
+        k_wave_max_peers<<<1, 32, 0, d->stream>>>(&d->sc->wave[d->stageCounter & 1][0], ps);
+        d->launches++;
+        if (int rc = launch_check(d, "k_wave_max_peers")) return rc;
+    }
+    return 0;
+}
+
+extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info) {
+    if (!hs || n < 1 || n > 32) return 1;
+    if (n == 1) return dfr2d_step(hs[0], nsteps, info);
+    if (int rc = multi_prepare(hs, n)) return rc;
+#define MULTI_ALL(call)                                  \
+    for (int g = 0; g < n; g++)                          \
+        if (int rc = call) return rc;
+    for (int s = 0; s < nsteps; s++) {
+        if (hs[0]->stepIndex >= 1 && hs[0]->stepIndex >= (long long)hs[0]->ph.maxIter) break;
+        for (int rk = 0; rk < 5; rk++) {
+            MULTI_ALL(stage_sensor(hs[g], rk));
+            if (hs[0]->ph.dissipation)
+                if (int rc = multi_exchange(hs, n, DFR2D_XCHG_VERTEX)) return rc;
+            MULTI_ALL(stage_prepare(hs[g], rk));
+            if (int rc = multi_exchange(hs, n, DFR2D_XCHG_EDGE)) return rc;
+            MULTI_ALL(stage_edges(hs[g], rk));
+            if (hs[0]->ph.dissipation)
+                if (int rc = multi_exchange(hs, n, DFR2D_XCHG_DISS)) return rc;
+            MULTI_ALL(stage_visc(hs[g], rk));
+            if (int rc = multi_wave_max(hs, n)) return rc;
+            MULTI_ALL(stage_update(hs[g], rk, nullptr));
+        }
+    }
+#undef MULTI_ALL
+    int rc = 0;
+    for (int g = n - 1; g >= 0; g--) {
+        dfr2d_step_info tmp{};
+        int r = dfr2d_step_finish(hs[g], &tmp);       // synchronises partition g; surfaces "NAN found"
+        if (r) rc = r;
+        if (g == 0 && info) {
+            *info = tmp;
+            if (hs[0]->stepIndex >= 1 && hs[0]->stepIndex >= (long long)hs[0]->ph.maxIter) info->finished = 1;
+        }
+    }
     return rc;
 }
 

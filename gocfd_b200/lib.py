@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -105,6 +105,7 @@ def load():
     lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
     lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
     lib.dfr2d_rcm_order.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _ip, _ip]
+    lib.dfr2d_multi_step.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.POINTER(StepInfo)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
     _lib = lib
@@ -167,6 +168,18 @@ def grad_mma_table(problem):
     out = np.zeros(n)
     lib.dfr2d_grad_mma_table(problem.N, _d(div), _d(bary), _d(out), n)
     return out
+
+
+def multi_step(devs, nsteps=1, sync=True):
+    """dfr2d_multi_step over the partitions `devs` (Dfr2d objects created with n_parts=len(devs), part=g): the
+    single-process multi-GPU driver -- peer copies for the halo, a peer-reading kernel for the wave-speed maximum."""
+    lib = load()
+    arr = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    info = StepInfo()
+    rc = lib.dfr2d_multi_step(arr, len(devs), nsteps, C.byref(info) if sync else None)
+    if rc != 0:
+        raise Dfr2dError("dfr2d_multi_step failed (%d): %s" % (rc, "; ".join(lib.dfr2d_last_error(d.h).decode() for d in devs)))
+    return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
 
 
 def rcm_order(problem):

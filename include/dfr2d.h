@@ -193,6 +193,16 @@ int dfr2d_exchange_counts(const dfr2d_handle *h, int which, int64_t *send_counts
 int dfr2d_exchange_buffers(dfr2d_handle *h, int which, void **send_dev, void **recv_dev);
 int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info); /* after stage 4: read back time/steps (info may be NULL) */
 
+/* ---- single-process multi-GPU driver (the natural shape for the Go host: one controller goroutine, euler.go:408-412) ----
+ * hs[g] = dfr2d_create(p, n, g, device_g, ...) for g = 0..n-1, all in this process (several partitions may share a device).
+ * dfr2d_multi_step runs nsteps x { 5 x the stage protocol above } over all partitions: every exchange is a set of
+ * cudaMemcpyPeerAsync copies (send segment of partition i -> receive segment of partition j, only between partitions that
+ * share cut edges / vertices) ordered by CUDA events, and the MAX of the wave-speed pair is taken by a one-warp kernel per
+ * partition that reads its peers' slots through peer access.  No host synchronisation inside the call; `info` (may be
+ * NULL) is read back from partition 0 at the end.  Replaces the goroutine fan-out of RungeKutta5SSP.Step
+ * (euler.go:408-418) and the serial max of calculateGlobalDT (euler.go:951-955). */
+int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info);
+
 /* ---- host-only partition plan (no CUDA): the bookkeeping dfr2d_create performs for (n_parts, part), exposed so
  * the decomposition can be verified bit-exactly on a CPU-only machine.  Mirrors utils.PartitionMap +
  * PartitionEdgesByK (parallelism.go:179-190) plus the ghost/halo lists that replace the goroutines' shared memory. */

@@ -49,3 +49,41 @@ def test_device_converges_to_the_exact_vortex(n, flux, coarse, fine, cfl, min_or
     e1, e2 = error(coarse), error(fine)
     assert e2 < max_fine_error
     assert np.log2(e1 / e2) > min_order
+
+
+# ---- dfr2d_multi_step: the single-process multi-GPU driver.  Written at the end of round 1 without a GPU at hand, so
+# it only runs on request until it has been through one GPU run; here all partitions share one device (peer copies
+# degenerate to device copies, the event waits to stream order) and the result must be the single-partition run, bit
+# for bit, like the hand-driven protocol of tests/test_gpu_parity.py.
+
+_EXPERIMENTAL = __import__("os").environ.get("DFR2D_TEST_EXPERIMENTAL") == "1"
+
+
+@pytest.mark.skipif(not _EXPERIMENTAL, reason="not yet run on a GPU (set DFR2D_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("n_parts,n,diss", [(3, 2, False), (2, 2, True), (4, 4, True)])
+def test_multi_step_driver_matches_single_partition(n_parts, n, diss):
+    from conftest import mesh_path
+    from gocfd_b200 import lib
+    if diss:
+        c = make(dict(PolynomialOrder=n, InitType="shocktube", CFL=2.0, FinalTime=0.2, Limiter="persson c0", Kappa=5.0),
+                 mesh_path("sod-aligned-100pts.su2"))
+        x, _ = c.DFR.solution_xy()
+        w = 0.5 * (1.0 - np.tanh((x - 0.503) / 0.004))
+        c.Q = np.stack([c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w for v in range(4)])
+    else:
+        c = make(dict(PolynomialOrder=n, InitType="IVortex", CFL=1.0, FinalTime=50.0), structured_tri_mesh(16, 12))
+    one = lib.Dfr2d(c.problem)
+    one.set_state(c.Q)
+    a = one.step(4)
+    devs = [lib.Dfr2d(c.problem, n_parts=n_parts, part=r) for r in range(n_parts)]
+    for d in devs:
+        d.set_state(c.Q)
+    b = lib.multi_step(devs, 4)
+    assert a["steps"] == b["steps"] == 4 and a["time"] == b["time"] and a["dt"] == b["dt"]
+    q = np.zeros_like(c.Q)
+    for d in devs:
+        d.get_state(q)
+    assert np.array_equal(q, one.get_state())
+    for d in devs:
+        d.close()
+    one.close()
