@@ -331,7 +331,7 @@ template <int N, int MG>      // MG: m-tiles accumulated at a time (2 or 3)
 __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradPipeArgs args) {
     using GD = GradMmaDim<N>;
     using PD = GradPipeDim<N>;
-    constexpr int NI = GD::NI, NEd = GD::NEd, NF = GD::NF, NF3 = GD::NF3, E = kElemsPerBlock, SE = GD::SE;
+    constexpr int NI = GD::NI, NEd = GD::NEd, NF3 = GD::NF3, E = kElemsPerBlock, SE = GD::SE;
     constexpr int MT = GD::MT, KI = GD::KI, KE = GD::KE, UROWS = GD::UROWS;
     const GradArgs &a = args.a;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
