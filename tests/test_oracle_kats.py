@@ -442,3 +442,67 @@ def test_rt_element_polynomial_divergence(p_rt):
             max_f = np.abs(f1).max()
             tol = 1e-9 * max_f if max_f >= 1e-9 else 1e-9
             assert np.abs(rt.Div @ proj - div(p)).max() <= tol
+
+
+def test_su2_reader_reference_fixture():
+    """TestReadSU2 (readfiles/readSU2_test.go:11-72) on the reference's own inline 22-element gmsh export
+    (tests/golden/meshes/su2_reader_kat.su2 is that literal): element/vertex counts, last element, last vertex to the
+    last bit, markers in file order with the two "periodic-rightleft" blocks concatenated."""
+    from gocfd_b200.host.readfiles import read_su2
+    m = read_su2(mesh_path("su2_reader_kat.su2"))
+    assert m.K == 22 and int(m.EToV[m.K - 1, 2]) == 17
+    assert len(m.VX) == 18 and len(m.VY) == 18
+    assert m.VX[-1] == -7.100939331382065 and m.VY[-1] == 2.889910324036197
+    assert list(m.BCEdges) == ["periodic-rightleft", "top", "bottom"]
+    assert [len(v) for v in m.BCEdges.values()] == [4, 4, 4]          # 2 + 2 periodic, 4 top, 4 bottom
+    bottom, per = m.BCEdges["bottom"], m.BCEdges["periodic-rightleft"]
+    assert bottom[2].tolist() == [5, 6] and bottom[3].tolist() == [6, 1]
+    assert per.tolist() == [[3, 11], [11, 0], [1, 7], [7, 2]]
+
+
+def test_input_parameters_parse():
+    """TestInputParameters_Parse (model_problems/Euler2D/euler_test.go:750-776), same document and checks."""
+    doc = """
+Title: Test Case
+CFL: 1.
+InitType: Freestream # Can be IVortex or Freestream
+FluxType: Roe
+PolynomialOrder: 2
+FinalTime: 4.
+BCs: 
+  Inflow:
+      37:
+         NPR: 4.0
+  Outflow:
+      22:
+         P: 1.5
+"""
+    ip = InputParameters2D().parse(doc)
+    assert ip.BCs["Inflow"][37]["NPR"] == 4.0
+    assert ip.BCs["Outflow"][22]["P"] == 1.5
+    assert ip.FinalTime == 4.0 and ip.CFL == 1.0 and ip.PolynomialOrder == 2
+    assert ip.InitType == "Freestream" and ip.FluxType == "Roe" and ip.Title == "Test Case"
+
+
+def test_element_mean_of_mach5_shock_field():
+    """TestElementMean (model_problems/Euler2D/dfr_shock_capturing_Euler_test.go:15-56; runs under `go test -v`):
+    Williams-Shunn-Jameson weighted element means (UpdateElementMean, euler.go:1004-1020) of the NORMALSHOCKTESTM5 field
+    (DG2D/test_functions2.go:133-236: u1 = 5, p1 = rho1 = 1, Rankine-Hugoniot state for x >= 0) at N=2 on
+    test_10tris_centered.neu.  Pins the solution-point coordinates and the cubature weights that build the mass matrix."""
+    dfr = new_dfr2d(2, mesh_path("test_10tris_centered.neu"))
+    g = 1.4
+    m1n = 5.0 / math.sqrt(g)
+    rho_ratio = ((g + 1) * m1n * m1n) / ((g - 1) * m1n * m1n + 2)
+    p_ratio = 1 + (2 * g / (g + 1)) * (m1n * m1n - 1)
+    u2 = 5.0 / rho_ratio
+    U1 = [1.0, 5.0, 0.0, 1.0 / (g - 1) + 0.5 * 25.0]
+    U2 = [rho_ratio, rho_ratio * u2, 0.0, p_ratio / (g - 1) + 0.5 * rho_ratio * u2 * u2]
+    x, _ = dfr.solution_xy()
+    w = dfr.SolutionElement.W
+    assert abs(w.sum() - 1.0) < 1e-12
+    means = [(w[:, None] * np.where(x < 0, U1[n], U2[n])).sum(axis=0) for n in range(4)]
+    np.testing.assert_allclose(means[0], [1, 1, 1.40545, 4.28205, 4.6875, 1, 1, 1.40545, 4.28205, 4.6875], atol=1e-4)
+    np.testing.assert_allclose(means[1], [5] * 10, atol=1e-4)
+    np.testing.assert_allclose(means[2], [0] * 10, atol=1e-4)
+    np.testing.assert_allclose(means[3], [15, 15, 19.32477, 50.00856, 54.33333, 15, 15, 19.32477, 50.00856, 54.33333],
+                               atol=1e-4)
