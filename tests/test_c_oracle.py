@@ -130,3 +130,27 @@ def test_naca_transonic_local_dt_with_dissipation():
     a, b = pair(c)
     a.step(12), b.step(12)
     assert rel_l2(a.get_state(), b.get_state()) < TOL
+
+
+def _naca_front_case():
+    """NACA0012 mesh, N=2, M=0.8, local time stepping, PerssonC0, with a smeared density/energy front at x = 0.6 so that
+    the sensor fires in ~400 elements during the first steps (the free-stream start needs thousands of iterations to
+    grow a shock): local dt with an ACTIVE viscous limit and the DTVisc carry-over (euler.go:989-999)."""
+    c = make(dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=100000, Minf=0.8, Alpha=2.0,
+                  Limiter="PerssonC0", Kappa=4.5), mesh_path("mesh_NACA0012_inv.su2"))
+    x, _ = c.DFR.solution_xy()
+    fac = 1.0 + 0.5 * (0.5 * (1.0 - np.tanh((x - 0.6) / 0.004)))
+    c.Q[0] *= fac
+    c.Q[3] *= fac
+    return c
+
+
+def test_naca_front_local_dt_active_dissipation():
+    c = _naca_front_case()
+    a, b = pair(c)
+    b.rhs(0)
+    assert b.SigmaScalar.max() > 0.1 and (b.SigmaScalar > 0.05).sum() > 100
+    a.step(2), b.step(2)
+    assert (b.DTVisc > 1e-9).sum() > 100           # the viscous branch of CalculateLocalDT was taken
+    assert rel_l2(a.get_state(), b.get_state()) < TOL
+    np.testing.assert_allclose(a.residual(), b.residual(), rtol=1e-9, atol=1e-13)

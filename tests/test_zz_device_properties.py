@@ -87,3 +87,23 @@ def test_multi_step_driver_matches_single_partition(n_parts, n, diss):
     for d in devs:
         d.close()
     one.close()
+
+
+@pytest.mark.parametrize("diss_elem", [1] + ([3] if _EXPERIMENTAL else []))
+def test_naca_front_local_dt_active_dissipation_on_device(diss_elem, monkeypatch):
+    """Local time stepping with an ACTIVE sensor (tests/test_c_oracle.py::_naca_front_case: ~400 elements above
+    sigma = 0.05 in the first steps, DTVisc > 1e-9 in ~500): viscous dt limit and DTVisc carry-over on the device."""
+    from test_c_oracle import _naca_front_case
+    from gocfd_b200 import lib
+    from oracle.euler2d_oracle import OracleSolver
+    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", str(diss_elem))
+    c = _naca_front_case()
+    dev, ora = lib.Dfr2d(c.problem), OracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    dev.step(3), ora.step(3)
+    assert (ora.DTVisc > 1e-9).sum() > 100
+    den = np.linalg.norm(ora.get_state())
+    assert np.linalg.norm(dev.get_state() - ora.get_state()) / den < 1e-11
+    np.testing.assert_allclose(dev.get_field(0), ora.DT, rtol=1e-10)
+    dev.close()
