@@ -225,3 +225,14 @@ def test_rcm_renumbering_shrinks_the_cuts_of_an_unstructured_mesh():
     plans = [lib.Plan(p2, 8, r) for r in range(8)]
     assert sum(pl.n_cut for pl in plans) == 2 * after
     print("cut edges at 8 partitions: %d -> %d, adjacency bandwidth %d -> %d" % (before, after, bw0, bw1))
+
+
+def test_multi_step_rejects_bad_requests_without_touching_cuda():
+    import ctypes as C
+    from gocfd_b200 import lib
+    L = lib.load()
+    assert L.dfr2d_multi_step(None, 2, 1, None) == 1
+    arr = (C.c_void_p * 2)(None, None)
+    assert L.dfr2d_multi_step(arr, 0, 1, None) == 1
+    assert L.dfr2d_multi_step(arr, 33, 1, None) == 1
+    assert L.dfr2d_multi_step(arr, 2, 1, None) == 1      # null handles
