@@ -7,7 +7,8 @@ import sys
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tensor_op_dmma.avg.pct_of_peak_sustained_active",
+        "sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active",          # FP64 + DMMA pipe shared by the 4 SMSPs
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
