@@ -272,6 +272,19 @@ func (m *MultiSolver) GetState(c *Euler2D.Euler) {
 	}
 }
 
+// Residual is the per-variable signed max over all partitions (PrintUpdate's loop over np, euler.go:823-829).
+func (m *MultiSolver) Residual() (r [4]float64) {
+	for g, s := range m.Parts {
+		rg := s.Residual()
+		for n := 0; n < 4; n++ {
+			if g == 0 || rg[n] > r[n] {
+				r[n] = rg[n]
+			}
+		}
+	}
+	return
+}
+
 func (m *MultiSolver) Close() {
 	for _, s := range m.Parts {
 		s.Close()
