@@ -1557,6 +1557,22 @@ extern "C" int64_t dfr2d_grad_mma_table(int N, const double *Div, const double *
     return (int64_t)tb.size();
 }
 
+extern "C" int64_t dfr2d_mma_diss_table(int N, const double *DivInt, const double *Vinv, const double *V, double *out, int64_t cap) {
+    std::vector<double> fr;
+    if (!DivInt || !Vinv || !V) return -1;
+    switch (N) {
+        case 0: build_mma_diss_frags<0>(DivInt, Vinv, V, fr); break;
+        case 1: build_mma_diss_frags<1>(DivInt, Vinv, V, fr); break;
+        case 2: build_mma_diss_frags<2>(DivInt, Vinv, V, fr); break;
+        case 3: build_mma_diss_frags<3>(DivInt, Vinv, V, fr); break;
+        case 4: build_mma_diss_frags<4>(DivInt, Vinv, V, fr); break;
+        default: return -1;
+    }
+    if (out)
+        for (int64_t i = 0; i < cap && i < (int64_t)fr.size(); i++) out[i] = fr[i];
+    return (int64_t)fr.size();
+}
+
 extern "C" int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
                                int32_t *order) {
     if (K <= 0 || NE < 0 || !edge_kL || !edge_kR || !edge_nconn || !order) { g_create_error = "bad rcm request"; return 1; }

@@ -51,7 +51,7 @@ EXPORTS = [
     "dfr2d_set_stream", "dfr2d_partition_range", "dfr2d_halo_counts", "dfr2d_halo_buffers",
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
-    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step",
+    "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -105,6 +105,8 @@ def load():
     lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
     lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
     lib.dfr2d_rcm_order.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _ip, _ip]
+    lib.dfr2d_mma_diss_table.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_int64]
+    lib.dfr2d_mma_diss_table.restype = C.c_int64
     lib.dfr2d_multi_step.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.POINTER(StepInfo)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
@@ -167,6 +169,18 @@ def grad_mma_table(problem):
         raise RuntimeError("dfr2d_grad_mma_table: bad request")
     out = np.zeros(n)
     lib.dfr2d_grad_mma_table(problem.N, _d(div), _d(bary), _d(out), n)
+    return out
+
+
+def mma_diss_table(problem):
+    """A-fragment table [DivInt | Vinv | V] of k_elem_mma_diss for `problem`'s order (host-only)."""
+    lib = load()
+    ops = [np.ascontiguousarray(x, dtype=np.float64) for x in (problem.DivInt, problem.Vinv, problem.V)]
+    n = lib.dfr2d_mma_diss_table(problem.N, _d(ops[0]), _d(ops[1]), _d(ops[2]), None, 0)
+    if n < 0:
+        raise RuntimeError("dfr2d_mma_diss_table: bad request")
+    out = np.zeros(n)
+    lib.dfr2d_mma_diss_table(problem.N, _d(ops[0]), _d(ops[1]), _d(ops[2]), _d(out), n)
     return out
 
 

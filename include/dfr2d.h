@@ -236,6 +236,10 @@ int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t
  * Exposed so that the layout can be checked on the CPU (tests/test_grad_mma_layout.py). */
 int64_t dfr2d_grad_mma_table(int N, const double *Div, const double *Bary, double *out, int64_t cap);
 
+/* Host-only: the A-fragment table [DivInt | Vinv | V] of the tensor-core dissipation element kernel (k_elem_mma_diss,
+ * DFR2D_DISS_ELEM_KERNEL=3), same conventions as dfr2d_grad_mma_table; for the CPU layout check. */
+int64_t dfr2d_mma_diss_table(int N, const double *DivInt, const double *Vinv, const double *V, double *out, int64_t cap);
+
 /* number of kernels this handle has launched (for the benchmark's gpu_launches claim) */
 int64_t dfr2d_launch_count(const dfr2d_handle *h);
 

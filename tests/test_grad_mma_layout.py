@@ -114,3 +114,76 @@ def test_grad_mma_tile_replay_matches_dense_gradient(n):
     assert np.abs(got_y[rows] - want_y[rows]).max() < 1e-12 * np.abs(want_y[rows]).max()
     # rows the kernel never writes are the duplicate interior block only
     assert not got_x[ni:2 * ni].any()
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_elem_mma_diss_tile_replay(n):
+    """k_elem_mma_diss (gocfd_b200/csrc/dfr2d_elem_mma_diss.cuh): RHS = -(1/J) DivInt . F, then the limiter
+    Vinv -> mode scaling -> V, replayed with the library's own fragment table and the kernel's smem row indexing
+    (rows [0, QROWS) of the F block are reused for RHS and for the scaled modes), against the dense statement of
+    RHSInternalPoints + limitAndFilterSolution (euler.go:665-699, dissipation.go:606-622)."""
+    ip = InputParameters2D(CFL=1.0, FluxType="Roe", InitType="Freestream", PolynomialOrder=n, FinalTime=1.0,
+                           MaxIterations=10, Gamma=1.4, Minf=0.5, Limiter="PerssonC0", Kappa=5.0)
+    c = Euler(ip, structured_tri_mesh(2, 2, tag="far"))
+    p = c.problem
+    ni, nf = p.NpInt, p.NpFlux
+    m1, k1, m3, k3 = (ni + 7) // 8, (nf + 3) // 4, (ni + 7) // 8, (ni + 3) // 4
+    qrows, frows = 4 * k3, 4 * k1
+    table = lib.mma_diss_table(p)
+    assert table.size == (m1 * k1 + 2 * m3 * k3) * 32
+    divint, vinv, v, mf = np.asarray(p.DivInt), np.asarray(p.Vinv), np.asarray(p.V), np.asarray(p.ModeFilter)
+    rng = np.random.default_rng(10 + n)
+    f = rng.standard_normal((nf, E))
+    mooj = -1.0 / (0.5 + rng.random(E))
+    oma = rng.random(E)                                   # 1 - sin(pi sigma / 2)
+    # dense statement
+    rhs = (divint @ f) * mooj
+    uh = vinv @ rhs
+    uh[1:] *= (mf[1:, None] * oma[None, :])
+    want = v @ uh
+    # replay
+    lanes = np.arange(32)
+    fr, fc = lanes >> 2, lanes & 3
+    s_f = np.zeros((frows, SE))
+    s_f[:nf, :E] = f
+
+    def product(frag0, mt_n, ks_n):
+        """C[mt][nt] fragments of (operator at table offset frag0) . s_f[rows < 4 ks_n]."""
+        acc = [[np.zeros((32, 2)) for _ in range(4)] for _ in range(mt_n)]
+        for ks in range(ks_n):
+            for nt in range(4):
+                b_lane = s_f[4 * ks + fc, 8 * nt + fr]
+                for mt in range(mt_n):
+                    a_lane = table[(frag0 + mt * ks_n + ks) * 32 + lanes]
+                    _dmma(acc[mt][nt], a_lane, b_lane)
+        return acc
+
+    def store_rows(acc, mt_n, scale=None):
+        for mt in range(mt_n):
+            for l in range(32):
+                i = 8 * mt + fr[l]
+                if i >= qrows:
+                    continue
+                for nt in range(4):
+                    e0 = 8 * nt + 2 * fc[l]
+                    for cc in range(2):
+                        val = acc[mt][nt][l, cc]
+                        if scale is not None:
+                            val = scale(i, e0 + cc, val)
+                        s_f[i, e0 + cc] = val
+
+    c1 = product(0, m1, k1)
+    store_rows(c1, m1, lambda i, e, val: val * mooj[e])
+    c3 = product(m1 * k1, m3, k3)
+    store_rows(c3, m3, lambda i, e, val: val * ((mf[i] if 1 <= i < ni else 0.0) * oma[e]) if i >= 1 else val)
+    c4 = product(m1 * k1 + m3 * k3, m3, k3)
+    got = np.zeros((ni, E))
+    for mt in range(m3):
+        for l in range(32):
+            i = 8 * mt + fr[l]
+            if i < ni:
+                for nt in range(4):
+                    e0 = 8 * nt + 2 * fc[l]
+                    got[i, e0] = c4[mt][nt][l, 0]
+                    got[i, e0 + 1] = c4[mt][nt][l, 1]
+    assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
