@@ -14,7 +14,8 @@
 //      for 8 elements (k = RT point, n = element), read from the same stride-36 shared-memory rows as k_elem_mma.
 // CTA = 32 elements x 8 warps; warp = (conserved variable, 16-element half of the tile).  The metric combination,
 // the Epsilon product (Bary . vertex eps, InterpolateEpsilonSigma dissipation.go:219-242) and the 128-bit stores of
-// DissX / DissY happen in the accumulator fragment layout.  Opt-in until measured: DFR2D_GRAD_KERNEL=2.
+// DissX / DissY happen in the accumulator fragment layout.  DFR2D_GRAD_KERNEL=2; measured 3.52 ms against 3.86 ms of the
+// DFMA kernel (k_edge + gradient, 2M triangles, N=4) -- the pipelined k_grad_pipe below (2.74 ms) is the default for N >= 2.
 #pragma once
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
@@ -203,7 +204,7 @@ template <int N> void build_grad_table(const double *Div, const double *Bary, st
 // ------------------------------------------------------------------------------------------------------------------
 // k_grad_pipe<N> (DFR2D_GRAD_KERNEL=3): k_grad_mma as a persistent, software-pipelined kernel.
 //
-// Measured on B200 (profiles/r01l_grad_ab.json): k_grad_mma is only 10 % faster than the DFMA kernel although its
+// Measured on B200 (profiles/r01l_grad_ab_k_grad_vs_k_grad_mma.json): k_grad_mma is only 10 % faster than the DFMA kernel although its
 // tensor-pipe floor is ~1 ms for 2M elements at N=4 -- a CTA loads its tile (three dependent global loads deep:
 // etoe -> edge table -> Q_Face), synchronises, computes, stores; nothing overlaps and the operator table is re-read
 // from L2 by every 32-element tile.  Here one CTA per SM holds the table for its lifetime and runs two independent
