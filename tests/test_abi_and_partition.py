@@ -48,11 +48,21 @@ def test_create_rejects_bad_requests_without_touching_cuda():
         lib.Dfr2d(c.problem)
 
 
-@pytest.mark.parametrize("mesh_name,n_parts", [("grid", 2), ("grid", 3), ("grid", 8), ("naca", 2), ("naca", 5)])
+def _shuffled_grid(seed):
+    """A structured grid whose elements are renumbered at random: contiguous Split1D ranges are then scattered in
+    space, so almost every edge is cut and vertices are shared by many partitions (the worst case for the halo lists)."""
+    from gocfd_b200.host import readfiles as rf
+    m = structured_tri_mesh(7, 5)
+    return rf.renumber_elements(m, np.random.default_rng(seed).permutation(m.K))
+
+
+@pytest.mark.parametrize("mesh_name,n_parts", [("grid", 2), ("grid", 3), ("grid", 8), ("naca", 2), ("naca", 5),
+                                               ("shuffled", 2), ("shuffled", 5), ("shuffled", 9)])
 def test_partition_plan_tables(mesh_name, n_parts):
     from gocfd_b200 import lib
-    mesh = structured_tri_mesh(12, 10) if mesh_name == "grid" else mesh_path("mesh_NACA0012_inv.su2")
-    c = _case(1, mesh, InitType="IVortex" if mesh_name == "grid" else "Freestream")
+    mesh = {"grid": lambda: structured_tri_mesh(12, 10), "naca": lambda: mesh_path("mesh_NACA0012_inv.su2"),
+            "shuffled": lambda: _shuffled_grid(n_parts)}[mesh_name]()
+    c = _case(1, mesh, InitType="Freestream" if mesh_name == "naca" else "IVortex")
     p = c.problem
     pm = PartitionMap(n_parts, p.K)
     plans = [lib.Plan(p, n_parts, r) for r in range(n_parts)]
@@ -137,7 +147,8 @@ def test_two_rank_gloo_exchange():
         assert "OK" in out, out
 
 
-@pytest.mark.parametrize("mesh_name,n_parts", [("sod", 2), ("sod", 3), ("naca", 5), ("naca", 8)])
+@pytest.mark.parametrize("mesh_name,n_parts", [("sod", 2), ("sod", 3), ("naca", 5), ("naca", 8), ("shuffled", 4),
+                                               ("shuffled", 7)])
 def test_shared_vertex_plan_reproduces_the_global_vertex_max(mesh_name, n_parts):
     """Dissipation across partitions: the per-peer shared-vertex lists are exactly the pairwise
     intersections of the partitions' vertex sets, both sides agree on the order, and local max + exchange + max equals
@@ -145,6 +156,8 @@ def test_shared_vertex_plan_reproduces_the_global_vertex_max(mesh_name, n_parts)
     from gocfd_b200 import lib
     if mesh_name == "sod":
         c = _case(2, mesh_path("sod-aligned-100pts.su2"), InitType="shocktube", Limiter="persson c0", Kappa=5.0)
+    elif mesh_name == "shuffled":       # every vertex shared by several scattered partitions
+        c = _case(2, _shuffled_grid(n_parts), InitType="IVortex", Limiter="PerssonC0")
     else:
         c = _case(2, mesh_path("mesh_NACA0012_inv.su2"), InitType="Freestream", Minf=0.8, Limiter="PerssonC0")
     p = c.problem
