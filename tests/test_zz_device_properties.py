@@ -107,3 +107,40 @@ def test_naca_front_local_dt_active_dissipation_on_device(diss_elem, monkeypatch
     assert np.linalg.norm(dev.get_state() - ora.get_state()) / den < 1e-11
     np.testing.assert_allclose(dev.get_field(0), ora.DT, rtol=1e-10)
     dev.close()
+
+
+@pytest.mark.parametrize("diss", [False, True])
+def test_scattered_partitions_on_device(diss):
+    """Elements renumbered at random, 5 partitions: contiguous Split1D ranges are scattered in space, so almost every edge
+    is cut and every partition is mostly halo -- the worst case for the ghost columns / halo lists the kernels consume
+    (their integer tables are checked bit-exactly on the CPU, tests/test_abi_and_partition.py).  Must equal the
+    single-partition device run bitwise and the oracle to 1e-11."""
+    from test_abi_and_partition import _shuffled_grid
+    from test_gpu_parity import _multi_partition_step
+    from gocfd_b200 import lib
+    from oracle.euler2d_oracle import OracleSolver
+    kw = dict(PolynomialOrder=2, InitType="IVortex", CFL=1.0, FinalTime=50.0)
+    if diss:
+        kw.update(Limiter="PerssonC0", Kappa=5.0)
+    c = make(kw, _shuffled_grid(5))
+    if diss:        # sharpen the vortex core so that the sensor fires somewhere
+        c.Q[0] *= 1.0 + 0.3 * np.sign(np.sin(7.0 * c.DFR.solution_xy()[0]))
+    devs = [lib.Dfr2d(c.problem, n_parts=5, part=r) for r in range(5)]
+    for d in devs:
+        d.set_state(c.Q)
+    _multi_partition_step(devs, 3)
+    q = np.zeros_like(c.Q)
+    for d in devs:
+        d.get_state(q)
+    one = lib.Dfr2d(c.problem)
+    one.set_state(c.Q)
+    one.step(3)
+    assert np.array_equal(q, one.get_state())
+    ora = OracleSolver(c.problem)
+    ora.set_state(c.Q)
+    ora.step(3)
+    if diss:
+        assert ora.SigmaScalar.max() > 0.02
+    assert np.linalg.norm(q - ora.get_state()) / np.linalg.norm(ora.get_state()) < 1e-11
+    for d in devs + [one]:
+        d.close()
