@@ -151,3 +151,33 @@ def test_solve_writes_output_final(tmp_path):
     vals = np.array([[float(v) for v in r.split("\t")] for r in rows[2:]])
     assert vals[0, 1] == pytest.approx(1.0, abs=1e-6) and vals[-1, 1] == pytest.approx(0.125, abs=1e-6)
     assert (tmp_path / "shocktube_analytic.dat").exists()
+
+
+def test_solve_progress_lines_follow_the_reference_format():
+    """PrintInitialization / PrintUpdate / PrintFinal (euler.go:802-862): header, "%8d%8.5f%8.5f" + six "%11.4e" columns
+    (Res0..3 as max(0, signed max), L1 = max, L2 = sqrt(sum sq)/4), and the rate line."""
+    import re
+    from oracle.euler2d_oracle import OracleSolver
+    from gocfd_b200.host.meshgen import structured_tri_mesh
+    ip = InputParameters2D(CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=1, FinalTime=100.0,
+                           MaxIterations=3, Gamma=1.4, Minf=0.1)
+    c = Euler(ip, structured_tri_mesh(6, 6, tag="wall"))
+    lines = []
+    c.Solve(OracleSolver(c.problem), out=lines.append)
+    assert lines[0].splitlines()[0] == "Solving until finaltime = 100.00000"
+    assert lines[0].splitlines()[1] == "    iter    time      dt       Res0       Res1       Res2       Res3         L1         L2"
+    upd = [ln for ln in lines[1:] if re.match(r"^\s+\d+ ", ln)]
+    assert len(upd) >= 2                                  # step 1 and the final step
+    first = upd[0]
+    assert re.fullmatch(r"\s{7}1\s+\d\.\d{5}\s*\d\.\d{5}(\s+\d\.\d{4}e[+-]\d\d){6}", first), first
+    cols = [float(x) for x in first.split()[3:]]
+    assert cols[4] == pytest.approx(max(cols[:4]), rel=1e-3)
+    assert cols[5] == pytest.approx(np.sqrt(sum(v * v for v in cols[:4])) / 4.0, rel=1e-3)
+    assert re.search(r"Rate of execution =\s+\d+\.\d{5} us/\(element\*iteration\) over 3 iterations", lines[-1])
+    # local time stepping prints the iteration only (euler.go:816-817)
+    ip.LocalTimeStepping = True
+    c = Euler(ip, structured_tri_mesh(6, 6, tag="wall"))
+    lines = []
+    c.Solve(OracleSolver(c.problem), out=lines.append)
+    assert lines[0].startswith("Solving until Max Iterations = 3\n    iter                ")
+    assert lines[1].startswith("         1              ")
