@@ -181,3 +181,44 @@ def test_solve_progress_lines_follow_the_reference_format():
     c.Solve(OracleSolver(c.problem), out=lines.append)
     assert lines[0].startswith("Solving until Max Iterations = 3\n    iter                ")
     assert lines[1].startswith("         1              ")
+
+
+def test_c1_run_script_configuration_end_to_end(tmp_path):
+    """Config C1 exactly as the reference's run script builds it (test_cases/Euler2D/SU2-naca12/runme.sh:7-13):
+    input-base.yaml with the overrides appended, so PolynomialOrder / CFL / MaxIterations appear twice and the last
+    one wins; then a (shortened) run and OutputFinal's wall plot file with "mach" and "pressure coefficient"."""
+    from oracle.c_oracle import COracleSolver
+    base = """Title: "Test Case"
+FluxType: Roe
+InitType: Freestream # Can be "Freestream" or "IVortex"
+FinalTime: 20
+Gamma: 1.4
+LocalTimeStepping: true
+Limiter: PerssonC0
+Kappa: 4.5
+PlotFields: ["mach", "pressure coefficient"]
+PolynomialOrder: 4
+CFL: 5
+Minf: 0.8
+Alpha: 1.25
+MaxIterations: 50000
+"""
+    doc = base + "PolynomialOrder: 0\nCFL: 2.0\nMaxIterations: 2000\n"
+    ip = InputParameters2D(Gamma=1.4, Minf=0.1).parse(doc)
+    assert (ip.PolynomialOrder, ip.CFL, ip.MaxIterations) == (0, 2.0, 2000)
+    assert ip.LocalTimeStepping is True and ip.Limiter == "PerssonC0" and ip.Kappa == 4.5 and ip.Alpha == 1.25
+    assert ip.PlotFields == ["mach", "pressure coefficient"]
+    assert [of.best_match_flow_function(f) for f in ip.PlotFields] == [(4, True), (7, True)]
+    ip.MaxIterations = 20                      # shortened run
+    c = Euler(ip, mesh_path("mesh_NACA0012_inv.su2"))
+    assert not c.Dissipation                   # N == 0 disables the limiter (euler.go:110)
+    lines = []
+    steps, _ = c.Solve(COracleSolver(c.problem), out=lines.append, output_dir=str(tmp_path))
+    assert steps == 20
+    assert lines[-1] == "Output plot data for wall, dimensions: 200 Wall edges by 1 points each"
+    rows = [[float(v) for v in ln.rstrip(",").split(",")] for ln in open(tmp_path / "plotfile.dat").read().splitlines()]
+    a = np.array(rows)
+    assert a.shape == (200, 4)
+    # Mach along the wall after 20 iterations from M = 0.8: a stagnation region at the nose, ~0.8 elsewhere
+    assert 0.0 <= a[:, 2].min() < 0.3 and a[:, 2].max() < 1.6 and 0.6 < np.median(a[:, 2]) < 1.0
+    assert np.isfinite(a).all()
