@@ -225,10 +225,11 @@ def roe_er_flux(gamma, ql, qr, nx, ny):
     uef = 0.05 * c
     du, dv = (u_r - u_l), (v_r - v_l)
     delta_v2 = du * du + dv * dv
-    oovmag = 1.0 / np.sqrt(u * u + v * v)
-    small = delta_v2 < 0.01 * c2
-    n1x = np.where(small, nx, oovmag * du)
-    n1y = np.where(small, ny, oovmag * dv)
+    with np.errstate(divide="ignore", invalid="ignore"):     # u = v = 0 (tube at rest): the `small` branch is taken
+        oovmag = 1.0 / np.sqrt(u * u + v * v)
+        small = delta_v2 < 0.01 * c2
+        n1x = np.where(small, nx, oovmag * du)
+        n1y = np.where(small, ny, oovmag * dv)
     n2x, n2y = n1y * (nx * n1y - n1x * ny), -n1x * (nx * n1y - n1x * ny)
     alp1, alp2 = nx * n1x + ny * n1y, nx * n2x + ny * n2y
     u1x, u1y = n1x * u, n1y * v

@@ -154,3 +154,19 @@ def test_naca_front_local_dt_active_dissipation():
     assert (b.DTVisc > 1e-9).sum() > 100           # the viscous branch of CalculateLocalDT was taken
     assert rel_l2(a.get_state(), b.get_state()) < TOL
     np.testing.assert_allclose(a.residual(), b.residual(), rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("flux", ["Roe", "Lax", "roe-er", "average"])
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_dissipation_matrix_fluxes_orders_dt_modes(n, flux, local):
+    """Every flux x order x {global, local} dt with an active sensor on the Sod mesh (In / Out / Wall boundaries), 2 RK
+    steps: the two restatements were written independently (numpy, vectorised; C, following the Go data flow) and must
+    agree to round-off -- measured worst case 6e-14 (N=1), 6e-16 otherwise."""
+    c = _sod(n, FluxType=flux, LocalTimeStepping=local, MaxIterations=1000)
+    q = _smeared(c, 0.004 if n == 1 else 0.002)
+    a, b = pair(c)
+    a.set_state(q), b.set_state(q)
+    a.step(2), b.step(2)
+    assert np.isfinite(b.get_state()).all()
+    assert rel_l2(a.get_state(), b.get_state()) < (1e-11 if n == 1 else 1e-13)
