@@ -144,3 +144,26 @@ def test_scattered_partitions_on_device(diss):
     assert np.linalg.norm(q - ora.get_state()) / np.linalg.norm(ora.get_state()) < 1e-11
     for d in devs + [one]:
         d.close()
+
+
+@pytest.mark.parametrize("local", [False, True])
+@pytest.mark.parametrize("flux", ["Roe", "Lax", "roe-er", "average"])
+def test_dissipation_flux_and_dt_matrix_on_device(flux, local):
+    """The PerssonC0 path with every numerical flux and both dt modes on the Sod mesh at N=2 (the GPU dissipation tests
+    of test_gpu_parity.py all use Roe + global dt).  The tube starts at rest, which puts Roe-ER on its u = v = 0 branch
+    (1/|V| is infinite and must not leak through the select, fluxes.go:440-450)."""
+    from conftest import mesh_path
+    from gocfd_b200 import lib
+    from oracle.euler2d_oracle import OracleSolver
+    c = make(dict(PolynomialOrder=2, InitType="shocktube", CFL=1.0, FinalTime=0.2, Limiter="persson c0", Kappa=5.0,
+                  FluxType=flux, LocalTimeStepping=local, MaxIterations=1000), mesh_path("sod-aligned-100pts.su2"))
+    x, _ = c.DFR.solution_xy()
+    w = 0.5 * (1.0 - np.tanh((x - 0.503) / 0.002))
+    q = np.stack([c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w for v in range(4)])
+    dev, ora = lib.Dfr2d(c.problem), OracleSolver(c.problem)
+    dev.set_state(q)
+    ora.set_state(q)
+    dev.step(2), ora.step(2)
+    assert ora.SigmaScalar.max() > 0.05 and np.isfinite(ora.get_state()).all()
+    assert np.linalg.norm(dev.get_state() - ora.get_state()) / np.linalg.norm(ora.get_state()) < 1e-11
+    dev.close()
