@@ -28,3 +28,12 @@ def test_algorithmic_bytes_match_the_survey_formulas():
     assert total == 3960.0 and abs(elem + edge - total) < 1e-9          # B_inv(4) = 3,960 B
     assert round(bench.algorithmic_bytes(2)[0], 1) == 2193.6             # B_inv(2) = 2,194 B
     assert bench.algorithmic_bytes_visc(4) == 10248.0                    # B_visc(4) = 10,248 B
+
+
+def test_cpu_arm_covers_the_dissipation_workload():
+    """The CPU arm of the shock-capturing workload (c3): the C port's PerssonC0 path on a bounded 4:1 Sod tube sample."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.cpu_run(2, steps=1, warmup=1, nx=80, dissipation=True)
+    assert r["kind"] == "port" and r["value"] > 0 and r["cores"] >= 1
+    assert "PerssonC0" in r["sample"] and "80x20x2=3200 triangles" in r["sample"]
