@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -33,6 +34,7 @@ struct dfr2d_handle {
     std::string err;
     std::vector<void *> allocs;
     std::vector<double> opsHost;      // Ops<N> image for constant memory
+    uint64_t opsFp = 0;               // fingerprint of opsHost (which table is resident on the device)
     // state
     double *q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // q[4] aliases q[1] (Q1 is dead after stage 1)
     double *R = nullptr, *qface = nullptr, *eflux = nullptr, *agg = nullptr, *DT = nullptr, *rhsScratch = nullptr;
@@ -83,6 +85,8 @@ struct dfr2d_handle {
     int pipeOcc[3] = {0, 0, 0};
     int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
     int edgePPT = 0;
+    void *scratch = nullptr;          // call-spanning scratch of residual / plot_field / init_state / rhs (scratch_reserve)
+    size_t scratchBytes = 0;
 };
 
 #define CK(call)                                                                                        \
@@ -152,15 +156,47 @@ template <int N> static void pack_ops(const dfr2d_problem *p, std::vector<double
     cp(&o->Div[0][0], p->Div, (size_t)NF * NF);
 }
 
-// One operator set is resident in constant memory at a time; re-upload when another handle's set
-// was active (stream ordered).  Concurrent handles with different operators on different streams
-// are not supported (documented in DESIGN.md).
-static const dfr2d_handle *g_ops_owner = nullptr;
+// The operator tables live in __constant__ memory, which exists once per DEVICE.  Per device we remember a
+// fingerprint of the resident table, the stream that uploaded it and an event behind the upload:
+//   - same table, same stream: nothing to do (the common case: every partition of a run has the same operators);
+//   - same table, other stream: that stream waits for the upload event (free once it has completed);
+//   - another table (handles of different order interleaved on one device): the device is drained first, because kernels
+//     of other streams may still be reading the old table, then the new one is uploaded.
+// Every stage_* entry calls this, so the stage API is safe for any interleaving of handles.
+struct OpsResident {
+    uint64_t fp = 0;
+    bool valid = false;
+    cudaStream_t stream = 0;
+    cudaEvent_t ev = nullptr;
+};
+static std::mutex g_ops_mutex;
+static std::unordered_map<int, OpsResident> g_ops_resident;
+
+static uint64_t ops_fingerprint(const std::vector<double> &v) {
+    uint64_t hsh = 1469598103934665603ull;               // FNV-1a over the bit patterns
+    for (double d : v) {
+        uint64_t b;
+        memcpy(&b, &d, sizeof(b));
+        hsh = (hsh ^ b) * 1099511628211ull;
+    }
+    return hsh ? hsh : 1;
+}
+
 static int ensure_ops(dfr2d_handle *h) {
-    if (g_ops_owner == h) return 0;
+    std::lock_guard<std::mutex> lock(g_ops_mutex);
+    OpsResident &r = g_ops_resident[h->device];
+    if (r.valid && r.fp == h->opsFp) {
+        if (r.stream != h->stream) CK(cudaStreamWaitEvent(h->stream, r.ev, 0));
+        return 0;
+    }
+    if (r.valid) CK(cudaDeviceSynchronize());
+    if (!r.ev) CK(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
     CK(cudaMemcpyToSymbolAsync(c_ops_raw, h->opsHost.data(), kOpsDoubles * sizeof(double), 0, cudaMemcpyHostToDevice,
                                h->stream));
-    g_ops_owner = h;
+    CK(cudaEventRecord(r.ev, h->stream));
+    r.fp = h->opsFp;
+    r.stream = h->stream;
+    r.valid = true;
     return 0;
 }
 
@@ -173,8 +209,8 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
     if (h->evXchg) cudaEventDestroy(h->evXchg);
     if (h->evWave) cudaEventDestroy(h->evWave);
     for (void *p : h->allocs) cudaFree(p);
+    if (h->scratch) cudaFree(h->scratch);
     if (h->scHost) cudaFreeHost(h->scHost);
-    if (g_ops_owner == h) g_ops_owner = nullptr;
     delete h;
 }
 
@@ -417,6 +453,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         case 3: pack_ops<3>(p, h->opsHost); break;
         default: pack_ops<4>(p, h->opsHost); break;
     }
+    h->opsFp = ops_fingerprint(h->opsHost);
     // physics block
     Phys &ph = h->ph;
     ph.gamma = p->FSFar.Gamma;
@@ -1084,6 +1121,7 @@ static int stage_prepare(dfr2d_handle *h, int rk) {
 // waiting for it (north star: halo transfer overlapped with interior work); optional -- stage_edges catches up
 static int stage_edges_interior(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
     if (h->interiorDone || !h->edgeSplit) return 0;
     if (int rc = run_edges(h, rk, 1)) return rc;
     h->interiorDone = true;
@@ -1092,6 +1130,7 @@ static int stage_edges_interior(dfr2d_handle *h, int rk) {
 
 static int stage_edges(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
     if (int rc = run_unpack(h)) return rc;
     if (int rc = run_edges(h, rk, h->interiorDone ? 2 : 3)) return rc;
     h->interiorDone = false;
@@ -1106,12 +1145,14 @@ static int stage_visc(dfr2d_handle *h, int rk) {
     (void)rk;
     if (!h->ph.dissipation) return 0;
     CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
     if (int rc = run_unpack_diss(h)) return rc;
     return run_diss_visc(h);
 }
 
 static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
     CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
     const bool fuse = (rhsOut == nullptr) && !h->ph.dissipation;
     if (int rc = run_elem(h, rk, rhsOut, fuse)) return rc;
     if (rhsOut == nullptr) {
@@ -1316,12 +1357,51 @@ extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step
     return rc;
 }
 
+// Scratch that outlives a call: grown on demand, freed with the handle (no cudaMalloc/cudaFree -- and the implicit device
+// synchronisation they bring -- on calls the host makes every few steps).
+static int scratch_reserve(dfr2d_handle *h, size_t bytes) {
+    if (bytes <= h->scratchBytes) return 0;
+    if (h->scratch) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaFree(h->scratch));
+        h->scratch = nullptr;
+        h->scratchBytes = 0;
+    }
+    bytes = (bytes + 255) & ~(size_t)255;
+    CK(cudaMalloc(&h->scratch, bytes));
+    h->scratchBytes = bytes;
+    return 0;
+}
+
 extern "C" int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out) {
     if (!h || !RHS_out || rk < 0 || rk > 4) return 1;
     if (h->nParts > 1) { h->err = "dfr2d_rhs is a single-partition test hook"; return 1; }
     CK(cudaSetDevice(h->device));
+    const size_t regBytes = (size_t)4 * h->NpInt * h->Kp * sizeof(double);
     if (!h->rhsScratch) {
         if (int rc = dev_alloc(h, &h->rhsScratch, (size_t)4 * h->NpInt * h->Kp)) return rc;
+    }
+    // once CheckIfFinished holds every launch is a no-op: report that instead of copying out stale scratch
+    if (h->stepIndex >= 1) {
+        dfr2d_step_info fin{};
+        if (int rc = dfr2d_step_finish(h, &fin)) return rc;
+        if (fin.finished || h->stepIndex >= (long long)h->ph.maxIter) {
+            h->err = "dfr2d_rhs: the run has finished (FinalTime or MaxIterations reached); no RHS is evaluated";
+            return 1;
+        }
+    }
+    CK(cudaMemsetAsync(h->rhsScratch, 0, regBytes, h->stream));
+    // the hook must not leak its wave-speed maxima into the next real stage: the edge kernels atomicMax into
+    // wave[stageCounter & 1] and the rhsOut path of the element kernel returns before that slot is reset
+    unsigned long long *slot = &h->sc->wave[h->stageCounter & 1][0];
+    CK(cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned long long), h->stream));
+    // with the limiter, stage 2 filters its input register in place (euler.go:605-609); the hook evaluates it on the
+    // caller's register like the reference would, then puts the unfiltered register back ("without advancing")
+    double *saved = nullptr;
+    if (h->ph.dissipation && rk == 2) {
+        if (int rc = scratch_reserve(h, regBytes)) return rc;
+        saved = (double *)h->scratch;
+        CK(cudaMemcpyAsync(saved, h->q[rk], regBytes, cudaMemcpyDeviceToDevice, h->stream));
     }
     h->qfaceValid = false;
     if (int rc = stage_sensor(h, rk)) return rc;
@@ -1330,23 +1410,21 @@ extern "C" int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out) {
     if (int rc = stage_visc(h, rk)) return rc;
     if (int rc = stage_update(h, rk, h->rhsScratch)) return rc;
     h->qfaceValid = false;
+    CK(cudaMemsetAsync(slot, 0, 2 * sizeof(unsigned long long), h->stream));
+    if (saved) CK(cudaMemcpyAsync(h->q[rk], saved, regBytes, cudaMemcpyDeviceToDevice, h->stream));
     return copy_out(h, h->rhsScratch, RHS_out);
 }
 
 extern "C" int dfr2d_residual(dfr2d_handle *h, double maxR[4]) {
     if (!h || !maxR) return 1;
     CK(cudaSetDevice(h->device));
-    double *tmp = nullptr;
-    CK(cudaMalloc(&tmp, 4 * sizeof(double)));
+    if (int rc = scratch_reserve(h, 4 * sizeof(double))) return rc;
+    double *tmp = (double *)h->scratch;
     k_signed_max<<<4, 1024, 0, h->stream>>>(h->R, h->NpInt, h->K, h->Kp, tmp);
-    int rc = launch_check(h, "k_signed_max");
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(maxR, tmp, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
-    }
-    cudaFree(tmp);
-    return rc;
+    if (int rc = launch_check(h, "k_signed_max")) return rc;
+    CK(cudaMemcpyAsync(maxR, tmp, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 extern "C" int dfr2d_get_field(dfr2d_handle *h, int which, double *out) {
@@ -1371,30 +1449,25 @@ extern "C" int dfr2d_init_state(dfr2d_handle *h, int init_case, int64_t nv, cons
     if (!h || !VX || !VY || !EToV || !R || !S || nv <= 0) return 1;
     if (init_case < DFR2D_CASE_Freestream || init_case > DFR2D_CASE_ShockTube) { h->err = "unknown case type"; return 1; }
     CK(cudaSetDevice(h->device));
-    double *vx = nullptr, *vy = nullptr, *rs = nullptr;
-    int *etov = nullptr;
-    int rc = 0;
-    cudaError_t e = cudaMalloc(&vx, (size_t)nv * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&vy, (size_t)nv * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&rs, (size_t)2 * h->NpInt * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&etov, (size_t)3 * std::max(h->K, 1) * sizeof(int));
-    if (e == cudaSuccess) e = cudaMemcpyAsync(vx, VX, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(vy, VY, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rs, R, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(rs + h->NpInt, S, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(etov, EToV + 3 * h->k0, (size_t)3 * h->K * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        InitArgs ia{};
-        ia.K = h->K; ia.Kp = h->Kp; ia.npInt = h->NpInt; ia.initCase = init_case;
-        ia.vx = vx; ia.vy = vy; ia.etov = etov; ia.r = rs; ia.s = rs + h->NpInt; ia.q = h->q[0]; ia.ph = h->ph;
-        k_init_state<<<(h->K + 127) / 128, 128, 0, h->stream>>>(ia);
-        rc = launch_check(h, "k_init_state");
-        if (!rc) e = cudaStreamSynchronize(h->stream);
-        h->qfaceValid = false;
-    }
-    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
-    cudaFree(vx); cudaFree(vy); cudaFree(rs); cudaFree(etov);
-    return rc;
+    // one scratch block: vx | vy | r,s | etov
+    const size_t oVy = (size_t)nv, oRs = 2 * (size_t)nv, oEt = oRs + 2 * (size_t)h->NpInt;
+    const size_t bytes = oEt * sizeof(double) + (size_t)3 * std::max(h->K, 1) * sizeof(int);
+    if (int rc = scratch_reserve(h, bytes)) return rc;
+    double *vx = (double *)h->scratch, *vy = vx + oVy, *rs = vx + oRs;
+    int *etov = (int *)(vx + oEt);
+    CK(cudaMemcpyAsync(vx, VX, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(vy, VY, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(rs, R, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(rs + h->NpInt, S, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(etov, EToV + 3 * h->k0, (size_t)3 * h->K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    InitArgs ia{};
+    ia.K = h->K; ia.Kp = h->Kp; ia.npInt = h->NpInt; ia.initCase = init_case;
+    ia.vx = vx; ia.vy = vy; ia.etov = etov; ia.r = rs; ia.s = rs + h->NpInt; ia.q = h->q[0]; ia.ph = h->ph;
+    k_init_state<<<(h->K + 127) / 128, 128, 0, h->stream>>>(ia);
+    if (int rc = launch_check(h, "k_init_state")) return rc;
+    h->qfaceValid = false;
+    CK(cudaStreamSynchronize(h->stream));       // the host arrays are only valid during the call (cgo pointer rules)
+    return 0;
 }
 
 extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_interp, int np_graph, float *out) {
@@ -1406,37 +1479,27 @@ extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double
         return 1;
     }
     CK(cudaSetDevice(h->device));
-    double *gi = nullptr;
-    float *dout = nullptr;
     const size_t nOut = (size_t)h->K * NG;
-    CK(cudaMalloc(&gi, (size_t)NG * h->NpInt * sizeof(double)));
-    cudaError_t e = cudaMalloc(&dout, std::max<size_t>(nOut, 1) * sizeof(float));
-    if (e != cudaSuccess) { cudaFree(gi); h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return 2; }
-    int rc = 0;
-    e = cudaMemcpyAsync(gi, graph_interp, (size_t)NG * h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
-    if (e == cudaSuccess) {
-        PlotArgs pa{};
-        pa.K = h->K; pa.Kp = h->Kp; pa.ff = flow_function;
-        pa.q = h->q[0]; pa.gi = gi; pa.out = dout;
-        pa.gamma = h->ph.fs[0].Gamma; pa.Pinf = h->ph.fs[0].Pinf; pa.QQinf = h->ph.fs[0].QQinf;
-        const int blocks = (h->K + kPlotThreads - 1) / kPlotThreads;
-        DISPATCH_N(h->N, (k_plot_field<NN><<<blocks, kPlotThreads, 0, h->stream>>>(pa)));
-        rc = launch_check(h, "k_plot_field");
-        if (!rc) {
-            e = cudaMemcpyAsync(out + (size_t)h->k0 * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        }
-    }
-    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = 2; }
-    cudaFree(gi);
-    cudaFree(dout);
-    return rc;
+    const size_t giBytes = ((size_t)NG * h->NpInt * sizeof(double) + 255) & ~(size_t)255;
+    if (int rc = scratch_reserve(h, giBytes + std::max<size_t>(nOut, 1) * sizeof(float))) return rc;
+    double *gi = (double *)h->scratch;
+    float *dout = (float *)((char *)h->scratch + giBytes);
+    CK(cudaMemcpyAsync(gi, graph_interp, (size_t)NG * h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    PlotArgs pa{};
+    pa.K = h->K; pa.Kp = h->Kp; pa.ff = flow_function;
+    pa.q = h->q[0]; pa.gi = gi; pa.out = dout;
+    pa.gamma = h->ph.fs[0].Gamma; pa.Pinf = h->ph.fs[0].Pinf; pa.QQinf = h->ph.fs[0].QQinf;
+    const int blocks = (h->K + kPlotThreads - 1) / kPlotThreads;
+    DISPATCH_N(h->N, (k_plot_field<NN><<<blocks, kPlotThreads, 0, h->stream>>>(pa)));
+    if (int rc = launch_check(h, "k_plot_field")) return rc;
+    CK(cudaMemcpyAsync(out + (size_t)h->k0 * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 extern "C" int dfr2d_set_stream(dfr2d_handle *h, void *s) {
     if (!h) return 1;
     h->stream = (cudaStream_t)s;
-    if (g_ops_owner == h) g_ops_owner = nullptr;     // re-upload on the new stream's order
     return 0;
 }
 extern "C" int dfr2d_partition_range(const dfr2d_handle *h, int64_t *b, int64_t *e) {

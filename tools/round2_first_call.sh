@@ -8,6 +8,8 @@
 tag=${1:-r02a}
 o=gpurun_out
 mkdir -p $o
+{ echo "go: $(command -v go || echo absent)"; go version 2>&1; ls -d /usr/local/go /usr/lib/go* 2>&1; echo "nsys: $(command -v nsys || echo absent)"; nproc; grep -m1 'model name' /proc/cpuinfo; free -g | head -2; nvidia-smi --query-gpu=name,memory.total --format=csv; } > $o/${tag}_box_probe.txt 2>&1
+cat $o/${tag}_box_probe.txt
 # fragment layouts of mma.sync f64 (m8n8k4 as used everywhere, m16n8k8 as assumed for the next gradient kernel)
 (cd tools/exp && { [ -x dmma_layout ] || nvcc -gencode arch=compute_100a,code=sm_100a -o dmma_layout dmma_layout.cu; } && ./dmma_layout) | tee $o/${tag}_dmma_layout.txt
 DFR2D_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q > $o/${tag}_pytest_all.log 2>&1; echo "pytest rc=$?"
