@@ -9,6 +9,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <unistd.h>
 
 #include "dfr2d_kernels.cuh"
 #include "dfr2d_diss_kernels.cuh"
@@ -64,7 +65,6 @@ struct dfr2d_handle {
     DevScalars *scHost = nullptr;     // pinned
     long long stageCounter = 0, stepIndex = 0, launches = 0;
     bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
-    cudaEvent_t evXchg = nullptr, evWave = nullptr;   // dfr2d_multi_step: "my sends are posted", "my edge phase is done"
     bool interiorDone = false;        // the interior-edge kernel of the stage in flight has been launched (overlap with the halo)
     int edgeBlocks = 0;
     bool smemAttrSet = false;
@@ -85,6 +85,17 @@ struct dfr2d_handle {
     int pipeOcc[3] = {0, 0, 0};
     int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
     int edgePPT = 0;
+    // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
+    // single IPC handle / peer pointer gives a partner everything it writes
+    unsigned long long *mailbox = nullptr;
+    size_t mailboxWords = 0;
+    int64_t mbOff[3] = {0, 0, 0}, mbFlags = 0, mbWaveFlag = 0, mbWaveIn = 0;     // word offsets inside the mailbox
+    bool connected = false;
+    PutTab *putTab[3] = {nullptr, nullptr, nullptr};      // device
+    WaitTab *waitTab[3] = {nullptr, nullptr, nullptr};    // device
+    unsigned int *putDone = nullptr;                      // device [3]
+    WaveTab waveTab{};
+    std::vector<void *> ipcMapped;
     void *scratch = nullptr;          // call-spanning scratch of residual / plot_field / init_state / rhs (scratch_reserve)
     size_t scratchBytes = 0;
 };
@@ -206,8 +217,7 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    if (h->evXchg) cudaEventDestroy(h->evXchg);
-    if (h->evWave) cudaEventDestroy(h->evWave);
+    for (void *p : h->ipcMapped) cudaIpcCloseMemHandle(p);
     for (void *p : h->allocs) cudaFree(p);
     if (h->scratch) cudaFree(h->scratch);
     if (h->scHost) cudaFreeHost(h->scHost);
@@ -526,8 +536,22 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (int rc = dev_upload(h, &h->bpx, bpx)) return rc;
     if (int rc = dev_upload(h, &h->bpy, bpy)) return rc;
     if (h->nParts > 1) {
+        // mailbox layout (8-byte words): [recv EDGE | recv VERTEX | recv DISS | flags[3][32] | wave flags[32] |
+        // wave inbox[32][2 slots][2]]; every region starts on a 16-word boundary
+        auto up16 = [](int64_t w) { return (w + 15) & ~(int64_t)15; };
+        const int64_t nE = h->recvTotal, nV = ph.dissipation ? 2 * (int64_t)h->nVtx : 0,
+                      nD = ph.dissipation ? (int64_t)8 * NEd * h->nRecvEdges : 0;
+        h->mbOff[DFR2D_XCHG_EDGE] = 0;
+        h->mbOff[DFR2D_XCHG_VERTEX] = up16(nE);
+        h->mbOff[DFR2D_XCHG_DISS] = h->mbOff[DFR2D_XCHG_VERTEX] + up16(nV);
+        h->mbFlags = h->mbOff[DFR2D_XCHG_DISS] + up16(nD);
+        h->mbWaveFlag = h->mbFlags + 3 * kMaxParts;
+        h->mbWaveIn = h->mbWaveFlag + kMaxParts;
+        h->mailboxWords = (size_t)(h->mbWaveIn + 4 * kMaxParts);
+        if (int rc = dev_alloc(h, &h->mailbox, h->mailboxWords)) return rc;
+        CK(cudaMemset(h->mailbox, 0, h->mailboxWords * sizeof(unsigned long long)));
+        h->recvBuf = (double *)(h->mailbox + h->mbOff[DFR2D_XCHG_EDGE]);
         if (int rc = dev_alloc(h, &h->sendBuf, (size_t)h->sendTotal)) return rc;
-        if (int rc = dev_alloc(h, &h->recvBuf, (size_t)h->recvTotal)) return rc;
         if (int rc = dev_upload(h, &h->sendElem, sendElem)) return rc;
         if (int rc = dev_upload(h, &h->sendRow0, sendRow0)) return rc;
         if (int rc = dev_upload(h, &h->recvCol, recvCol)) return rc;
@@ -567,9 +591,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
             for (int pt = 0; pt < h->nParts; pt++) h->dissCounts[pt] = (h->sendCounts[pt] / h->ePer) * 8 * NEd;
             if (int rc = dev_upload(h, &h->vtxList, pl.vtxList)) return rc;
             if (int rc = dev_alloc(h, &h->vSendBuf, (size_t)2 * h->nVtx)) return rc;
-            if (int rc = dev_alloc(h, &h->vRecvBuf, (size_t)2 * h->nVtx)) return rc;
+            h->vRecvBuf = (double *)(h->mailbox + h->mbOff[DFR2D_XCHG_VERTEX]);
             if (int rc = dev_alloc(h, &h->dSendBuf, (size_t)8 * NEd * h->nSendEdges)) return rc;
-            if (int rc = dev_alloc(h, &h->dRecvBuf, (size_t)8 * NEd * h->nRecvEdges)) return rc;
+            h->dRecvBuf = (double *)(h->mailbox + h->mbOff[DFR2D_XCHG_DISS]);
         }
         if (int rc = dev_alloc(h, &d.dissX, (size_t)4 * h->NpFlux * Kp)) return rc;
         if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * h->NpFlux * Kp)) return rc;
@@ -738,59 +762,65 @@ static int run_interp(dfr2d_handle *h, const double *reg) {
     return launch_check(h, "k_interp");
 }
 
+static unsigned long long xchg_seq(const dfr2d_handle *h) { return (unsigned long long)h->stageCounter + 1ull; }
+
 static int run_pack(dfr2d_handle *h) {
     if (h->nSendEdges == 0) return 0;
-    const int tail = h->ePer - 4 * h->NpEdge;
-    const int total = h->nSendEdges * h->ePer;
-    k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->ePer, h->NpEdge, 3 * h->NpEdge, 0, h->Kp, h->qface,
-                                                            h->sendElem, h->sendRow0, h->sendBuf, 0, tail, h->ds.etov, h->ds.epsV);
+    HaloPackArgs a{};
+    a.total = h->nSendEdges * h->ePer; a.per = h->ePer; a.npEdge = h->NpEdge; a.planeRows = 3 * h->NpEdge; a.rowBase = 0;
+    a.Kp = h->Kp; a.nTail = h->ePer - 4 * h->NpEdge;
+    a.src = h->qface; a.src2 = nullptr; a.elem = h->sendElem; a.row0 = h->sendRow0; a.etov = h->ds.etov; a.epsV = h->ds.epsV;
+    a.buf = h->sendBuf; a.put = h->connected ? h->putTab[DFR2D_XCHG_EDGE] : nullptr; a.seq = xchg_seq(h);
+    k_halo_pack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
     return launch_check(h, "k_halo_pack");
 }
 
 static int run_unpack(dfr2d_handle *h) {
     if (h->nRecvEdges == 0) return 0;
-    const int tail = h->ePer - 4 * h->NpEdge;
-    const int total = h->nRecvEdges * h->ePer;
-    k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, h->ePer, h->NpEdge, 3 * h->NpEdge, 0, h->Kp, h->qface,
-                                                              h->recvCol, h->recvRow0, h->recvBuf, 0, tail, h->K, h->NV, h->ds.epsV);
+    HaloUnpackArgs a{};
+    a.total = h->nRecvEdges * h->ePer; a.per = h->ePer; a.npEdge = h->NpEdge; a.planeRows = 3 * h->NpEdge; a.rowBase = 0;
+    a.Kp = h->Kp; a.nTail = h->ePer - 4 * h->NpEdge; a.K = h->K; a.NV = h->NV;
+    a.dst = h->qface; a.dst2 = nullptr; a.col = h->recvCol; a.row0 = h->recvRow0; a.epsV = h->ds.epsV;
+    a.buf = h->recvBuf; a.wait = h->connected ? h->waitTab[DFR2D_XCHG_EDGE] : nullptr; a.seq = xchg_seq(h);
+    k_halo_unpack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
     return launch_check(h, "k_halo_unpack");
 }
 
-// DissX / DissY edge rows of the cut edges (rows 2 NpInt + edge * NpEdge + i of the sender's element)
+// DissX then DissY edge rows of the cut edges (rows 2 NpInt + edge * NpEdge + i of the sender's element), one launch
 static int run_pack_diss(dfr2d_handle *h) {
     if (h->nSendEdges == 0) return 0;
-    const int body = 4 * h->NpEdge, total = h->nSendEdges * body;
-    for (int xy = 0; xy < 2; xy++) {
-        k_halo_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, 2 * body, h->NpEdge, h->NpFlux, 2 * h->NpInt, h->Kp,
-                                                                xy ? h->ds.dissY : h->ds.dissX, h->sendElem, h->sendRow0,
-                                                                h->dSendBuf, xy * body, 0, nullptr, nullptr);
-        if (int rc = launch_check(h, "k_halo_pack(diss)")) return rc;
-    }
-    return 0;
+    HaloPackArgs a{};
+    a.per = 8 * h->NpEdge; a.total = h->nSendEdges * a.per; a.npEdge = h->NpEdge; a.planeRows = h->NpFlux; a.rowBase = 2 * h->NpInt;
+    a.Kp = h->Kp; a.nTail = 0;
+    a.src = h->ds.dissX; a.src2 = h->ds.dissY; a.elem = h->sendElem; a.row0 = h->sendRow0; a.etov = nullptr; a.epsV = nullptr;
+    a.buf = h->dSendBuf; a.put = h->connected ? h->putTab[DFR2D_XCHG_DISS] : nullptr; a.seq = xchg_seq(h);
+    k_halo_pack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
+    return launch_check(h, "k_halo_pack(diss)");
 }
 
 static int run_unpack_diss(dfr2d_handle *h) {
     if (h->nRecvEdges == 0) return 0;
-    const int body = 4 * h->NpEdge, total = h->nRecvEdges * body;
-    for (int xy = 0; xy < 2; xy++) {
-        k_halo_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(total, 2 * body, h->NpEdge, h->NpFlux, 2 * h->NpInt, h->Kp,
-                                                                  xy ? h->ds.dissY : h->ds.dissX, h->recvCol, h->recvRow0,
-                                                                  h->dRecvBuf, xy * body, 0, h->K, h->NV, nullptr);
-        if (int rc = launch_check(h, "k_halo_unpack(diss)")) return rc;
-    }
-    return 0;
+    HaloUnpackArgs a{};
+    a.per = 8 * h->NpEdge; a.total = h->nRecvEdges * a.per; a.npEdge = h->NpEdge; a.planeRows = h->NpFlux; a.rowBase = 2 * h->NpInt;
+    a.Kp = h->Kp; a.nTail = 0; a.K = h->K; a.NV = h->NV;
+    a.dst = h->ds.dissX; a.dst2 = h->ds.dissY; a.col = h->recvCol; a.row0 = h->recvRow0; a.epsV = nullptr;
+    a.buf = h->dRecvBuf; a.wait = h->connected ? h->waitTab[DFR2D_XCHG_DISS] : nullptr; a.seq = xchg_seq(h);
+    k_halo_unpack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
+    return launch_check(h, "k_halo_unpack(diss)");
 }
 
 static int run_pack_vertex(dfr2d_handle *h) {
     if (h->nVtx == 0) return 0;
-    k_vertex_pack<<<(h->nVtx + 255) / 256, 256, 0, h->stream>>>(h->nVtx, h->vtxList, h->ds.sigmaV, h->ds.epsV, h->vSendBuf);
+    k_vertex_pack<<<(h->nVtx + 255) / 256, 256, 0, h->stream>>>(h->nVtx, h->vtxList, h->ds.sigmaV, h->ds.epsV, h->vSendBuf,
+                                                                h->connected ? h->putTab[DFR2D_XCHG_VERTEX] : nullptr, xchg_seq(h));
     return launch_check(h, "k_vertex_pack");
 }
 
 static int run_unpack_vertex(dfr2d_handle *h) {
     if (h->nVtx == 0) return 0;
     k_vertex_unpack_max<<<(h->nVtx + 255) / 256, 256, 0, h->stream>>>(h->nVtx, h->vtxList, (unsigned long long *)h->ds.sigmaV,
-                                                                      (unsigned long long *)h->ds.epsV, h->vRecvBuf);
+                                                                      (unsigned long long *)h->ds.epsV, h->vRecvBuf,
+                                                                      h->connected ? h->waitTab[DFR2D_XCHG_VERTEX] : nullptr, xchg_seq(h));
     return launch_check(h, "k_vertex_unpack_max");
 }
 
@@ -1181,6 +1211,10 @@ extern "C" int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info) {
     info->steps = h->scHost->steps;
     info->finished = h->scHost->finished;
     info->nan_found = h->scHost->nanFlag;
+    if (h->scHost->nanFlag == 2) {
+        h->err = "peer exchange timed out: a partner partition never delivered its halo / wave-speed message";
+        return DFR2D_ERR_PEER;
+    }
     if (h->scHost->nanFlag) {
         h->err = "NAN found";
         return DFR2D_ERR_NAN;
@@ -1188,159 +1222,260 @@ extern "C" int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info) {
     return 0;
 }
 
+// {max wave speed, max viscous wave speed} over all partitions (calculateGlobalDT, euler.go:945-971): put + gather over
+// the peer mailboxes; the gather is also the stage barrier of the mailbox protocol (dfr2d_peer.cuh).  Two launches so
+// that partitions sharing one stream (tests: all partitions on one device) can post every put before the first wait.
+static int stage_wave_put(dfr2d_handle *h) {
+    if (!h->connected) return 0;
+    CK(cudaSetDevice(h->device));
+    const int slot = (int)(h->stageCounter & 1);
+    k_wave_put<<<1, 32, 0, h->stream>>>(&h->sc->wave[slot][0], h->waveTab, slot, xchg_seq(h));
+    return launch_check(h, "k_wave_put");
+}
+static int stage_wave_gather(dfr2d_handle *h) {
+    if (!h->connected) return 0;
+    CK(cudaSetDevice(h->device));
+    const int slot = (int)(h->stageCounter & 1);
+    k_wave_gather<<<1, 32, 0, h->stream>>>(&h->sc->wave[slot][0], h->waveTab, slot, xchg_seq(h));
+    return launch_check(h, "k_wave_gather");
+}
+extern "C" int dfr2d_stage_wave(dfr2d_handle *h, int rk) {
+    (void)rk;
+    if (!h) return 1;
+    if (!h->connected) { h->err = "dfr2d_stage_wave needs dfr2d_peer_connect (unconnected hosts max-reduce dfr2d_wavespeed_buffer)"; return 1; }
+    if (int rc = stage_wave_put(h)) return rc;
+    return stage_wave_gather(h);
+}
+
+static bool host_finished(const dfr2d_handle *h) { return h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter; }
+
 extern "C" int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info) {
     if (!h) return 1;
-    if (h->nParts > 1) {
-        h->err = "dfr2d_step drives a single partition; multi-partition hosts use the stage calls with their own exchange";
+    if (h->nParts > 1 && !h->connected) {
+        h->err = "dfr2d_step on one partition of several needs dfr2d_peer_connect first (or drive the stage calls with "
+                 "your own exchange, or use dfr2d_multi_step)";
         return 1;
     }
     for (int s = 0; s < nsteps; s++) {
-        if (h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) break;   // host-visible half of CheckIfFinished
+        if (host_finished(h)) break;      // host-visible half of CheckIfFinished
         for (int rk = 0; rk < 5; rk++) {
-            if (int rc = stage_sensor(h, rk)) return rc;
-            if (int rc = stage_prepare(h, rk)) return rc;
-            if (int rc = stage_edges(h, rk)) return rc;
-            if (int rc = stage_visc(h, rk)) return rc;
+            if (int rc = stage_sensor(h, rk)) return rc;              // (+ put VERTEX)
+            if (int rc = stage_prepare(h, rk)) return rc;             // (wait VERTEX) ... (+ put EDGE)
+            if (h->connected)
+                if (int rc = stage_edges_interior(h, rk)) return rc;  // overlaps the halo flight
+            if (int rc = stage_edges(h, rk)) return rc;               // (wait EDGE) ... (+ put DISS)
+            if (int rc = stage_visc(h, rk)) return rc;                // (wait DISS)
+            if (int rc = stage_wave_put(h)) return rc;
+            if (int rc = stage_wave_gather(h)) return rc;
             if (int rc = stage_update(h, rk, nullptr)) return rc;
         }
     }
     int rc = dfr2d_step_finish(h, info);
-    if (info && h->stepIndex >= 1 && h->stepIndex >= (long long)h->ph.maxIter) info->finished = 1;
+    if (info && host_finished(h)) info->finished = 1;
     return rc;
 }
 
-// ---- single-process multi-GPU driver ------------------------------------------------------------------------------
-struct PeerSlots {
-    const unsigned long long *p[32];
-    int n;
+// ---- peer connection -----------------------------------------------------------------------------------------------
+// What a partner needs to know about a partition's mailbox.  Fixed-size, plain data: it travels through whatever the host
+// has (an all-gather between processes; nothing at all inside one process).
+struct PeerBlob {
+    uint64_t magic;
+    int32_t device, part, nParts, pad;
+    int64_t hostPid;
+    cudaIpcMemHandle_t mem;
+    int64_t words;
+    int64_t off[3], offFlags, offWaveFlag, offWaveIn;
+    int64_t cnt[3][kMaxParts];          // doubles I receive from partition p per exchange (symmetric: = what I send to p)
 };
+static_assert(sizeof(PeerBlob) <= DFR2D_PEER_BLOB_BYTES, "PeerBlob must fit the ABI blob");
+constexpr uint64_t kPeerMagic = 0x3244524644504231ull;
 
-// {max wave speed, max viscous wave speed} over all partitions: bit patterns of non-negative doubles order like the
-// doubles.  A peer may be updating its own slot while it is read here; the slot only ever grows towards the global
-// maximum, so either value is a valid contribution.
-__global__ void k_wave_max_peers(unsigned long long *mine, PeerSlots peers) {
-    const int t = threadIdx.x;
-    if (t < 2) {
-        unsigned long long v = mine[t];
-        for (int i = 0; i < peers.n; i++) {
-            const unsigned long long w = *(const volatile unsigned long long *)(peers.p[i] + t);
-            v = w > v ? w : v;
-        }
-        mine[t] = v;
+static void fill_blob(const dfr2d_handle *h, PeerBlob &b) {
+    memset(&b, 0, sizeof(b));
+    b.magic = kPeerMagic;
+    b.device = h->device; b.part = h->part; b.nParts = h->nParts;
+    b.hostPid = (int64_t)getpid();
+    b.words = (int64_t)h->mailboxWords;
+    for (int w = 0; w < 3; w++) b.off[w] = h->mbOff[w];
+    b.offFlags = h->mbFlags; b.offWaveFlag = h->mbWaveFlag; b.offWaveIn = h->mbWaveIn;
+    for (int p = 0; p < h->nParts; p++) {
+        b.cnt[DFR2D_XCHG_EDGE][p] = h->recvCounts[p];
+        b.cnt[DFR2D_XCHG_VERTEX][p] = h->vtxCounts[p];
+        b.cnt[DFR2D_XCHG_DISS][p] = h->dissCounts[p];
     }
 }
 
-static int multi_prepare(dfr2d_handle **hs, int n) {
+extern "C" int dfr2d_peer_export(dfr2d_handle *h, void *blob) {
+    if (!h || !blob) return 1;
+    if (h->nParts < 2 || !h->mailbox) { h->err = "dfr2d_peer_export: a single partition has no peers"; return 1; }
+    CK(cudaSetDevice(h->device));
+    PeerBlob b;
+    fill_blob(h, b);
+    CK(cudaIpcGetMemHandle(&b.mem, h->mailbox));
+    memset(blob, 0, DFR2D_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof(b));
+    return 0;
+}
+
+// base[p] = address of partition p's mailbox as seen from h's device
+static int connect_with(dfr2d_handle *h, const PeerBlob *blobs, unsigned long long *const *base) {
+    const int n = h->nParts, me = h->part;
+    CK(cudaSetDevice(h->device));
+    PutTab put[3];
+    WaitTab wait[3];
+    memset(put, 0, sizeof(put));
+    memset(wait, 0, sizeof(wait));
+    if (!h->putDone) {
+        if (int rc = dev_alloc(h, &h->putDone, 4)) return rc;
+        CK(cudaMemset(h->putDone, 0, 4 * sizeof(unsigned int)));
+        for (int w = 0; w < 3; w++) {
+            if (int rc = dev_alloc(h, &h->putTab[w], 1)) return rc;
+            if (int rc = dev_alloc(h, &h->waitTab[w], 1)) return rc;
+        }
+    }
+    for (int w = 0; w < 3; w++) {
+        const std::vector<int64_t> &mine = (w == DFR2D_XCHG_EDGE) ? h->sendCounts : (w == DFR2D_XCHG_VERTEX ? h->vtxCounts : h->dissCounts);
+        put[w].nParts = wait[w].nParts = n;
+        put[w].done = h->putDone + w;
+        wait[w].flag = h->mailbox + h->mbFlags + (size_t)w * kMaxParts;
+        wait[w].err = &h->sc->nanFlag;
+        int64_t acc = 0;
+        for (int p = 0; p < n; p++) {
+            put[w].first[p] = wait[w].first[p] = acc;
+            const int64_t cnt = (p == me) ? 0 : mine[p];
+            if (cnt != blobs[p].cnt[w][me]) { h->err = "dfr2d_peer_connect: partner disagrees on the message size (different mesh or partitioning?)"; return 1; }
+            if (cnt > 0) {
+                int64_t segOff = 0;                   // my segment inside p's receive buffer: behind those of partitions < me
+                for (int k = 0; k < me; k++) segOff += blobs[p].cnt[w][k];
+                put[w].dst[p] = (double *)(base[p] + blobs[p].off[w]) + segOff;
+                put[w].flag[p] = base[p] + blobs[p].offFlags + (size_t)w * kMaxParts + me;
+            }
+            acc += cnt;
+        }
+        for (int p = n; p <= kMaxParts; p++) put[w].first[p] = wait[w].first[p] = acc;
+        CK(cudaMemcpy(h->putTab[w], &put[w], sizeof(PutTab), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->waitTab[w], &wait[w], sizeof(WaitTab), cudaMemcpyHostToDevice));
+    }
+    WaveTab &wt = h->waveTab;
+    memset(&wt, 0, sizeof(wt));
+    wt.nParts = n; wt.me = me;
+    wt.myInbox = h->mailbox + h->mbWaveIn;
+    wt.myFlag = h->mailbox + h->mbWaveFlag;
+    wt.err = &h->sc->nanFlag;
+    for (int p = 0; p < n; p++)
+        if (p != me) {
+            wt.inbox[p] = base[p] + blobs[p].offWaveIn + (size_t)me * 4;
+            wt.flag[p] = base[p] + blobs[p].offWaveFlag + me;
+        }
+    h->connected = true;
+    return 0;
+}
+
+// Between processes: blobs = [n_parts][DFR2D_PEER_BLOB_BYTES] gathered from every partition (index = partition).  The
+// mailboxes are mapped with cudaIpcOpenMemHandle (which also enables peer access); partitions of this very process are
+// used directly.  Collective in spirit: every partition must connect before anyone steps.
+extern "C" int dfr2d_peer_connect(dfr2d_handle *h, const void *blobs_raw, int n) {
+    if (!h || !blobs_raw) return 1;
+    if (n != h->nParts || n < 2 || n > kMaxParts) { h->err = "dfr2d_peer_connect: need one blob per partition (2..32)"; return 1; }
+    if (h->putDone) { h->connected = true; return 0; }
+    CK(cudaSetDevice(h->device));
+    std::vector<PeerBlob> blobs((size_t)n);
+    std::vector<unsigned long long *> base((size_t)n, nullptr);
+    for (int p = 0; p < n; p++) {
+        memcpy(&blobs[p], (const char *)blobs_raw + (size_t)p * DFR2D_PEER_BLOB_BYTES, sizeof(PeerBlob));
+        if (blobs[p].magic != kPeerMagic || blobs[p].part != p || blobs[p].nParts != n) { h->err = "dfr2d_peer_connect: bad blob"; return 1; }
+    }
+    for (int p = 0; p < n; p++) {
+        if (p == h->part) { base[p] = h->mailbox; continue; }
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, blobs[p].mem, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            h->err = std::string("cudaIpcOpenMemHandle (partition ") + std::to_string(p) + "): " + cudaGetErrorString(e);
+            cudaGetLastError();
+            return 2;
+        }
+        h->ipcMapped.push_back(ptr);
+        base[p] = (unsigned long long *)ptr;
+    }
+    return connect_with(h, blobs.data(), base.data());
+}
+
+// Switch between the peer-memory exchange (on) and the host-moved exchange of the plain stage API (off) on a handle that
+// has been connected; the mappings stay.  Every partition must switch at the same stage boundary.
+extern "C" int dfr2d_peer_enable(dfr2d_handle *h, int on) {
+    if (!h) return 1;
+    if (on && !h->putDone) { h->err = "dfr2d_peer_enable: not connected (dfr2d_peer_connect / dfr2d_multi_step first)"; return 1; }
+    h->connected = on != 0;
+    return 0;
+}
+
+// Inside one process (the Go controller goroutine owning all partitions): plain peer access, no IPC.
+static int connect_local(dfr2d_handle **hs, int n) {
+    std::vector<PeerBlob> blobs((size_t)n);
+    std::vector<unsigned long long *> base((size_t)n, nullptr);
     for (int i = 0; i < n; i++) {
         dfr2d_handle *h = hs[i];
         if (!h || h->nParts != n || h->part != i) return 1;
-        CK(cudaSetDevice(h->device));
-        if (!h->evXchg) {
-            CK(cudaEventCreateWithFlags(&h->evXchg, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&h->evWave, cudaEventDisableTiming));
-            for (int j = 0; j < n; j++)
-                if (hs[j] && hs[j]->device != h->device) {
-                    int can = 0;
-                    cudaDeviceCanAccessPeer(&can, h->device, hs[j]->device);
-                    if (!can) { h->err = "dfr2d_multi_step needs peer access between the devices"; return 2; }
-                    cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
-                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return 2; }
-                    cudaGetLastError();
-                }
-        }
+        if (!h->mailbox) { h->err = "dfr2d_multi_step: handle has no mailbox"; return 1; }
+        fill_blob(h, blobs[i]);
+        base[i] = h->mailbox;
     }
-    return 0;
-}
-
-static const std::vector<int64_t> &xchg_counts(const dfr2d_handle *h, int which) {
-    return which == DFR2D_XCHG_EDGE ? h->sendCounts : (which == DFR2D_XCHG_VERTEX ? h->vtxCounts : h->dissCounts);
-}
-
-// segment j of partition i's send buffer -> segment i of partition j's receive buffer (all_to_all semantics; counts are
-// symmetric).  Copies run on the sender's stream behind its pack kernel; receivers wait for the senders' events.  The
-// receive buffer of the previous stage has been consumed by then: every stage ends in multi_wave_max, where each stream
-// waits for all others' edge phase.
-static int multi_exchange(dfr2d_handle **hs, int n, int which) {
-    bool any = false;
     for (int i = 0; i < n; i++) {
         dfr2d_handle *h = hs[i];
-        const std::vector<int64_t> &ci = xchg_counts(h, which);
-        if ((int)ci.size() < n) continue;
-        const double *sb = which == DFR2D_XCHG_EDGE ? h->sendBuf : (which == DFR2D_XCHG_VERTEX ? h->vSendBuf : h->dSendBuf);
+        if (h->putDone) { h->connected = true; continue; }
         CK(cudaSetDevice(h->device));
-        int64_t so = 0;
-        bool sent = false;
-        for (int j = 0; j < n; j++) {
-            const int64_t cnt = ci[j];
-            if (j != i && cnt > 0) {
-                dfr2d_handle *d = hs[j];
-                const std::vector<int64_t> &cj = xchg_counts(d, which);
-                int64_t ro = 0;
-                for (int k = 0; k < i; k++) ro += cj[k];
-                double *rb = which == DFR2D_XCHG_EDGE ? d->recvBuf : (which == DFR2D_XCHG_VERTEX ? d->vRecvBuf : d->dRecvBuf);
-                CK(cudaMemcpyPeerAsync(rb + ro, d->device, sb + so, h->device, (size_t)cnt * sizeof(double), h->stream));
-                sent = true;
+        for (int j = 0; j < n; j++)
+            if (hs[j]->device != h->device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, h->device, hs[j]->device);
+                if (!can) { h->err = "dfr2d_multi_step needs peer access between the devices"; return 2; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(hs[j]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return 2; }
+                cudaGetLastError();
             }
-            so += cnt;
-        }
-        if (sent) { CK(cudaEventRecord(h->evXchg, h->stream)); any = true; }
-    }
-    if (!any) return 0;
-    for (int j = 0; j < n; j++) {
-        dfr2d_handle *d = hs[j], *h = d;       // (CK reports into h)
-        const std::vector<int64_t> &cj = xchg_counts(d, which);
-        if ((int)cj.size() < n) continue;
-        CK(cudaSetDevice(d->device));
-        for (int i = 0; i < n; i++)
-            if (i != j && cj[i] > 0 && !(hs[i]->device == d->device && hs[i]->stream == d->stream))
-                CK(cudaStreamWaitEvent(d->stream, hs[i]->evXchg, 0));
+        if (int rc = connect_with(h, blobs.data(), base.data())) return rc;
     }
     return 0;
 }
 
-static int multi_wave_max(dfr2d_handle **hs, int n) {
-    for (int i = 0; i < n; i++) {
-        dfr2d_handle *h = hs[i];
-        CK(cudaSetDevice(h->device));
-        CK(cudaEventRecord(h->evWave, h->stream));
-    }
-    for (int j = 0; j < n; j++) {
-        dfr2d_handle *d = hs[j], *h = d;
-        CK(cudaSetDevice(d->device));
-        PeerSlots ps{};
-        for (int i = 0; i < n; i++)
-            if (i != j) {
-                if (!(hs[i]->device == d->device && hs[i]->stream == d->stream)) CK(cudaStreamWaitEvent(d->stream, hs[i]->evWave, 0));
-                ps.p[ps.n++] = &hs[i]->sc->wave[hs[i]->stageCounter & 1][0];
-            }
-        k_wave_max_peers<<<1, 32, 0, d->stream>>>(&d->sc->wave[d->stageCounter & 1][0], ps);
-        d->launches++;
-        if (int rc = launch_check(d, "k_wave_max_peers")) return rc;
-    }
-    return 0;
-}
+// ---- single-process multi-GPU driver ------------------------------------------------------------------------------
+// The same stage protocol as dfr2d_step, issued phase by phase over all partitions by the one calling thread: every
+// partition's put of an exchange is enqueued before any partition's wait for it, so partitions that share a device (and
+// hence a stream) cannot deadlock, and partitions on different devices run concurrently.  prof (optional): CUDA events
+// at the phase boundaries of one step on every partition's stream.
+struct MultiProf {
+    std::vector<cudaEvent_t> ev;       // [n][5 stages][kProfPhases + 1]
+};
+constexpr int kProfPhases = 6;         // sensor+prepare(pack,put) | interior edges | halo wait+cut/boundary edges(+grad) | visc | wave | update
 
-extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info) {
-    if (!hs || n < 1 || n > 32) return 1;
+static int multi_step_impl(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info, MultiProf *prof) {
+    if (!hs || n < 1 || n > kMaxParts) return 1;
     if (n == 1) return dfr2d_step(hs[0], nsteps, info);
-    if (int rc = multi_prepare(hs, n)) return rc;
-#define MULTI_ALL(call)                                  \
-    for (int g = 0; g < n; g++)                          \
-        if (int rc = call) return rc;
+    if (int rc = connect_local(hs, n)) return rc;
+    auto mark = [&](int g, int rk, int ph) -> int {
+        if (!prof) return 0;
+        dfr2d_handle *h = hs[g];
+        CK(cudaSetDevice(h->device));
+        CK(cudaEventRecord(prof->ev[((size_t)g * 5 + rk) * (kProfPhases + 1) + ph], h->stream));
+        return 0;
+    };
+#define MULTI_ALL(call, ph)                              \
+    for (int g = 0; g < n; g++) {                        \
+        if (int rc = call) return rc;                    \
+        if (ph >= 0) if (int rc = mark(g, rk, ph)) return rc; \
+    }
     for (int s = 0; s < nsteps; s++) {
-        if (hs[0]->stepIndex >= 1 && hs[0]->stepIndex >= (long long)hs[0]->ph.maxIter) break;
+        if (host_finished(hs[0])) break;
         for (int rk = 0; rk < 5; rk++) {
-            MULTI_ALL(stage_sensor(hs[g], rk));
-            if (hs[0]->ph.dissipation)
-                if (int rc = multi_exchange(hs, n, DFR2D_XCHG_VERTEX)) return rc;
-            MULTI_ALL(stage_prepare(hs[g], rk));
-            if (int rc = multi_exchange(hs, n, DFR2D_XCHG_EDGE)) return rc;
-            MULTI_ALL(stage_edges(hs[g], rk));
-            if (hs[0]->ph.dissipation)
-                if (int rc = multi_exchange(hs, n, DFR2D_XCHG_DISS)) return rc;
-            MULTI_ALL(stage_visc(hs[g], rk));
-            if (int rc = multi_wave_max(hs, n)) return rc;
-            MULTI_ALL(stage_update(hs[g], rk, nullptr));
+            MULTI_ALL(mark(g, rk, 0), -1);
+            MULTI_ALL(stage_sensor(hs[g], rk), -1);
+            MULTI_ALL(stage_prepare(hs[g], rk), 1);
+            MULTI_ALL(stage_edges_interior(hs[g], rk), 2);
+            MULTI_ALL(stage_edges(hs[g], rk), 3);
+            MULTI_ALL(stage_visc(hs[g], rk), 4);
+            MULTI_ALL(stage_wave_put(hs[g]), -1);
+            MULTI_ALL(stage_wave_gather(hs[g]), 5);
+            MULTI_ALL(stage_update(hs[g], rk, nullptr), 6);
         }
     }
 #undef MULTI_ALL
@@ -1351,9 +1486,46 @@ extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step
         if (r) rc = r;
         if (g == 0 && info) {
             *info = tmp;
-            if (hs[0]->stepIndex >= 1 && hs[0]->stepIndex >= (long long)hs[0]->ph.maxIter) info->finished = 1;
+            if (host_finished(hs[0])) info->finished = 1;
         }
     }
+    return rc;
+}
+
+extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info) {
+    return multi_step_impl(hs, n, nsteps, info, nullptr);
+}
+
+// One profiled step: ms_out[n][5][6] = duration of each phase of each stage on each partition (CUDA events on the
+// partition's stream; waiting for a partner's halo or wave value is inside the phase that waits).
+extern "C" int dfr2d_multi_step_profile(dfr2d_handle **hs, int n, float *ms_out) {
+    if (!hs || n < 1 || n > kMaxParts || !ms_out) return 1;
+    MultiProf prof;
+    prof.ev.assign((size_t)n * 5 * (kProfPhases + 1), nullptr);
+    int rc = 0;
+    for (int g = 0; g < n && !rc; g++) {
+        dfr2d_handle *h = hs[g];
+        if (!h) { rc = 1; break; }
+        if (cudaSetDevice(h->device) != cudaSuccess) { rc = 2; break; }
+        for (int i = 0; i < 5 * (kProfPhases + 1); i++)
+            if (cudaEventCreate(&prof.ev[(size_t)g * 5 * (kProfPhases + 1) + i]) != cudaSuccess) { rc = 2; break; }
+    }
+    if (!rc) rc = multi_step_impl(hs, n, 1, nullptr, n > 1 ? &prof : nullptr);
+    if (!rc && n > 1)
+        for (int g = 0; g < n; g++) {
+            cudaSetDevice(hs[g]->device);
+            cudaStreamSynchronize(hs[g]->stream);
+            for (int rk = 0; rk < 5; rk++)
+                for (int ph = 0; ph < kProfPhases; ph++) {
+                    const size_t i = ((size_t)g * 5 + rk) * (kProfPhases + 1) + ph;
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, prof.ev[i], prof.ev[i + 1]);
+                    ms_out[((size_t)g * 5 + rk) * kProfPhases + ph] = ms;
+                }
+        }
+    for (size_t i = 0; i < prof.ev.size(); i++)
+        if (prof.ev[i]) cudaEventDestroy(prof.ev[i]);
+    cudaGetLastError();
     return rc;
 }
 

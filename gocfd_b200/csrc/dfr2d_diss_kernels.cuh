@@ -1,6 +1,7 @@
 // Utility kernels (halo pack/unpack, residual reduction) and the artificial-dissipation path.
 #pragma once
 #include "dfr2d_kernels.cuh"
+#include "dfr2d_peer.cuh"
 
 namespace dfr2d {
 
@@ -16,60 +17,6 @@ struct DissBuffers {
     double *aggv = nullptr;              // [NEp]
     double *DTVisc = nullptr;            // [Kp]
 };
-
-// Halo messages.  One message slot per cut edge, `per` doubles each:
-//   [4 vars][NpEdge points] rows `rowBase + row0[c] + i` of a [4][planeRows][Kp] array (Q_Face, DissX or DissY), in
-//   the sender's own edge-point order, followed (Q_Face message of the dissipation path only, nTail = 3) by the three
-//   vertex epsilon values of the sender's element.
-__global__ void k_halo_pack(int total, int per, int npEdge, int planeRows, int rowBase, int Kp, const double *src,
-                            const int *elem, const int *row0, double *buf, int bufOff, int nTail, const int *etov,
-                            const double *epsV) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int body = 4 * npEdge;
-    const int c = t / (body + nTail), r = t % (body + nTail);
-    double v;
-    if (r < body) {
-        const int n = r / npEdge, i = r % npEdge;
-        v = src[((size_t)n * planeRows + rowBase + row0[c] + i) * Kp + elem[c]];
-    } else {
-        v = epsV[etov[(size_t)(r - body) * Kp + elem[c]]];
-    }
-    buf[(size_t)c * per + bufOff + r] = v;
-}
-
-// ghost element g = col - K gets the private vertex slots NV + 3g + {0,1,2} (its etov entries point there)
-__global__ void k_halo_unpack(int total, int per, int npEdge, int planeRows, int rowBase, int Kp, double *dst,
-                              const int *col, const int *row0, const double *buf, int bufOff, int nTail, int K, int NV,
-                              double *epsV) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int body = 4 * npEdge;
-    const int c = t / (body + nTail), r = t % (body + nTail);
-    const double v = buf[(size_t)c * per + bufOff + r];
-    if (r < body) {
-        const int n = r / npEdge, i = r % npEdge;
-        dst[((size_t)n * planeRows + rowBase + row0[c] + i) * Kp + col[c]] = v;
-    } else {
-        epsV[(size_t)NV + 3 * (size_t)(col[c] - K) + (r - body)] = v;
-    }
-}
-
-// shared-vertex exchange of the element -> vertex max merge: message = (sigma, eps) per listed vertex
-__global__ void k_vertex_pack(int n, const int *vid, const double *sigmaV, const double *epsV, double *buf) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    buf[2 * (size_t)t] = sigmaV[vid[t]];
-    buf[2 * (size_t)t + 1] = epsV[vid[t]];
-}
-__global__ void k_vertex_unpack_max(int n, const int *vid, unsigned long long *sigmaV, unsigned long long *epsV,
-                                    const double *buf) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const double s = buf[2 * (size_t)t], e = buf[2 * (size_t)t + 1];
-    if (s > 0.0) atomic_max_nonneg(&sigmaV[vid[t]], s);
-    if (e > 0.0) atomic_max_nonneg(&epsV[vid[t]], e);
-}
 
 // Columns [K, Kp) of a [4][npInt][Kp] register get a benign constant state (rho=1, E=2.5, no momentum) so that the
 // persistent element kernel can treat every 32-element tile as full; their metrics are zero, so they stay constant.

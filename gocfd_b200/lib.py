@@ -52,6 +52,7 @@ EXPORTS = [
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
+    "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -108,6 +109,11 @@ def load():
     lib.dfr2d_mma_diss_table.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_mma_diss_table.restype = C.c_int64
     lib.dfr2d_multi_step.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.POINTER(StepInfo)]
+    lib.dfr2d_peer_export.argtypes = [H, C.c_void_p]
+    lib.dfr2d_peer_connect.argtypes = [H, C.c_void_p, C.c_int]
+    lib.dfr2d_stage_wave.argtypes = [H, C.c_int]
+    lib.dfr2d_peer_enable.argtypes = [H, C.c_int]
+    lib.dfr2d_multi_step_profile.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
     _lib = lib
@@ -194,6 +200,22 @@ def multi_step(devs, nsteps=1, sync=True):
     if rc != 0:
         raise Dfr2dError("dfr2d_multi_step failed (%d): %s" % (rc, "; ".join(lib.dfr2d_last_error(d.h).decode() for d in devs)))
     return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
+
+
+PEER_BLOB_BYTES = 1280
+PROFILE_PHASES = ("sensor+prepare+pack/put", "interior edges", "halo wait + boundary/cut edges (+ RT gradient)",
+                  "viscous edges", "wave put+gather", "element update")
+
+
+def multi_step_profile(devs):
+    """One profiled dfr2d_multi_step step: array [n][5 stages][6 phases] of milliseconds (CUDA events per partition)."""
+    lib = load()
+    arr = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    out = np.zeros((len(devs), 5, len(PROFILE_PHASES)), dtype=np.float32)
+    rc = lib.dfr2d_multi_step_profile(arr, len(devs), out.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != 0:
+        raise Dfr2dError("dfr2d_multi_step_profile failed (%d): %s" % (rc, "; ".join(lib.dfr2d_last_error(d.h).decode() for d in devs)))
+    return out
 
 
 def rcm_order(problem):
@@ -356,6 +378,24 @@ class Dfr2d:
 
     def stage_update(self, rk):
         self._ck(self.lib.dfr2d_stage_update(self.h, rk))
+
+    def stage_wave(self, rk):
+        self._ck(self.lib.dfr2d_stage_wave(self.h, rk))
+
+    def peer_export(self):
+        """The mailbox description a partner needs (bytes); gather one per partition and pass the list to peer_connect."""
+        blob = C.create_string_buffer(PEER_BLOB_BYTES)
+        self._ck(self.lib.dfr2d_peer_export(self.h, blob))
+        return blob.raw
+
+    def peer_connect(self, blobs):
+        """blobs[p] = peer_export() of partition p (own entry included).  Afterwards step() works on this partition."""
+        assert len(blobs) == self.n_parts and all(len(b) == PEER_BLOB_BYTES for b in blobs)
+        raw = C.create_string_buffer(b"".join(blobs), PEER_BLOB_BYTES * len(blobs))
+        self._ck(self.lib.dfr2d_peer_connect(self.h, raw, len(blobs)))
+
+    def peer_enable(self, on):
+        self._ck(self.lib.dfr2d_peer_enable(self.h, int(bool(on))))
 
     def step_finish(self, sync=True):
         info = StepInfo()

@@ -42,6 +42,7 @@ enum { DFR2D_FIELD_DT = 0, DFR2D_FIELD_SigmaScalar = 1, DFR2D_FIELD_EpsilonScala
 
 #define DFR2D_MAX_ORDER 4
 #define DFR2D_ERR_NAN 7
+#define DFR2D_ERR_PEER 8   /* a partner partition never delivered its message (peer exchange timed out) */
 
 /* fluids.go:237-243 FreeStream */
 typedef struct dfr2d_freestream {
@@ -193,15 +194,35 @@ int dfr2d_exchange_counts(const dfr2d_handle *h, int which, int64_t *send_counts
 int dfr2d_exchange_buffers(dfr2d_handle *h, int which, void **send_dev, void **recv_dev);
 int dfr2d_step_finish(dfr2d_handle *h, dfr2d_step_info *info); /* after stage 4: read back time/steps (info may be NULL) */
 
-/* ---- single-process multi-GPU driver (the natural shape for the Go host: one controller goroutine, euler.go:408-412) ----
- * hs[g] = dfr2d_create(p, n, g, device_g, ...) for g = 0..n-1, all in this process (several partitions may share a device).
- * dfr2d_multi_step runs nsteps x { 5 x the stage protocol above } over all partitions: every exchange is a set of
- * cudaMemcpyPeerAsync copies (send segment of partition i -> receive segment of partition j, only between partitions that
- * share cut edges / vertices) ordered by CUDA events, and the MAX of the wave-speed pair is taken by a one-warp kernel per
- * partition that reads its peers' slots through peer access.  No host synchronisation inside the call; `info` (may be
- * NULL) is read back from partition 0 at the end.  Replaces the goroutine fan-out of RungeKutta5SSP.Step
- * (euler.go:408-418) and the serial max of calculateGlobalDT (euler.go:951-955). */
+/* ---- partition-to-partition exchange over peer memory (NVLink P2P), no host and no collective library in the loop ----
+ * Replaces the shared memory through which the reference's partition goroutines read each other's Q_Face / edge store
+ * (RungeKutta5SSP.Step, euler.go:408-418; calculateSharedEdgeFlux, edges.go:379-411) and the serial max over partitions
+ * of calculateGlobalDT (euler.go:951-955).  Every partition owns a MAILBOX in device memory (receive buffers of the
+ * three exchanges, arrival flags, a wave-speed inbox).  Once partitions are connected, the pack kernels store their
+ * messages straight into the partner's mailbox and publish the stage's sequence number in its arrival flag; the unpack
+ * kernels spin on the flag (csrc/dfr2d_peer.cuh).  After connecting, dfr2d_step() works on every partition of a
+ * multi-partition run -- each owner just calls it -- and the stage calls exchange by themselves (the host must then NOT
+ * move the halo buffers; it calls dfr2d_stage_wave instead of max-reducing dfr2d_wavespeed_buffer).
+ *
+ *   one process per partition (torchrun / MPI style): dfr2d_peer_export on every partition, all-gather the blobs by any
+ *       means, dfr2d_peer_connect(h, blobs, n_parts) everywhere (cudaIpcOpenMemHandle under the hood), barrier, step.
+ *   one process owning all partitions (the Go controller goroutine): dfr2d_multi_step connects them itself
+ *       (cudaDeviceEnablePeerAccess) and issues the stages of all partitions from the calling thread. */
+#define DFR2D_PEER_BLOB_BYTES 1280
+int dfr2d_peer_export(dfr2d_handle *h, void *blob /* [DFR2D_PEER_BLOB_BYTES] */);
+int dfr2d_peer_connect(dfr2d_handle *h, const void *blobs /* [n_parts][DFR2D_PEER_BLOB_BYTES], index = partition */, int n_parts);
+/* back to the host-moved exchange of the plain stage API (on = 0) or to the mailboxes again (on = 1); mappings stay */
+int dfr2d_peer_enable(dfr2d_handle *h, int on);
+int dfr2d_stage_wave(dfr2d_handle *h, int rk);   /* connected hosts: put + gather of the wave-speed pair, between visc and update */
+
+/* hs[g] = dfr2d_create(p, n, g, device_g, ...) for g = 0..n-1, all in this process (several partitions may share a device).
+ * dfr2d_multi_step runs nsteps x { 5 stages } over all partitions with the mailbox protocol above; the numerical flux of
+ * the edges that touch no ghost column runs while the halo is in flight.  No host synchronisation inside the call;
+ * `info` (may be NULL) is read back from partition 0 at the end.  Results are bitwise those of a single partition. */
 int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info);
+/* One profiled step: ms_out[n][5 stages][6 phases] = CUDA-event duration of {sensor+prepare+pack/put, interior edges,
+ * halo wait + boundary/cut edges (+ RT gradient), viscous edges, wave put+gather, element update} on each partition. */
+int dfr2d_multi_step_profile(dfr2d_handle **hs, int n, float *ms_out);
 
 /* ---- host-only partition plan (no CUDA): the bookkeeping dfr2d_create performs for (n_parts, part), exposed so
  * the decomposition can be verified bit-exactly on a CPU-only machine.  Mirrors utils.PartitionMap +

@@ -365,6 +365,21 @@ int ora_threads(void) {
 #endif
 }
 
+/* Explicit thread count for the CPU arm of bench.py: launchers such as torchrun export OMP_NUM_THREADS=1, which would
+ * silently turn the "all host cores" baseline into a single-thread one.  n <= 0 leaves the OpenMP default. */
+int ora_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) {
+        omp_set_dynamic(0);
+        omp_set_num_threads(n);
+    }
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 void ora_set_state(ora *o, const double *Q) { memcpy(o->Q[0], Q, sizeof(double) * 4 * (size_t)o->NpInt * (size_t)o->K); }
 void ora_set_register(ora *o, int reg, const double *Q) {
     if (reg >= 0 && reg < 5) memcpy(o->Q[reg], Q, sizeof(double) * 4 * (size_t)o->NpInt * (size_t)o->K);

@@ -35,6 +35,8 @@ def load():
         lib.ora_destroy.argtypes = [H]
         lib.ora_destroy.restype = None
         lib.ora_threads.restype = C.c_int
+        lib.ora_set_threads.argtypes = [C.c_int]
+        lib.ora_set_threads.restype = C.c_int
         lib.ora_set_state.argtypes = [H, _dp]
         lib.ora_get_state.argtypes = [H, _dp]
         lib.ora_residual.argtypes = [H, _dp]
@@ -47,6 +49,11 @@ def load():
 
 def threads():
     return int(load().ora_threads())
+
+
+def set_threads(n):
+    """Use n OpenMP threads regardless of OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1); returns the count in force."""
+    return int(load().ora_set_threads(int(n)))
 
 
 class COracleSolver:

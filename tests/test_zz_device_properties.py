@@ -1,5 +1,7 @@
 """Size-independent properties of full device runs (no oracle).  Needs a GPU.  Kept in its own module, collected last:
 these runs were added at the very end of round 1 and have only been through the CPU restatement so far."""
+import os
+
 import numpy as np
 import pytest
 
@@ -56,14 +58,23 @@ def test_device_converges_to_the_exact_vortex(n, flux, coarse, fine, cfl, min_or
 # degenerate to device copies, the event waits to stream order) and the result must be the single-partition run, bit
 # for bit, like the hand-driven protocol of tests/test_gpu_parity.py.
 
-_EXPERIMENTAL = __import__("os").environ.get("DFR2D_TEST_EXPERIMENTAL") == "1"
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
 
 
-@pytest.mark.skipif(not _EXPERIMENTAL, reason="not yet run on a GPU (set DFR2D_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("spread", [False, True])
 @pytest.mark.parametrize("n_parts,n,diss", [(3, 2, False), (2, 2, True), (4, 4, True)])
-def test_multi_step_driver_matches_single_partition(n_parts, n, diss):
+def test_multi_step_driver_matches_single_partition(n_parts, n, diss, spread):
+    """dfr2d_multi_step (mailbox protocol of csrc/dfr2d_peer.cuh: P2P puts + arrival flags + wave inbox) must reproduce
+    the single-partition run bit for bit.  spread=False: all partitions on device 0 (one stream: the issue order
+    'all puts before any wait' is what keeps it deadlock free).  spread=True: partition g on device g mod #devices --
+    real peer stores over NVLink; needs >= 2 GPUs."""
     from conftest import mesh_path
     from gocfd_b200 import lib
+    ndev = _n_devices()
+    if spread and ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
     if diss:
         c = make(dict(PolynomialOrder=n, InitType="shocktube", CFL=2.0, FinalTime=0.2, Limiter="persson c0", Kappa=5.0),
                  mesh_path("sod-aligned-100pts.su2"))
@@ -75,10 +86,13 @@ def test_multi_step_driver_matches_single_partition(n_parts, n, diss):
     one = lib.Dfr2d(c.problem)
     one.set_state(c.Q)
     a = one.step(4)
-    devs = [lib.Dfr2d(c.problem, n_parts=n_parts, part=r) for r in range(n_parts)]
+    devs = [lib.Dfr2d(c.problem, n_parts=n_parts, part=r, device=(r % ndev) if spread else 0) for r in range(n_parts)]
     for d in devs:
         d.set_state(c.Q)
-    b = lib.multi_step(devs, 4)
+    lib.multi_step(devs, 1)
+    prof = lib.multi_step_profile(devs)                  # the profiled step is an ordinary step
+    assert prof.shape == (n_parts, 5, len(lib.PROFILE_PHASES)) and (prof >= 0).all() and prof.sum() > 0
+    b = lib.multi_step(devs, 2)
     assert a["steps"] == b["steps"] == 4 and a["time"] == b["time"] and a["dt"] == b["dt"]
     q = np.zeros_like(c.Q)
     for d in devs:
@@ -89,7 +103,42 @@ def test_multi_step_driver_matches_single_partition(n_parts, n, diss):
     one.close()
 
 
-@pytest.mark.parametrize("diss_elem", [1] + ([3] if _EXPERIMENTAL else []))
+@pytest.mark.parametrize("world,diss", [(2, False), (3, True)])
+def test_peer_connected_processes_match_single_partition(world, diss, tmp_path):
+    """One PROCESS per partition (the torchrun shape): every process creates its partition, the mailbox descriptions are
+    all-gathered (gloo), dfr2d_peer_connect maps the partners' mailboxes through CUDA IPC, then each process simply calls
+    dfr2d_step.  No NCCL, no host in the stage loop.  Partitions use device rank mod #devices (on a one-GPU box the
+    processes time-slice the device).  Must equal the single-partition run bit for bit."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from gocfd_b200 import lib
+    port = 29600 + (os.getpid() % 300)
+    out = str(tmp_path / "state")
+    procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "peer_ipc_worker.py"), str(r), str(world),
+                               str(int(diss)), str(port), out], cwd=ROOT) for r in range(world)]
+    try:
+        rcs = [p.wait(timeout=240) for p in procs]
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    assert rcs == [0] * world
+    from peer_ipc_worker import build
+    c = build(diss)
+    one = lib.Dfr2d(c.problem)
+    one.set_state(c.Q)
+    a = one.step(4)
+    q = np.zeros_like(c.Q)
+    for r in range(world):
+        part = np.load("%s_%d.npz" % (out, r))
+        q[:, :, int(part["k0"]):int(part["k1"])] = part["q"]
+        assert float(part["time"]) == a["time"] and int(part["steps"]) == 4
+    assert np.array_equal(q, one.get_state())
+    one.close()
+
+
+@pytest.mark.parametrize("diss_elem", [1, 3])
 def test_naca_front_local_dt_active_dissipation_on_device(diss_elem, monkeypatch):
     """Local time stepping with an ACTIVE sensor (tests/test_c_oracle.py::_naca_front_case: ~400 elements above
     sigma = 0.05 in the first steps, DTVisc > 1e-9 in ~500): viscous dt limit and DTVisc carry-over on the device."""
