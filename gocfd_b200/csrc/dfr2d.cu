@@ -726,6 +726,49 @@ extern "C" int dfr2d_get_state(dfr2d_handle *h, double *Q) {
     if (!h || !Q) return 1;
     return copy_out(h, h->q[0], Q);
 }
+// All partitions of one process at once: the copies of different devices are enqueued before anything is waited for, so
+// they cross PCIe concurrently (one controller thread, n GPUs).
+static int multi_copy(dfr2d_handle **hs, int n, double *Q, bool in) {
+    if (!hs || !Q || n < 1) return 1;
+    for (int g = 0; g < n; g++) {
+        dfr2d_handle *h = hs[g];
+        if (!h) return 1;
+        CK(cudaSetDevice(h->device));
+        const size_t rows = (size_t)4 * h->NpInt;
+        if (in) {
+            h->qfaceValid = false;
+            CK(cudaMemcpy2DAsync(h->q[0], (size_t)h->Kp * sizeof(double), Q + h->k0, (size_t)h->Kglobal * sizeof(double),
+                                 (size_t)h->K * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
+        } else {
+            CK(cudaMemcpy2DAsync(Q + h->k0, (size_t)h->Kglobal * sizeof(double), h->q[0], (size_t)h->Kp * sizeof(double),
+                                 (size_t)h->K * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    for (int g = 0; g < n; g++) {
+        dfr2d_handle *h = hs[g];
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+extern "C" int dfr2d_multi_set_state(dfr2d_handle **hs, int n, const double *Q) { return multi_copy(hs, n, (double *)Q, true); }
+extern "C" int dfr2d_multi_get_state(dfr2d_handle **hs, int n, double *Q) { return multi_copy(hs, n, Q, false); }
+
+// rk.Time / rk.StepCount as the host sees them (restart from a saved state; euler.go:175-182 keeps them in the Euler struct)
+extern "C" int dfr2d_set_clock(dfr2d_handle *h, double time, int64_t steps) {
+    if (!h || steps < 0) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->scHost, h->sc, sizeof(DevScalars), cudaMemcpyDeviceToHost));
+    h->scHost->time[0] = h->scHost->time[1] = time;
+    h->scHost->timeOut = time;
+    h->scHost->steps = steps;
+    h->scHost->finished = 0;
+    CK(cudaMemcpy(h->sc, h->scHost, sizeof(DevScalars), cudaMemcpyHostToDevice));
+    h->stepIndex = steps;
+    return 0;
+}
+
 extern "C" int dfr2d_set_register(dfr2d_handle *h, int reg, const double *Q) {
     if (!h || !Q || reg < 0 || reg > 4) return 1;
     h->qfaceValid = false;
@@ -1479,12 +1522,13 @@ static int multi_step_impl(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info
         }
     }
 #undef MULTI_ALL
+    if (!info) return 0;                              // like dfr2d_step: no host synchronisation without info
     int rc = 0;
     for (int g = n - 1; g >= 0; g--) {
         dfr2d_step_info tmp{};
         int r = dfr2d_step_finish(hs[g], &tmp);       // synchronises partition g; surfaces "NAN found"
         if (r) rc = r;
-        if (g == 0 && info) {
+        if (g == 0) {
             *info = tmp;
             if (host_finished(hs[0])) info->finished = 1;
         }

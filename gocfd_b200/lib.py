@@ -52,7 +52,8 @@ EXPORTS = [
     "dfr2d_wavespeed_buffer", "dfr2d_stage_prepare", "dfr2d_stage_edges", "dfr2d_stage_update",
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
-    "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
+    "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
+    "dfr2d_set_clock", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -113,6 +114,9 @@ def load():
     lib.dfr2d_peer_connect.argtypes = [H, C.c_void_p, C.c_int]
     lib.dfr2d_stage_wave.argtypes = [H, C.c_int]
     lib.dfr2d_peer_enable.argtypes = [H, C.c_int]
+    lib.dfr2d_multi_set_state.argtypes = [C.POINTER(H), C.c_int, _dp]
+    lib.dfr2d_multi_get_state.argtypes = [C.POINTER(H), C.c_int, _dp]
+    lib.dfr2d_set_clock.argtypes = [H, C.c_double, C.c_int64]
     lib.dfr2d_multi_step_profile.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
@@ -202,6 +206,24 @@ def multi_step(devs, nsteps=1, sync=True):
     return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
 
 
+def multi_set_state(devs, q):
+    lib = load()
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    assert q.shape == devs[0].shape
+    arr = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    if lib.dfr2d_multi_set_state(arr, len(devs), _d(q)) != 0:
+        raise Dfr2dError("dfr2d_multi_set_state failed: %s" % "; ".join(lib.dfr2d_last_error(d.h).decode() for d in devs))
+
+
+def multi_get_state(devs, out=None):
+    lib = load()
+    q = np.zeros(devs[0].shape) if out is None else out
+    arr = (C.c_void_p * len(devs))(*[d.h for d in devs])
+    if lib.dfr2d_multi_get_state(arr, len(devs), _d(q)) != 0:
+        raise Dfr2dError("dfr2d_multi_get_state failed: %s" % "; ".join(lib.dfr2d_last_error(d.h).decode() for d in devs))
+    return q
+
+
 PEER_BLOB_BYTES = 1280
 PROFILE_PHASES = ("sensor+prepare+pack/put", "interior edges", "halo wait + boundary/cut edges (+ RT gradient)",
                   "viscous edges", "wave put+gather", "element update")
@@ -288,6 +310,9 @@ class Dfr2d:
         info = StepInfo()
         self._ck(self.lib.dfr2d_step(self.h, nsteps, C.byref(info) if sync else None))
         return {"time": info.time, "dt": info.dt, "steps": int(info.steps), "finished": bool(info.finished)}
+
+    def set_clock(self, time=0.0, steps=0):
+        self._ck(self.lib.dfr2d_set_clock(self.h, float(time), int(steps)))
 
     def rhs(self, rk=0):
         out = np.zeros(self.shape)

@@ -129,6 +129,9 @@ const char *dfr2d_last_error(const dfr2d_handle *h); /* h may be NULL: error of 
 int dfr2d_set_state(dfr2d_handle *h, const double *Q);
 int dfr2d_get_state(dfr2d_handle *h, double *Q);
 
+/* c.Time / c.StepCount (euler.go:175-182) as the next dfr2d_step sees them: restart from a saved state, or rewind. */
+int dfr2d_set_clock(dfr2d_handle *h, double time, int64_t steps);
+
 /* nsteps x { RK.Step; Time += GlobalDT; StepCount++ } (euler.go:177-182); stops early when finished.
  * info may be NULL (no host synchronisation at all). */
 int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info);
@@ -220,6 +223,9 @@ int dfr2d_stage_wave(dfr2d_handle *h, int rk);   /* connected hosts: put + gathe
  * the edges that touch no ghost column runs while the halo is in flight.  No host synchronisation inside the call;
  * `info` (may be NULL) is read back from partition 0 at the end.  Results are bitwise those of a single partition. */
 int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info);
+/* c.Q <-> all partitions of this process; the copies of the n devices cross PCIe concurrently */
+int dfr2d_multi_set_state(dfr2d_handle **hs, int n, const double *Q);
+int dfr2d_multi_get_state(dfr2d_handle **hs, int n, double *Q);
 /* One profiled step: ms_out[n][5 stages][6 phases] = CUDA-event duration of {sensor+prepare+pack/put, interior edges,
  * halo wait + boundary/cut edges (+ RT gradient), viscous edges, wave put+gather, element update} on each partition. */
 int dfr2d_multi_step_profile(dfr2d_handle **hs, int n, float *ms_out);

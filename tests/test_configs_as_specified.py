@@ -1,0 +1,174 @@
+"""The configurations of BASELINE.json exactly as the reference ships them, on the device, against
+the C restatement of the stage: the same mesh files, the same input-file settings, run as long as the reference runs them.
+
+  C3  test_cases/Euler2D/shock-tube/{sod-aligned-100pts,sod-aligned-500pts}.su2 + input-wall.yaml / runme.sh at order 4:
+      Roe, global dt, CFL 5, Limiter "persson c0", Kappa 5, to FinalTime 0.2; OutputFinal's Sod comparison on the result.
+  C4  test_cases/Euler2D/naca_12/mesh/nacaAirfoil-base.su2 (K = 10,697) + input-bench.yaml (N=2, Roe, local dt, CFL 1,
+      Minf 0.3, 100 iterations), and the transonic variant of BASELINE.json (M = 0.8, alpha = 2, PerssonC0 Kappa 4.5);
+      residual history every 10 iterations as PrintUpdate reports it; RCM-renumbered 8-partition run.
+Needs a GPU.  The whole module takes about two minutes (the CPU oracle dominates).
+"""
+import numpy as np
+import pytest
+
+from conftest import mesh_path
+from gocfd_b200.host.euler2d import Euler
+from gocfd_b200.host.input_parameters import InputParameters2D
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def rel_l2(a, b):
+    den = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (den if den > 0 else 1.0)
+
+
+def _sod_case(mesh):
+    # shock-tube/input-wall.yaml with runme.sh's per-order override at order 4 (CFL 5, Kappa 5)
+    ip = InputParameters2D(Title="Test Case", CFL=5.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=4, FinalTime=0.2,
+                           LocalTimeStepping=False, MaxIterations=80000, Gamma=1.4, Limiter="persson c0", Kappa=5.0)
+    return Euler(ip, mesh_path(mesh))
+
+
+def _check_sod_profile(c, q, t):
+    """OutputFinal's shock-tube post-processing (euler.go:221-250): centre-line samples against SOD_Exact."""
+    from gocfd_b200.host.sod_shock_tube import SODExact, SODShockTube
+    st = SODShockTube(4 * c.DFR.K // 5, c.DFR)
+    st.interpolate_fields(q)
+    sod = SODExact(t)
+    x = st.XLocations
+    mid = (x > sod.x2 + 0.02) & (x < sod.x3 - 0.04)          # between rarefaction tail and (smeared) contact
+    post = (x > sod.x3 + 0.03) & (x < sod.x4 - 0.02)         # between contact and shock
+    assert mid.sum() > 5 and post.sum() > 5
+    assert np.abs(st.Rho[mid] - sod.rho_middle).max() < 0.02 * sod.rho_middle
+    assert np.abs(st.Rho[post] - sod.post_s.rho).max() < 0.02 * sod.post_s.rho
+    level = 0.5 * (sod.post_s.rho + 0.125)
+    xs, rs = x[x > sod.x3 + 0.02], st.Rho[x > sod.x3 + 0.02]
+    x_shock = xs[np.argmax(rs < level)]
+    assert abs(x_shock - sod.x4) < 0.02
+    exact = np.array([sod.getx(xx)[0] for xx in x])
+    assert np.abs(st.Rho - exact).mean() < 0.01
+
+
+def test_c3_sod_100pts_to_final_time_against_the_oracle():
+    """C3 on sod-aligned-100pts.su2 (K = 2,398) to FinalTime 0.2: 712 RK steps with an active sensor.  Device and C oracle
+    are compared every 100 steps (state, time, step count, residual maxima) and at the end; then the Sod profile check."""
+    from gocfd_b200 import lib
+    from oracle.c_oracle import COracleSolver
+    c = _sod_case("sod-aligned-100pts.su2")
+    assert c.DFR.K == 2398 and c.problem.Dissipation
+    dev, ora = lib.Dfr2d(c.problem), COracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    a = b = None
+    for _ in range(100):
+        a, b = dev.step(100), ora.step(100)
+        assert a["steps"] == b["steps"] and a["finished"] == b["finished"]
+        assert abs(a["time"] - b["time"]) <= 1e-13 * max(b["time"], 1e-30)
+        assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+        np.testing.assert_allclose(dev.residual(), ora.residual(), rtol=1e-8, atol=1e-12)
+        if a["finished"]:
+            break
+    assert a["finished"] and a["time"] == pytest.approx(0.2, abs=1e-14) and 600 < a["steps"] < 900
+    q = dev.get_state()
+    assert np.isfinite(q).all()
+    assert dev.get_field(1).max() > 0.5                       # SigmaScalar: the sensor is on at the shock
+    _check_sod_profile(c, q, a["time"])
+    dev.close()
+    ora.close()
+
+
+def test_c3_sod_500pts_to_final_time():
+    """C3 on sod-aligned-500pts.su2 (K = 6,016): the first 150 steps against the C oracle at 1e-11, then the device alone
+    to FinalTime 0.2 (the CPU oracle would need minutes), checked through OutputFinal's exact-solution comparison."""
+    from gocfd_b200 import lib
+    from oracle.c_oracle import COracleSolver
+    c = _sod_case("sod-aligned-500pts.su2")
+    assert c.DFR.K == 6016
+    dev, ora = lib.Dfr2d(c.problem), COracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    for _ in range(3):
+        a, b = dev.step(50), ora.step(50)
+        assert a["steps"] == b["steps"] and abs(a["time"] - b["time"]) <= 1e-13 * b["time"]
+        assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    ora.close()
+    info = a
+    while not info["finished"]:
+        info = dev.step(200)
+        assert info["steps"] < 20000
+    assert info["time"] == pytest.approx(0.2, abs=1e-14)
+    q = dev.get_state()
+    assert np.isfinite(q).all()
+    _check_sod_profile(c, q, info["time"])
+    dev.close()
+
+
+def _naca_bench_ip(**kw):
+    # naca_12/input-bench.yaml:1-11
+    base = dict(Title="Test Case", CFL=1.0, FluxType="Roe", InitType="Freestream", PolynomialOrder=2, FinalTime=20.0, Minf=0.3,
+                Gamma=1.4, Alpha=0.0, LocalTimeStepping=True, MaxIterations=100)
+    base.update(kw)
+    return InputParameters2D(**base)
+
+
+@pytest.mark.parametrize("variant", ["input-bench.yaml", "transonic PerssonC0"])
+def test_c4_naca_base_mesh_residual_history(variant):
+    """C4 on nacaAirfoil-base.su2 for the 100 iterations input-bench.yaml asks for: residual maxima (PrintUpdate,
+    euler.go:821-835) and state every 10 iterations against the C oracle."""
+    from gocfd_b200 import lib
+    from oracle.c_oracle import COracleSolver
+    ip = _naca_bench_ip() if variant == "input-bench.yaml" else _naca_bench_ip(Minf=0.8, Alpha=2.0, Limiter="PerssonC0", Kappa=4.5)
+    c = Euler(ip, mesh_path("nacaAirfoil-base.su2"))
+    assert c.DFR.K == 10697 and bool(c.problem.Dissipation) == (variant != "input-bench.yaml")
+    dev, ora = lib.Dfr2d(c.problem), COracleSolver(c.problem)
+    dev.set_state(c.Q)
+    ora.set_state(c.Q)
+    history = []
+    for it in range(10):
+        a, b = dev.step(10), ora.step(10)
+        assert a["steps"] == b["steps"] == 10 * (it + 1)
+        ra, rb = np.array(dev.residual()), np.array(ora.residual())
+        history.append(ra)
+        np.testing.assert_allclose(ra, rb, rtol=1e-8, atol=1e-13)
+        assert rel_l2(dev.get_state(), ora.get_state()) < TOL
+    assert a["finished"] and b["finished"]                    # MaxIterations 100
+    assert np.isfinite(np.array(history)).all() and np.abs(history[-1]).max() > 0
+    dev.close()
+    ora.close()
+
+
+def test_c4_naca_base_mesh_rcm_8_partitions():
+    """The same C4 run on the RCM-renumbered mesh split into 8 partitions (dfr2d_multi_step; partitions spread over the
+    available GPUs): bitwise the single-partition run of the renumbered problem, 1e-11 from the oracle, and far fewer cut
+    edges than the mesh generator's numbering."""
+    import torch
+    from gocfd_b200 import lib
+    from gocfd_b200.host import readfiles as rf
+    from oracle.c_oracle import COracleSolver
+    mesh = rf.read_mesh(mesh_path("nacaAirfoil-base.su2"))
+    ip = _naca_bench_ip(Minf=0.8, Alpha=2.0, Limiter="PerssonC0", Kappa=4.5, MaxIterations=30)
+    c0 = Euler(ip, mesh)
+    c1 = Euler(ip, rf.renumber_elements(mesh, lib.rcm_order(c0.problem)))
+    ndev = torch.cuda.device_count()
+    devs = [lib.Dfr2d(c1.problem, n_parts=8, part=r, device=r % ndev) for r in range(8)]
+    cut_rcm = sum(sum(d.halo_counts()[0]) for d in devs)
+    cut_orig = sum(sum(lib.Plan(c0.problem, 8, r).send_counts) for r in range(8))
+    assert cut_rcm < 0.5 * cut_orig
+    lib.multi_set_state(devs, c1.Q)
+    one, ora = lib.Dfr2d(c1.problem), COracleSolver(c1.problem)
+    one.set_state(c1.Q)
+    ora.set_state(c1.Q)
+    for _ in range(3):
+        a, b, o = lib.multi_step(devs, 10), one.step(10), ora.step(10)
+        assert a["steps"] == b["steps"] == o["steps"]
+        q = lib.multi_get_state(devs)
+        assert np.array_equal(q, one.get_state())
+        assert rel_l2(q, ora.get_state()) < TOL
+        np.testing.assert_allclose(one.residual(), ora.residual(), rtol=1e-8, atol=1e-13)
+    assert a["finished"]
+    for d in devs + [one]:
+        d.close()
+    ora.close()
