@@ -229,10 +229,12 @@ func (s *Solver) PlotField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []float32 
 func (s *Solver) Close() { C.dfr2d_destroy(s.h); s.h = nil }
 
 // MultiSolver drives one handle per GPU from a single Go process -- the shape of the reference's controller goroutine
-// (euler.go:408-412): dfr2d_multi_step runs the per-stage protocol of include/dfr2d.h over all partitions, moving the
-// halo bytes with cudaMemcpyPeerAsync ordered by CUDA events and taking the wave-speed maximum with a peer-reading
-// kernel; nothing synchronises with the host inside the call.  (One process per GPU with NCCL, as bench.py does it
-// through torch.distributed, uses the dfr2d_stage_* / dfr2d_exchange_* calls instead.)
+// (euler.go:408-412): dfr2d_multi_step runs the per-stage protocol of include/dfr2d.h over all partitions.  The partitions
+// exchange Q_Face halo rows, shared-vertex maxima, DissX/DissY edge rows and the wave-speed maxima among themselves:
+// pack kernels store straight into the partner GPU's mailbox over NVLink and raise an arrival flag, unpack kernels wait
+// on the flag (gocfd_b200/csrc/dfr2d_peer.cuh) -- no host synchronisation, no collective library.  Measured on 2 B200:
+// 1.39e11 DOF-stage-updates/s at config C5, bitwise equal to one partition (profiles/r02b_*).  (One process per GPU
+// uses dfr2d_peer_export / dfr2d_peer_connect and then plain dfr2d_step on every partition.)
 type MultiSolver struct {
 	Parts []*Solver
 }
@@ -261,11 +263,28 @@ func (m *MultiSolver) Step(nsteps int) (time, dt float64, steps int, finished bo
 	return float64(info.time), float64(info.dt), int(info.steps), info.finished != 0
 }
 
+func (m *MultiSolver) handles() []*C.dfr2d_handle {
+	hs := make([]*C.dfr2d_handle, len(m.Parts))
+	for g, s := range m.Parts {
+		hs[g] = s.h
+	}
+	return hs
+}
+
+// SetState scatters c.Q4 to all partitions; the copies to the different GPUs cross PCIe concurrently.
+func (m *MultiSolver) SetState(c *Euler2D.Euler) {
+	g := m.Parts[0]
+	for n := 0; n < 4; n++ {
+		copy(g.global[n*g.np*g.k:(n+1)*g.np*g.k], c.Q4[n].DataP)
+	}
+	hs := m.handles()
+	g.check(C.dfr2d_multi_set_state(&hs[0], C.int(len(hs)), d(g.global)), "dfr2d_multi_set_state")
+}
+
 // GetState gathers every partition's columns into c.Q4 (each handle writes only its own element range).
 func (m *MultiSolver) GetState(c *Euler2D.Euler) {
-	for _, s := range m.Parts {
-		s.check(C.dfr2d_get_state(s.h, d(m.Parts[0].global)), "dfr2d_get_state")
-	}
+	hs := m.handles()
+	m.Parts[0].check(C.dfr2d_multi_get_state(&hs[0], C.int(len(hs)), d(m.Parts[0].global)), "dfr2d_multi_get_state")
 	g := m.Parts[0]
 	for n := 0; n < 4; n++ {
 		copy(c.Q4[n].DataP, g.global[n*g.np*g.k:(n+1)*g.np*g.k])
