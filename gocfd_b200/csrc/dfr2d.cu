@@ -96,6 +96,7 @@ struct dfr2d_handle {
     unsigned int *putDone = nullptr;                      // device [3]
     WaveTab waveTab{};
     std::vector<void *> ipcMapped;
+    double kappaGiven = 0.0;          // ip.Kappa as given: c.ShockFinder of the plot path (euler.go:82)
     void *scratch = nullptr;          // call-spanning scratch of residual / plot_field / init_state / rhs (scratch_reserve)
     size_t scratchBytes = 0;
 };
@@ -472,6 +473,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     ph.fs[0] = p->FSFar; ph.fs[1] = p->FSIn; ph.fs[2] = p->FSOut;
     ph.vortex = p->vortex;
     ph.sdKappa = (p->Kappa != 0.0) ? p->Kappa : 5.0;         // dissipation.go:140-147
+    h->kappaGiven = p->Kappa;
     ph.Eps0 = 5.0 / 1.5;                                     // fixed before the kappa override
     ph.S0 = 4.0 / pow((double)(N + 1), 4.0);                 // dissipation.go:500
     ph.Cdiff = 1.0 / (double)((N + 1) * (N + 1));            // euler.go:958-960
@@ -1690,11 +1692,14 @@ extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double
     if (!h || !graph_interp || !out) return 1;
     const int NG = 3 * (1 + h->NpEdge) + h->NpInt;
     if (np_graph != NG) { h->err = "GraphInterp must have 3(1+NpEdge)+NpInt rows (GetRSForGraphMesh)"; return 1; }
-    if (flow_function < 0 || flow_function > 13) {
-        h->err = "only the GetFlowFunction family (Density..Entropy, fluids.go:209-223) is evaluated on the device";
+    if ((flow_function < 0 || flow_function > 13) && flow_function != 100) {
+        h->err = "dfr2d_plot_field evaluates the GetFlowFunction family (Density..Entropy = 0..13, fluids.go:209-223) and "
+                 "ShockFunction (100); the epsilon fields are dfr2d_epsilon_field";
         return 1;
     }
     CK(cudaSetDevice(h->device));
+    if (flow_function == 100)
+        if (int rc = ensure_ops(h)) return rc;
     const size_t nOut = (size_t)h->K * NG;
     const size_t giBytes = ((size_t)NG * h->NpInt * sizeof(double) + 255) & ~(size_t)255;
     if (int rc = scratch_reserve(h, giBytes + std::max<size_t>(nOut, 1) * sizeof(float))) return rc;
@@ -1705,10 +1710,27 @@ extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double
     pa.K = h->K; pa.Kp = h->Kp; pa.ff = flow_function;
     pa.q = h->q[0]; pa.gi = gi; pa.out = dout;
     pa.gamma = h->ph.fs[0].Gamma; pa.Pinf = h->ph.fs[0].Pinf; pa.QQinf = h->ph.fs[0].QQinf;
+    pa.kappa = h->ph.dissipation ? h->kappaGiven : 2.0;      // c.ShockFinder (euler.go:82) or NewAliasShockFinder(2) (plot.go:36)
     const int blocks = (h->K + kPlotThreads - 1) / kPlotThreads;
     DISPATCH_N(h->N, (k_plot_field<NN><<<blocks, kPlotThreads, 0, h->stream>>>(pa)));
     if (int rc = launch_check(h, "k_plot_field")) return rc;
     CK(cudaMemcpyAsync(out + (size_t)h->k0 * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int dfr2d_epsilon_field(dfr2d_handle *h, int c0, double *out) {
+    if (!h || !out) return 1;
+    if (!h->ph.dissipation) { h->err = "the epsilon fields exist only with the PerssonC0 limiter (c.Dissipation != nil)"; return 1; }
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
+    const size_t n = (size_t)h->NpFlux * std::max(h->K, 1);
+    if (int rc = scratch_reserve(h, n * sizeof(double))) return rc;
+    double *tmp = (double *)h->scratch;
+    DISPATCH_N(h->N, (k_epsilon_field<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(h->K, h->Kp, c0, h->ds.epsk, h->ds.epsV, h->ds.etov, tmp)));
+    if (int rc = launch_check(h, "k_epsilon_field")) return rc;
+    CK(cudaMemcpy2DAsync(out + h->k0, (size_t)h->Kglobal * sizeof(double), tmp, (size_t)h->K * sizeof(double),
+                         (size_t)h->K * sizeof(double), (size_t)h->NpFlux, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

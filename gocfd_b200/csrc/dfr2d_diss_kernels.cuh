@@ -376,7 +376,34 @@ struct PlotArgs {
     const double *gi;      // [NpGraph][NpInt] row-major (device copy of DFR.GraphInterp)
     float *out;            // [K][NpGraph]
     double gamma, Pinf, QQinf;
+    double kappa;          // ShockFunction: sf.Kappa of the finder GetPlotField uses (plot.go:31-37)
 };
+
+// ModeAliasShockFinder.ShockIndicator (DG2D/dfr_shock_capturing.go:189-235) on one element's density: the L2 moment of
+// U - Clipper U with the diagonal of the mass matrix, Persson's ramp with S0 = 4 / N^4 (N, not N+1: this is the plot
+// path's indicator, not UpdateShockFinderSigma).  Clipper = I - D (the resident operator set carries D).
+template <int N>
+__device__ __forceinline__ double shock_indicator(const double (&u)[Dim<N>::NpInt], double kappa) {
+    constexpr int NI = Dim<N>::NpInt;
+    const Ops<N> &op = ops<N>();
+    double num = 0.0, den = 0.0;
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        double clipped = 0.0;
+#pragma unroll
+        for (int j = 0; j < NI; j++) clipped = fma(((i == j) ? 1.0 : 0.0) - op.D[i][j], u[j], clipped);
+        const double t1 = u[i] - clipped, mass = op.M[i][i];
+        num += mass * (t1 * t1);
+        den += mass * (u[i] * u[i]);
+    }
+    const double Se = log10(num / den);
+    const double S0 = 4.0 / pow((double)N, 4.0);
+    const double left = S0 - kappa, right = S0 + kappa;
+    if (Se < left) return 0.0;
+    if (Se <= right) return 0.5 * (1.0 + sin(3.14159265358979323846 * (0.5 / kappa) * (Se - S0)));
+    if (Se > right) return 1.0;
+    return 0.0;                                    // NaN: none of the reference's switch cases fires
+}
 
 __device__ __forceinline__ double flow_function(int pf, double gamma, double Pinf, double QQinf, double rho, double rhoU,
                                                 double rhoV, double E) {
@@ -416,11 +443,19 @@ __global__ void __launch_bounds__(kPlotThreads) k_plot_field(PlotArgs a) {
     const int kb = blockIdx.x * kPlotThreads, k = kb + threadIdx.x;
     if (k < a.K) {
         double f[NI];
+        if (a.ff == 100) {                          // ShockFunction: the element's indicator at every node (plot.go:30-47)
 #pragma unroll
-        for (int i = 0; i < NI; i++) {
-            const size_t o = (size_t)i * a.Kp + k;
-            const size_t plane = (size_t)NI * a.Kp;
-            f[i] = flow_function(a.ff, a.gamma, a.Pinf, a.QQinf, a.q[o], a.q[plane + o], a.q[2 * plane + o], a.q[3 * plane + o]);
+            for (int i = 0; i < NI; i++) f[i] = a.q[(size_t)i * a.Kp + k];
+            const double m = shock_indicator<N>(f, a.kappa);
+#pragma unroll
+            for (int i = 0; i < NI; i++) f[i] = m;
+        } else {
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const size_t o = (size_t)i * a.Kp + k;
+                const size_t plane = (size_t)NI * a.Kp;
+                f[i] = flow_function(a.ff, a.gamma, a.Pinf, a.QQinf, a.q[o], a.q[plane + o], a.q[2 * plane + o], a.q[3 * plane + o]);
+            }
         }
         double g[NG];
 #pragma unroll
@@ -480,6 +515,25 @@ __global__ void k_init_state(InitArgs a) {
         }
 #pragma unroll
         for (int n = 0; n < 4; n++) a.q[n * plane + (size_t)i * a.Kp + k] = Q[n];
+    }
+}
+
+// EpsilonDissipation / EpsilonDissipationC0 plot fields (plot.go:48-53; dissipation.go:377-395): [NpFlux][K] doubles, not
+// interpolated -- the element's scalar epsilon at every RT point, or Bary . (vertex epsilon) as InterpolateEpsilonSigma
+// left it (dissipation.go:219-242).
+template <int N>
+__global__ void k_epsilon_field(int K, int Kp, int c0, const double *epsk, const double *epsV, const int *etov, double *out) {
+    constexpr int NF = Dim<N>::NpFlux;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    if (!c0) {
+        const double e = epsk[k];
+#pragma unroll
+        for (int i = 0; i < NF; i++) out[(size_t)i * K + k] = e;
+    } else {
+        const double e0 = epsV[etov[k]], e1 = epsV[etov[(size_t)Kp + k]], e2 = epsV[etov[2 * (size_t)Kp + k]];
+#pragma unroll
+        for (int i = 0; i < NF; i++) out[(size_t)i * K + k] = eps_row<N>(i, e0, e1, e2);
     }
 }
 

@@ -62,15 +62,17 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 // A partner that never arrives (crashed process, mismatched stage sequence) must not hang the GPU: after kPeerTimeoutNs
-// the waiter gives up and raises err (DevScalars.nanFlag = 2, reported by dfr2d_step_finish as a failed exchange).
-constexpr unsigned long long kPeerTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;
+// the waiter gives up and raises err (DevScalars.nanFlag = 2, reported by dfr2d_step_finish as a failed exchange); every
+// later wait of this partition then returns at once, so a dead partner costs one time-out, not one per kernel.
+constexpr unsigned long long kPeerTimeoutNs = 5ull * 1000ull * 1000ull * 1000ull;
 __device__ __forceinline__ void wait_flag(const unsigned long long *p, unsigned long long seq, int *err) {
     if (ld_acquire_sys(p) >= seq) return;
+    if (err && *(volatile int *)err == 2) return;        // an earlier wait already gave up: do not stack time-outs
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(p) < seq) {
         __nanosleep(100);
         if (global_ns() - t0 > kPeerTimeoutNs) {
-            if (err) *err = 2;
+            if (err) *(volatile int *)err = 2;
             return;
         }
     }

@@ -53,7 +53,7 @@ EXPORTS = [
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
-    "dfr2d_set_clock", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
+    "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -117,6 +117,7 @@ def load():
     lib.dfr2d_multi_set_state.argtypes = [C.POINTER(H), C.c_int, _dp]
     lib.dfr2d_multi_get_state.argtypes = [C.POINTER(H), C.c_int, _dp]
     lib.dfr2d_set_clock.argtypes = [H, C.c_double, C.c_int64]
+    lib.dfr2d_epsilon_field.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_multi_step_profile.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
@@ -346,6 +347,13 @@ class Dfr2d:
             out = np.zeros((self.p.K, gi.shape[0]), dtype=np.float32)
         self._ck(self.lib.dfr2d_plot_field(self.h, int(flow_function), _d(gi), gi.shape[0],
                                            out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def epsilon_field(self, c0=False, out=None):
+        """EpsilonDissipation (c0=False) / EpsilonDissipationC0 (c0=True) plot fields: [NpFlux, K] float64."""
+        if out is None:
+            out = np.zeros((self.p.NpFlux, self.p.K))
+        self._ck(self.lib.dfr2d_epsilon_field(self.h, int(bool(c0)), _d(out)))
         return out
 
     # ---- multi-partition plumbing -------------------------------------------------------

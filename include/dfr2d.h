@@ -161,6 +161,13 @@ int dfr2d_init_state(dfr2d_handle *h, int init_case, int64_t nv, const double *V
  * DG2D/graphics_support.go:80-93).  graph_interp = [np_graph x NpInt] row-major with np_graph = 3(1+NpEdge)+NpInt;
  * out = [K x np_graph] (global element index; own rows only are written). */
 int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_interp, int np_graph, float *out);
+/* flow_function 100 = ShockFunction (plot.go:30-47): ModeAliasShockFinder.ShockIndicator of the element's density
+ * (DG2D/dfr_shock_capturing.go:189-235; Kappa of c.ShockFinder, or 2 without the limiter) at every node, then the same
+ * GraphInterp / vertex-average / float32 path.
+ * The two epsilon fields bypass the interpolation in the reference (plot.go:48-53): out = [NpFlux x K] doubles, global
+ * column index, own columns written.  c0 = 0: EpsilonDissipation = the element's scalar epsilon at every RT point
+ * (dissipation.go:377-390); c0 = 1: EpsilonDissipationC0 = Bary . vertex epsilon as the last stage left it (:392-395). */
+int dfr2d_epsilon_field(dfr2d_handle *h, int c0, double *out);
 
 /* ---- plumbing for one-process-per-GPU hosts (torch.distributed / NCCL) ---------------------
  * The library never calls a collective itself: per stage the host moves the halo bytes and

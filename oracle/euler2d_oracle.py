@@ -291,11 +291,36 @@ def flow_function(fs, q, pf):
     raise ValueError("flow function %d does not go through GetFlowFunction" % pf)
 
 
+FF_ShockFunction, FF_EpsilonDissipation, FF_EpsilonDissipationC0 = 100, 101, 102       # fluids.go:224-226
+
+
+def shock_indicator(p, rho, kappa):
+    """ModeAliasShockFinder.ShockIndicator per element (DG2D/dfr_shock_capturing.go:189-235): moment of U - Clipper U with
+    the mass-matrix diagonal, Persson ramp with S0 = 4 / N^4.  rho = [NpInt, K]."""
+    clipper = np.eye(p.NpInt) - p.D
+    t1 = rho - clipper @ rho
+    mass = np.diag(p.MassMatrix)[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        se = np.log10((mass * t1 * t1).sum(axis=0) / (mass * rho * rho).sum(axis=0))
+        s0 = 4.0 / float(p.N) ** 4 if p.N > 0 else np.inf
+        left, right = s0 - kappa, s0 + kappa
+        sigma = np.zeros(rho.shape[1])
+        mid = (se >= left) & (se <= right)
+        sigma[mid] = 0.5 * (1.0 + np.sin(np.pi * (0.5 / kappa) * (se[mid] - s0)))
+        sigma[se > right] = 1.0
+    return sigma
+
+
 def plot_field(p, q, pf, graph_interp):
     """Euler.GetPlotField for the GetFlowFunction family (plot.go:14-86): node values, GraphInterp product,
     AverageGraphFieldVertices (DG2D/graphics_support2.go:184-199), transpose -> [K, NpGraph]; the AVS writer then
     narrows to float32 (DG2D/graphics_support.go:80-93), which the caller applies."""
-    fld = flow_function(tuple(p.FSFar.as_array()), q, pf)
+    if pf == FF_ShockFunction:
+        # plot.go:30-47: c.ShockFinder (Kappa = ip.Kappa as given, euler.go:82) with the limiter, else NewAliasShockFinder(2)
+        kappa = p.Kappa if p.Dissipation else 2.0
+        fld = np.tile(shock_indicator(p, q[0], kappa), (p.NpInt, 1))
+    else:
+        fld = flow_function(tuple(p.FSFar.as_array()), q, pf)
     field = graph_interp @ fld
     npe = p.NpEdge + 2
     for n_edge in range(3):

@@ -83,9 +83,53 @@ def test_device_plot_field_matches_oracle(n):
         # float64 arithmetic narrowed to float32 at the end on both sides: at most one float32 ulp apart
         np.testing.assert_allclose(got, want.astype(np.float32), rtol=2.5e-7, atol=1e-7)
     with pytest.raises(lib.Dfr2dError):
-        dev.plot_field(100, gi)
+        dev.plot_field(99, gi)
     with pytest.raises(lib.Dfr2dError):
         dev.plot_field(0, gi[:-1])
+    with pytest.raises(lib.Dfr2dError):
+        dev.epsilon_field()                  # no limiter, no epsilon (c.Dissipation == nil)
+    dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+@pytest.mark.parametrize("diss", [False, True])
+def test_device_shock_function_and_epsilon_fields(n, diss):
+    """The plot fields that do not go through GetFlowFunction (plot.go:30-53): ShockFunction (ShockIndicator of the density,
+    Kappa 2 without the limiter, ip.Kappa with it, S0 = 4/N^4) through the GraphInterp path, and -- with the limiter --
+    the two epsilon fields [NpFlux x K] as the last stage left them."""
+    from conftest import mesh_path
+    from gocfd_b200 import lib
+    from gocfd_b200.host.euler2d import Euler
+    from gocfd_b200.host.input_parameters import InputParameters2D
+    from oracle.euler2d_oracle import OracleSolver
+    kw = dict(CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=n, FinalTime=0.2, MaxIterations=100, Gamma=1.4)
+    if diss:
+        kw.update(Limiter="persson c0", Kappa=3.0)
+    c = Euler(InputParameters2D(**kw), mesh_path("sod-aligned-100pts.su2"))
+    p = c.problem
+    x, _ = c.DFR.solution_xy()
+    w = 0.5 * (1.0 - np.tanh((x - 0.503) / (0.006 if n == 1 else 0.003)))
+    q0 = np.stack([c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w for v in range(4)])
+    gi = c.DFR.graph_interp()
+    dev, o = lib.Dfr2d(p), OracleSolver(p)
+    # ShockFunction of a sharp front (no stepping needed: the field is a function of c.Q alone)
+    ws = 0.5 * (1.0 - np.tanh((x - 0.503) / 0.0003))
+    q = np.stack([c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * ws for v in range(4)])
+    dev.set_state(q)
+    want = ora.plot_field(p, q, ora.FF_ShockFunction, gi)
+    got = dev.plot_field(ora.FF_ShockFunction, gi)
+    if n >= 2 and not diss:
+        assert want.max() > 0.1 and want.min() == 0.0       # the front is flagged (Kappa 2), the plateaus are not
+    # sigma is a function of log10 of a ratio of sums: summation order moves it at the 1e-12 level, far below float32
+    np.testing.assert_allclose(got, want.astype(np.float32), rtol=1e-6, atol=1e-6)
+    dev.set_state(q0)
+    o.set_state(q0)
+    dev.step(2), o.step(2)
+    if diss:
+        assert o.EpsilonScalar.max() > 0
+        np.testing.assert_allclose(dev.epsilon_field(False), np.tile(o.EpsilonScalar, (p.NpFlux, 1)), rtol=1e-9, atol=1e-14)
+        np.testing.assert_allclose(dev.epsilon_field(True), o.Epsilon, rtol=1e-9, atol=1e-14)
     dev.close()
 
 
