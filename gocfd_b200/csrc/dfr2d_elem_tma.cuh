@@ -34,8 +34,21 @@ constexpr int kTmaMaxStages = 6;
 template <int N> struct TmaDim {
     static constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
     static constexpr int SE = 36;                                  // row stride of the slabs (doubles): 4 k-rows x 8 n conflict free
-    static constexpr int M1 = (NI + 7) / 8, KI = (NI + 3) / 4, KE = (NF3 + 3) / 4, K1 = 2 * KI + KE;
-    static constexpr int M2 = (NF3 + 7) / 8, K2 = (NI + 3) / 4;
+    static constexpr int M1 = (NI + 7) / 8, KI = (NI + 3) / 4;
+    // Tensor-pipe work is co-limiting with HBM here (ncu: shared FP64/DMMA pipe 65 % busy, profiles/r02c_*), so the zero
+    // padding of the 8 x 8 x 4 tiles is cut where it is cheap:
+    //  * the interior k-steps have 4 KI - NI idle point slots each for Fr and for Fs; the LAST nMoved edge rows ride in
+    //    them (lane fc of k-step 2m / 2m+1 carries edge row NE3k + 2 (4m + fc - NI) [+ 1] instead of a zero), which
+    //    shortens the edge block from ceil(NF3 / 4) to KE k-steps (N=4: 13 -> 12 k-steps of C1);
+    //  * the interpolation operator has NF3 rows: when NF3 mod 8 is 1..4 the ragged last m-tile (N=4: rows 16, 17 of 24) is
+    //    evaluated with plain DFMA on constant-bank operands instead of a mostly empty DMMA tile (48 -> 32 DMMA of C2).
+    static constexpr int padI = 4 * KI - NI;
+    static constexpr int nMoved = (2 * padI < NF3) ? 2 * padI : NF3;
+    static constexpr int NE3k = NF3 - nMoved;                      // edge rows that stay in the edge k-steps
+    static constexpr int KE = (NE3k + 3) / 4, K1 = 2 * KI + KE;
+    static constexpr int remF = NF3 % 8;
+    static constexpr bool tailDfma = remF >= 1 && remF <= 4;
+    static constexpr int M2 = tailDfma ? NF3 / 8 : (NF3 + 7) / 8, NTail = tailDfma ? remF : 0, K2 = (NI + 3) / 4;
     static constexpr int qOff = 0;                                 // [4 NI][SE] stage input
     static constexpr int eOff = 4 * NI * SE;                       // [4 NF3][SE] gathered numerical edge flux (raw)
     static constexpr int gOff = eOff + 4 * NF3 * SE;               // [9][32]: Jdet, Jinv0..3, (+-)IInII0..2, dt
@@ -256,6 +269,12 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsRegs));
         const int group = warp >> 2, wq = warp & 3;
         const int fr = lane >> 2, fc = lane & 3;
+        // Row of the first contraction held by accumulator row fr: bits 0 and 1 of fr swapped (0,2,1,3,4,6,5,7).  The 128-bit
+        // shared-memory accesses of the epilogue are served per quarter warp (fr = 2j, 2j+1; fc = 0..3); with the natural
+        // order the two rows lie 72 words = 8 banks apart and collide 2-way (ncu: 37 % of the shared wavefronts of this
+        // kernel were conflicts, profiles/r01j_*), with the swap they lie 144 words = 16 banks apart: conflict free.  The
+        // operator fragments below are built with the same permutation, nothing else notices.
+        const int frP = (fr & 4) | ((fr & 1) << 1) | ((fr >> 1) & 1);
         const int eB = 8 * wq + fr;                  // B-operand column of this lane
         const int eC = 8 * wq + 2 * fc;              // first of the two accumulator columns of this lane
         constexpr int NFL = Dim<N>::NpFlux;
@@ -265,18 +284,23 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
         double a1[M1][K1], a2[M2][K2];
 #pragma unroll
         for (int mt = 0; mt < M1; mt++) {
-            const int row = 8 * mt + fr;
+            const int row = 8 * mt + frP;
 #pragma unroll
             for (int m = 0; m < KI; m++) {
                 const int p = 4 * m + fc;
-                const bool ok = row < NI && p < NI;
-                a1[mt][2 * m] = ok ? opD[row * NFL + p] : 0.0;
-                a1[mt][2 * m + 1] = ok ? opD[row * NFL + NI + p] : 0.0;
+                if (p < NI) {
+                    a1[mt][2 * m] = row < NI ? opD[row * NFL + p] : 0.0;
+                    a1[mt][2 * m + 1] = row < NI ? opD[row * NFL + NI + p] : 0.0;
+                } else {                // idle point slot: edge rows NE3k + t, NE3k + t + 1 ride here
+                    const int t = 2 * (p - NI);
+                    a1[mt][2 * m] = (row < NI && t < TD::nMoved) ? opD[row * NFL + 2 * NI + TD::NE3k + t] : 0.0;
+                    a1[mt][2 * m + 1] = (row < NI && t + 1 < TD::nMoved) ? opD[row * NFL + 2 * NI + TD::NE3k + t + 1] : 0.0;
+                }
             }
 #pragma unroll
             for (int ke = 0; ke < KE; ke++) {
                 const int r = 4 * ke + fc;
-                a1[mt][2 * KI + ke] = (row < NI && r < NF3) ? opD[row * NFL + 2 * NI + r] : 0.0;
+                a1[mt][2 * KI + ke] = (row < NI && r < TD::NE3k) ? opD[row * NFL + 2 * NI + r] : 0.0;
             }
         }
 #pragma unroll
@@ -323,6 +347,22 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
                         Fr[v] = jd * (j0 * Fx[v] + j1 * Fy[v]);
                         Fs[v] = jd * (j2 * Fx[v] + j3 * Fy[v]);
                     }
+                } else if (TD::nMoved > 0) {
+                    // idle point slot of the last interior k-steps: the numerical flux of edge rows NE3k + t (Fr slot) and
+                    // NE3k + t + 1 (Fs slot), scaled like the edge block below
+                    const int t = 2 * (p - NI);
+                    if (t < TD::nMoved) {
+                        const int r = TD::NE3k + t;
+                        const double scl = pick3((r >= NEd) + (r >= 2 * NEd), sc0, sc1, sc2);
+#pragma unroll
+                        for (int v = 0; v < 4; v++) Fr[v] = sE[(v * NF3 + r) * SE + eB] * scl;
+                    }
+                    if (t + 1 < TD::nMoved) {
+                        const int r = TD::NE3k + t + 1;
+                        const double scl = pick3((r >= NEd) + (r >= 2 * NEd), sc0, sc1, sc2);
+#pragma unroll
+                        for (int v = 0; v < 4; v++) Fs[v] = sE[(v * NF3 + r) * SE + eB] * scl;
+                    }
                 }
 #pragma unroll
                 for (int v = 0; v < 4; v++)
@@ -337,7 +377,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
             for (int ke = 0; ke < KE; ke++) {
                 const int r = 4 * ke + fc;
                 double b[4] = {0.0, 0.0, 0.0, 0.0};
-                if (4 * ke + 3 < NF3 || r < NF3) {
+                if (4 * ke + 3 < TD::NE3k || r < TD::NE3k) {
                     const int le = (r >= NEd) + (r >= 2 * NEd);
                     const double scl = pick3(le, sc0, sc1, sc2);
 #pragma unroll
@@ -358,7 +398,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
             for (int v = 0; v < 4; v++) {
 #pragma unroll
                 for (int mt = 0; mt < M1; mt++) {
-                    const int i = 8 * mt + fr;
+                    const int i = 8 * mt + frP;
                     if (i < NI) {
                         const double rhs0 = c1[v][mt][0] * mo0, rhs1 = c1[v][mt][1] * mo1;
                         const size_t o = ((size_t)v * NI + i) * Kp + k0 + eC;
@@ -400,6 +440,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
             }
             const bool doInterp = a.rhsOut == nullptr && a.qface != nullptr;
             double c2[4][M2][2];
+            double tail[TD::NTail > 0 ? TD::NTail : 1];
             if (doInterp) {
                 __syncwarp();
                 // ---- C2 = FluxEdgeInterp . q_new: next stage's Q_Face ---------------------------------------------
@@ -420,6 +461,19 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
 #pragma unroll
                         for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[mt][ks], b[v]);
                 }
+                // ragged last rows of FluxEdgeInterp by DFMA: lane = (variable, column) of the warp's 8 columns
+                if (TD::NTail > 0) {
+                    const Ops<N> &op = ops<N>();
+                    const double *qv = sQ + ((lane >> 3) * NI) * SE + 8 * wq + (lane & 7);
+#pragma unroll
+                    for (int r = 0; r < TD::NTail; r++) tail[r] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NI; j++) {
+                        const double q = qv[j * SE];
+#pragma unroll
+                        for (int r = 0; r < TD::NTail; r++) tail[r] = fma(op.FEI[8 * M2 + r][j], q, tail[r]);
+                    }
+                }
             }
             // ---- the stage is consumed: hand it back to the producer (generic-proxy accesses ordered before the
             // async-proxy refill), then stream out Q_Face from registers
@@ -436,6 +490,9 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
                             *reinterpret_cast<double2 *>(a.qface + ((size_t)v * NF3 + m) * Kp + k0 + eC) =
                                 make_double2(c2[v][mt][0], c2[v][mt][1]);
                     }
+#pragma unroll
+                for (int r = 0; r < TD::NTail; r++)
+                    a.qface[((size_t)(lane >> 3) * NF3 + 8 * M2 + r) * Kp + k0 + 8 * wq + (lane & 7)] = tail[r];
             }
 #pragma unroll
             for (int t = 0; t < kGroups; t++)       // this group's next tile is kGroups fills further on

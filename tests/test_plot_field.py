@@ -105,11 +105,11 @@ def test_device_shock_function_and_epsilon_fields(n, diss):
     from oracle.euler2d_oracle import OracleSolver
     kw = dict(CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=n, FinalTime=0.2, MaxIterations=100, Gamma=1.4)
     if diss:
-        kw.update(Limiter="persson c0", Kappa=3.0)
+        kw.update(Limiter="persson c0", Kappa=5.0)
     c = Euler(InputParameters2D(**kw), mesh_path("sod-aligned-100pts.su2"))
     p = c.problem
     x, _ = c.DFR.solution_xy()
-    w = 0.5 * (1.0 - np.tanh((x - 0.503) / (0.006 if n == 1 else 0.003)))
+    w = 0.5 * (1.0 - np.tanh((x - 0.503) / (0.004 if n == 1 else 0.002)))
     q0 = np.stack([c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w for v in range(4)])
     gi = c.DFR.graph_interp()
     dev, o = lib.Dfr2d(p), OracleSolver(p)
