@@ -84,6 +84,7 @@ struct dfr2d_handle {
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
+    int tmaCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_TMA_CW)
     int edgePPT = 0;
     // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
     // single IPC handle / peer pointer gives a partner everything it writes
@@ -633,6 +634,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->elemKernel = (N >= 2) ? 5 : 1;
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
     if (const char *ev = getenv("DFR2D_TMA_STAGES")) h->tmaStages = atoi(ev);
+    if (const char *ev = getenv("DFR2D_TMA_CW")) h->tmaCW = atoi(ev) == 12 ? 12 : 8;
     {
         std::vector<double> fr;
         switch (N) {
@@ -997,12 +999,18 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
                 stages = std::min(stages, (rk >= 3 && rhsOut == nullptr) ? 2 : 3);
                 if (h->tmaStages > 1) stages = std::min(std::max(2, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))), h->tmaStages);
                 ta.nStages = stages;
+                // three consumer groups (12 warps, 152 registers each) need a ring of >= 3 stages: every stage but the last
+                // (rk 4: 109 KB per stage, two fit).  DFR2D_TMA_CW=12 selects them; measured A/B in profiles/r02f_*
+                const bool cw12 = h->tmaCW == 12 && (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1)) >= 3;
+                if (cw12) stages = std::max(3, std::min(h->tmaStages > 1 ? h->tmaStages : 3, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))));
+                ta.nStages = stages;
                 const size_t sm = TD::smem_bytes(ta.nExtra, stages);
-                // (a 12-consumer-warp instantiation was measured: 152 registers per consumer spill the operator fragments,
-                // and three groups need a ring of >= 3 stages, which stage 4 does not have -- two groups of four it is)
-                if (!h->smemAttrSet)
+                if (!h->smemAttrSet) {
                     cudaFuncSetAttribute(k_elem_tma<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
-                k_elem_tma<NN, 8><<<std::min(blocks, h->sms), (8 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
+                    cudaFuncSetAttribute(k_elem_tma<NN, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                }
+                if (cw12) k_elem_tma<NN, 12><<<std::min(blocks, h->sms), (12 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
+                else k_elem_tma<NN, 8><<<std::min(blocks, h->sms), (8 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
             });
             h->smemAttrSet = true;
             return launch_check(h, "k_elem_tma");
