@@ -62,17 +62,30 @@ def algorithmic_bytes_visc(n):
     return algorithmic_bytes(n)[0] + 8.0 * (17.6 * np_int + 84 * np_edge + 18)
 
 
-def build_case(nx, ny, n, max_iter=10 ** 9, dissipation=False):
+def build_case(nx, ny, n, max_iter=10 ** 9, dissipation=False, window=None):
+    """The host-side problem of a workload.  window = (n_parts, part): only the partition's window of the mesh is built
+    (gocfd_b200/host/window.py) and the result carries c.window = (K_global, k_offset)."""
     from gocfd_b200.host.euler2d import Euler
     from gocfd_b200.host.input_parameters import InputParameters2D
     from gocfd_b200.host.meshgen import structured_tri_mesh
+    from gocfd_b200.host.window import structured_window_case
     if dissipation:
         # config C3 scaled up: the shipped sod-aligned meshes are [0,1] x [0,~0.1] tubes with in/out/wall tags
         ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=n,
                                FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.0, Limiter="persson c0", Kappa=5.0)
-        mesh = structured_tri_mesh(nx, ny, 0.0, 1.0, 0.0, float(ny) / float(nx),
-                                   side_tags={"left": "in", "right": "out", "top": "wall", "bottom": "wall"})
-        c = Euler(ip, mesh)
+        box = (0.0, 1.0, 0.0, float(ny) / float(nx))
+        mesh_kw = dict(side_tags={"left": "in", "right": "out", "top": "wall", "bottom": "wall"})
+    else:
+        ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n,
+                               FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.1)
+        box = (-10.0, 10.0, -10.0, 10.0)
+        mesh_kw = dict(tag="wall")
+    if window is None:
+        c = Euler(ip, structured_tri_mesh(nx, ny, *box, **mesh_kw))
+        c.window = None
+    else:
+        c, c.window = structured_window_case(lambda m: Euler(ip, m), nx, ny, window[0], window[1], *box, **mesh_kw)
+    if dissipation:
         # a raw jump inside a P4 element undershoots to negative density at the edge points (the reference would
         # NaN-panic as well), so the front is smeared over half an element width and kept off the grid lines
         x, _ = c.DFR.solution_xy()
@@ -80,10 +93,7 @@ def build_case(nx, ny, n, max_iter=10 ** 9, dissipation=False):
         w = 0.5 * (1.0 - np.tanh((x - (0.5 + 0.3 * h)) / (0.5 * h)))
         for v in range(4):
             c.Q[v] = c.FSOut.Qinf[v] + (c.FSIn.Qinf[v] - c.FSOut.Qinf[v]) * w
-        return c
-    ip = InputParameters2D(Title="bench", CFL=1.0, FluxType="Roe", InitType="IVortex", PolynomialOrder=n,
-                           FinalTime=1.0e9, MaxIterations=max_iter, Gamma=1.4, Minf=0.1)
-    return Euler(ip, structured_tri_mesh(nx, ny, tag="wall"))
+    return c
 
 
 class ClockSampler:
@@ -294,18 +304,24 @@ class Runner:
         self.nx, self.ny, self.n = nx, ny, n
         self.diss = workload in DISSIPATION_WORKLOADS
         t0 = time.perf_counter()
-        self.c = build_case(nx, ny, n, dissipation=self.diss)
+        # one process per GPU: every rank builds only its window of the mesh (no global problem anywhere); a single
+        # process (N = 1, or the multi_step driver) owns the whole mesh like the Go host does
+        windowed = world > 1 and args.driver != "multi_step" and not args.global_problem
+        self.c = build_case(nx, ny, n, dissipation=self.diss, window=(world, rank) if windowed else None)
         self.p = self.c.problem
         assert bool(self.p.Dissipation) == self.diss
         self.build_s = time.perf_counter() - t0
         self.stream = torch.cuda.current_stream()
-        self.dof_per_step = 4 * self.p.NpInt * self.p.K * 5
+        self.k_global = self.c.window[0] if self.c.window else self.p.K
+        self.k_off = self.c.window[1] if self.c.window else 0
+        self.dof_per_step = 4 * self.p.NpInt * self.k_global * 5
+        self._global_case = None
 
     # ---- per-process partition (drivers peer / nccl) ---------------------------------------------------------------
     def open(self):
         torch, dist, lib = self.torch, self.dist, self.lib
         t0 = time.perf_counter()
-        self.dev = lib.Dfr2d(self.p, n_parts=self.world, part=self.rank, device=self.local_rank)
+        self.dev = lib.Dfr2d(self.p, n_parts=self.world, part=self.rank, device=self.local_rank, window=self.c.window)
         self.dev.set_stream(self.stream.cuda_stream)
         self.k0, self.k1 = self.dev.partition_range()
         self.create_s = time.perf_counter() - t0
@@ -465,7 +481,7 @@ class Runner:
         k_local = self.k1 - self.k0
         if self.diss:
             bv = algorithmic_bytes_visc(n)
-            ach = bv * p.K * 5 * steps / (ms * 1e-3) / 1e9
+            ach = bv * self.k_global * 5 * steps / (ms * 1e-3) / 1e9
             return {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad_pipe [DMMA], k_visc_edge, element kernel)",
                     "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
                     "peak_source": peak_src, "bytes_per_element_stage": bv, "phase_ms": phases, "per_gpu": True}
@@ -483,8 +499,8 @@ class Runner:
                              "note": "interior-edge kernel only; the boundary / cut-edge list runs in the next phase"},
              "phase_ms": phases,
              "whole_stage": {"bytes_per_element": b_total,
-                             "achieved_per_gpu": b_total * p.K * 5 * steps / (ms * 1e-3) / 1e9 / world,
-                             "frac": b_total * p.K * 5 * steps / (ms * 1e-3) / 1e9 / peak / world}}
+                             "achieved_per_gpu": b_total * self.k_global * 5 * steps / (ms * 1e-3) / 1e9 / world,
+                             "frac": b_total * self.k_global * 5 * steps / (ms * 1e-3) / 1e9 / peak / world}}
         prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if world == 1 and os.path.exists(prof):
             try:
@@ -520,7 +536,7 @@ class Runner:
         el = self.reduce_max(time.perf_counter() - t0)
         qb = 4 * self.p.NpInt * (self.k1 - self.k0) * 8
         # checksum of the state after exactly `steps` steps from the initial condition: identical at every N
-        own = self.q_host[:, :, self.k0:self.k1]
+        own = self.q_host[:, :, self.k0 - self.k_off:self.k1 - self.k_off]
         sq = self.reduce_list([float((own[v] * own[v]).sum()) for v in range(4)], self.dist.ReduceOp.SUM if self.world > 1 else None)
         return ({"value": self.dof_per_step * steps / el, "unit": "DOF-stage-updates/s",
                  "h2d_bytes_per_step": qb / steps, "d2h_bytes_per_step": qb / steps + 40,
@@ -535,11 +551,15 @@ class Runner:
     def multi_step_run(self, n_gpus, steps, warmup):
         torch, lib = self.torch, self.lib
         t0 = time.perf_counter()
-        devs = [lib.Dfr2d(self.p, n_parts=n_gpus, part=g, device=g) for g in range(n_gpus)]
+        gc = self.c if self.c.window is None else build_case(self.nx, self.ny, self.n, dissipation=self.diss)
+        gp = gc.problem
+        build_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        devs = [lib.Dfr2d(gp, n_parts=n_gpus, part=g, device=g) for g in range(n_gpus)]
         create_s = time.perf_counter() - t0
-        q_host_t = torch.empty((4, self.p.NpInt, self.p.K), dtype=torch.float64, pin_memory=True)
+        q_host_t = torch.empty((4, gp.NpInt, gp.K), dtype=torch.float64, pin_memory=True)
         q_host = q_host_t.numpy()
-        q_host[...] = self.c.Q
+        q_host[...] = gc.Q
         for d in devs:
             d.set_state(q_host)
         lib.multi_step(devs, warmup, sync=True)
@@ -567,7 +587,7 @@ class Runner:
         prof = lib.multi_step_profile(devs)                     # [n][5][phases] ms
         sync_all()
         # end to end with host buffers
-        q_host[...] = self.c.Q
+        q_host[...] = gc.Q
         for d in devs:
             d.set_clock(0.0, 0)
         t0 = time.perf_counter()
@@ -584,7 +604,7 @@ class Runner:
         torch.cuda.set_device(self.local_rank)
         per_stage = prof.sum(axis=2)                             # [n][5]
         return {"value": self.dof_per_step * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches),
-                "host_issue_ms_per_step": t_issue * 1e3 / steps, "create_s": create_s,
+                "host_issue_ms_per_step": t_issue * 1e3 / steps, "create_s": create_s, "host_problem_build_s": build_s,
                 "e2e": {"value": self.dof_per_step * steps / el, "unit": "DOF-stage-updates/s",
                         "what": "one process: dfr2d_multi_set_state + %d x dfr2d_multi_step(1, info) + dfr2d_multi_get_state" % steps},
                 "checksum": {"after_steps": steps, "time": info["time"], "l2": l2},
@@ -599,9 +619,9 @@ class Runner:
 def workload_text(r):
     if r.diss:
         return ("%s: Sod shock tube, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, PerssonC0 sensor + artificial "
-                "dissipation, In/Out/Wall boundaries" % (r.workload, r.nx, r.ny, r.p.K, r.n, r.p.NpInt))
+                "dissipation, In/Out/Wall boundaries" % (r.workload, r.nx, r.ny, r.k_global, r.n, r.p.NpInt))
     return ("%s: isentropic vortex, %dx%dx2=%d triangles, N=%d (NpInt=%d), Roe flux, global dt, IVortex+Riemann boundaries"
-            % (r.workload, r.nx, r.ny, r.p.K, r.n, r.p.NpInt))
+            % (r.workload, r.nx, r.ny, r.k_global, r.n, r.p.NpInt))
 
 
 def measure(args, workload, rank, world, local_rank, gloo, steps, warmup, full):
@@ -625,7 +645,7 @@ def measure(args, workload, rank, world, local_rank, gloo, steps, warmup, full):
     p = r.p
     out = {
         "value": r.dof_per_step * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": launches,
-        "element_stages_per_s": p.K * 5 * steps / (ms * 1e-3), "us_per_element_iteration": ms * 1e3 / steps / p.K,
+        "element_stages_per_s": r.k_global * 5 * steps / (ms * 1e-3), "us_per_element_iteration": ms * 1e3 / steps / r.k_global,
         "driver": driver, "e2e": e2e, "checksum": checksum, "roofline": roof, "clocks": clocks,
         "config": {"workload": workload_text(r),
                    "partition": "PartitionMap.Split1D element ranges over %d GPU(s)" % world,
@@ -634,7 +654,9 @@ def measure(args, workload, rank, world, local_rank, gloo, steps, warmup, full):
                                 "nccl": "host-driven stage API, NCCL all_to_all_single + all_reduce(MAX)"}[driver],
                    "l2": "no flush needed: per-GPU working set %.2f GB >> 126 MB L2"
                          % ((5 * 4 * p.NpInt + 12 * p.NpEdge + 6 * p.NpEdge) * 8 * k_local / 1e9),
-                   "setup_s": {"host_problem_build": r.build_s, "dfr2d_create": r.create_s}},
+                   "setup_s": {"host_problem_build": r.build_s, "dfr2d_create": r.create_s,
+                               "host_problem": ("window of %d of %d elements per rank (dfr2d_create_window)" % (p.K, r.k_global))
+                               if r.c.window else "global"}},
     }
     if world > 1 and r.peer_error:
         out["config"]["peer_error"] = r.peer_error
@@ -671,6 +693,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the C2 / C3 lines under 'also'")
     ap.add_argument("--no-compare", action="store_true", help="skip the nccl / multi_step comparison drivers at N > 1")
+    ap.add_argument("--global-problem", action="store_true", help="N > 1: every rank builds the global problem (round 1 behaviour)")
     ap.add_argument("--sample-only", action="store_true", help="reference arm: only the bounded sample, not the full mesh")
     ap.add_argument("--cpu-full-worker", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -28,6 +28,8 @@ static thread_local std::string g_create_error;
 struct dfr2d_handle {
     int N = 0, device = 0, nParts = 1, part = 0;
     int64_t Kglobal = 0, k0 = 0, k1 = 0;
+    int64_t winOff = 0;               // dfr2d_create_window: global id of the first element the problem arrays describe
+    int64_t hostOff = 0, hostPitch = 0;   // host-side [rows][hostPitch] arrays: this partition's columns start at hostOff
     int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
     int NpInt = 0, NpEdge = 0, NpFlux = 0;
     Phys ph{};
@@ -232,6 +234,7 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
 struct dfr2d_plan {
     int N = 0, nParts = 1, part = 0;
     int64_t Kglobal = 0, k0 = 0, k1 = 0;
+    int64_t kOff = 0;                      // window mode: the problem arrays describe elements [kOff, kOff + p->K) only
     int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
     std::vector<int> ekL, ekR, emeta, etoe, sendElem, sendRow0, recvCol, recvRow0, bndList;
     std::vector<double> enx, eny, eoohk, eooLen, bpx, bpy, Jdet, Jinv, IInII;
@@ -249,11 +252,20 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     pl.N = N;
     const int NEd = N + 2;
     // ---- partition (utils.PartitionMap, parallelism.go:179-190) ------------------------------
-    pl.Kglobal = p->K;
-    split1d(p->K, pl.nParts, pl.part, &pl.k0, &pl.k1);
+    // The problem arrays may describe the whole mesh (kOff = 0, Kglobal = p->K) or a WINDOW of it: elements
+    // [kOff, kOff + p->K) of a mesh of Kglobal elements, which must contain the partition's own range and every element
+    // that shares an edge (with the limiter: a vertex) with it.  Element indices inside the arrays (edge_kL / edge_kR,
+    // rows of Jdet, EToV, ...) are window-local; vertex ids stay global.  Everything below works on GLOBAL element ids
+    // kg and indexes the arrays with kg - kOff.
+    if (pl.Kglobal <= 0) pl.Kglobal = p->K;
+    const int64_t kOff = pl.kOff, Kg = pl.Kglobal, Kw = p->K;
+    split1d(Kg, pl.nParts, pl.part, &pl.k0, &pl.k1);
     const int64_t k0 = pl.k0, k1 = pl.k1;
     pl.K = (int)(k1 - k0);
+    if (k0 < kOff || k1 > kOff + Kw) { pl.err = "the window does not contain the partition's own element range"; return 1; }
     auto mine = [&](int64_t k) { return k >= k0 && k < k1; };
+    auto eL = [&](int64_t e) -> int64_t { return (int64_t)p->edge_kL[e] + kOff; };
+    auto eR = [&](int64_t e) -> int64_t { return (p->edge_nconn[e] == 2) ? (int64_t)p->edge_kR[e] + kOff : -1; };
 
     // local edges = every edge touching an owned element; remote sides become ghost columns
     struct LE { int64_t ge; int l, r; };
@@ -271,15 +283,15 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
         return pl.K + g;
     };
     for (int64_t e = 0; e < p->NE; e++) {
-        const int64_t kl = p->edge_kL[e], kr = (p->edge_nconn[e] == 2) ? p->edge_kR[e] : -1;
+        const int64_t kl = eL(e), kr = eR(e);
         if (!(mine(kl) || (kr >= 0 && mine(kr)))) continue;
         led.push_back({e, 0, 0});
     }
     // ghosts are numbered in global-edge order so that both sides of a cut agree on the message order
     for (auto &le : led) {
         const int64_t e = le.ge;
-        le.l = local_col(p->edge_kL[e]);
-        le.r = (p->edge_nconn[e] == 2) ? local_col(p->edge_kR[e]) : -1;
+        le.l = local_col(eL(e));
+        le.r = (p->edge_nconn[e] == 2) ? local_col(eR(e)) : -1;
     }
     pl.G = (int)ghostGlobal.size();
     pl.Kp = ((pl.K + pl.G + 31) / 32) * 32;
@@ -321,7 +333,7 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
         const int64_t e = led[s].ge;
         pl.edgeGlobal[s] = e;
         if (pl.nParts == 1) slotOfEdgeDense[e] = s; else slotOfGlobalEdge.emplace(e, s);
-        const int64_t kl = p->edge_kL[e];
+        const int64_t kl = eL(e) - kOff;          // window row of the owner
         const int numL = p->edge_numL[e], numR = p->edge_numR[e];
         ekL[s] = led[s].l;
         emeta[s] = (numL & 3) | ((numR & 3) << 2) | ((p->edge_bc[e] & 15) << 4);
@@ -358,13 +370,14 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     etoe.assign((size_t)3 * Kp, 0);
     for (int k = 0; k < K; k++) {
         const int64_t kg = k0 + k;
-        Jdet[k] = p->Jdet[kg];
-        for (int c = 0; c < 4; c++) Jinv[(size_t)c * Kp + k] = p->Jinv[kg * 4 + c];
+        const int64_t kw = kg - kOff;
+        Jdet[k] = p->Jdet[kw];
+        for (int c = 0; c < 4; c++) Jinv[(size_t)c * Kp + k] = p->Jinv[kw * 4 + c];
         for (int le = 0; le < 3; le++) {
-            IInII[(size_t)le * Kp + k] = p->IInII[kg + p->K * le];
-            const int64_t e = p->EtoEdge[kg * 3 + le];
+            IInII[(size_t)le * Kp + k] = p->IInII[kw + p->K * le];
+            const int64_t e = p->EtoEdge[kw * 3 + le];
             const int s = slot_of(e);
-            etoe[(size_t)le * Kp + k] = (p->edge_kL[e] == kg) ? s : -1 - s;
+            etoe[(size_t)le * Kp + k] = (eL(e) == kg) ? s : -1 - s;
         }
     }
 
@@ -378,13 +391,14 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
         for (int s = 0; s < pl.NE; s++) {
             const int64_t e = led[s].ge;
             if (p->edge_nconn[e] != 2) continue;
-            const int64_t kl = p->edge_kL[e], kr = p->edge_kR[e];
+            const int64_t kl = eL(e), kr = eR(e);
             if (mine(kl) && mine(kr)) continue;
             const bool lMine = mine(kl);
             const int64_t remote = lMine ? kr : kl;
             Cut c;
-            c.peer = bucket_of(remote, p->K, pl.nParts);
-            c.ge = e;
+            c.peer = bucket_of(remote, Kg, pl.nParts);
+            c.ge = kl * 4 + p->edge_numL[e];       // global key of the edge (owner element, owner's edge number): both
+                                                   // sides of a cut order their messages by it, whatever window they see
             c.myCol = lMine ? led[s].l : led[s].r;
             c.myNum = lMine ? p->edge_numL[e] : p->edge_numR[e];
             c.ghCol = lMine ? led[s].r : led[s].l;
@@ -417,15 +431,16 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     if (pl.nParts > 1 && p->dissipation) {
         std::vector<int> firstPart((size_t)p->NV, -1);
         std::vector<std::pair<int64_t, int>> multi;      // (vertex, partition) for vertices touched by >= 2 partitions
-        for (int pt = 0; pt < pl.nParts; pt++) {
-            int64_t lo, hi;
-            split1d(p->K, pl.nParts, pt, &lo, &hi);
-            for (int64_t k = lo; k < hi; k++)
-                for (int v = 0; v < 3; v++) {
-                    const int64_t vid = p->EToV[k * 3 + v];
-                    if (firstPart[vid] < 0) firstPart[vid] = pt;
-                    else if (firstPart[vid] != pt) multi.emplace_back(vid, pt);
-                }
+        // (ascending global element id = partition by partition: the same visiting order as the reference's per-partition
+        // loops; in window mode only the window's elements are seen, which by contract include every element touching a
+        // vertex of this partition)
+        for (int64_t kw = 0; kw < Kw; kw++) {
+            const int pt = bucket_of(kw + kOff, Kg, pl.nParts);
+            for (int v = 0; v < 3; v++) {
+                const int64_t vid = p->EToV[kw * 3 + v];
+                if (firstPart[vid] < 0) firstPart[vid] = pt;
+                else if (firstPart[vid] != pt) multi.emplace_back(vid, pt);
+            }
         }
         std::sort(multi.begin(), multi.end());
         multi.erase(std::unique(multi.begin(), multi.end()), multi.end());
@@ -488,7 +503,10 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // ---- partition plan (host only) -------------------------------------------------------------
     dfr2d_plan pl;
     pl.nParts = h->nParts; pl.part = h->part;
+    pl.kOff = h->winOff; pl.Kglobal = h->Kglobal;           // (0, 0) unless dfr2d_create_window
     if (int rc = build_plan(p, pl)) { h->err = pl.err; return rc; }
+    h->hostPitch = p->K;                                    // host arrays of set/get_state etc. have the problem's columns
+    h->hostOff = pl.k0 - pl.kOff;
     h->Kglobal = pl.Kglobal; h->k0 = pl.k0; h->k1 = pl.k1;
     h->K = pl.K; h->G = pl.G; h->Kp = pl.Kp; h->NE = pl.NE; h->NEp = pl.NEp; h->NV = pl.NV; h->NBP = pl.NBP;
     h->sendCounts = pl.sendCounts; h->recvCounts = pl.recvCounts;
@@ -565,7 +583,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         std::vector<int> etov((size_t)3 * Kp, 0);
         std::vector<double> hk((size_t)Kp, 1.0);
         for (int k = 0; k < K; k++) {
-            const int64_t kg = k0 + k;
+            const int64_t kg = k0 + k - pl.kOff;            // row of the problem arrays
             for (int v = 0; v < 3; v++) etov[(size_t)v * Kp + k] = p->EToV[kg * 3 + v];
             hk[k] = p->EdgeLenMax[kg] / np12;
         }
@@ -575,8 +593,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         std::vector<double> nxk((size_t)3 * Kp, 0.0), nyk((size_t)3 * Kp, 0.0);
         for (int k = 0; k < K; k++)
             for (int le = 0; le < 3; le++) {
-                nxk[(size_t)le * Kp + k] = p->FaceNormX[(k0 + k) + p->K * le];
-                nyk[(size_t)le * Kp + k] = p->FaceNormY[(k0 + k) + p->K * le];
+                nxk[(size_t)le * Kp + k] = p->FaceNormX[(k0 + k - pl.kOff) + p->K * le];
+                nyk[(size_t)le * Kp + k] = p->FaceNormY[(k0 + k - pl.kOff) + p->K * le];
             }
         DissBuffers &d = h->ds;
         if (int rc = dev_upload(h, &d.etov, etov)) return rc;
@@ -677,8 +695,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
             const double oojd = 1.0 / pl.Jdet[k];
             for (int le = 0; le < 3; le++) {
                 const double iin = pl.IInII[(size_t)le * Kp + k];
-                mxy[(size_t)(2 * le) * Kp + k] = oojd * p->FaceNormX[(k0 + k) + p->K * le] * iin;
-                mxy[(size_t)(2 * le + 1) * Kp + k] = oojd * p->FaceNormY[(k0 + k) + p->K * le] * iin;
+                mxy[(size_t)(2 * le) * Kp + k] = oojd * p->FaceNormX[(k0 + k - pl.kOff) + p->K * le] * iin;
+                mxy[(size_t)(2 * le + 1) * Kp + k] = oojd * p->FaceNormY[(k0 + k - pl.kOff) + p->K * le] * iin;
             }
         }
         if (int rc = dev_upload(h, &h->gradMxy, mxy)) return rc;
@@ -687,12 +705,17 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     return 0;
 }
 
-extern "C" int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int device, dfr2d_handle **out) {
+static int create_common(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part, int device,
+                         dfr2d_handle **out) {
     if (!p || !out) { g_create_error = "null argument"; return 1; }
     if (p->N < 0 || p->N > DFR2D_MAX_ORDER) { g_create_error = "polynomial order out of range 0..4"; return 1; }
-    if (n_parts < 1 || part < 0 || part >= n_parts || p->K < n_parts) { g_create_error = "bad partition request"; return 1; }
+    if (n_parts < 1 || part < 0 || part >= n_parts || K_global < n_parts || k_offset < 0 || k_offset + p->K > K_global) {
+        g_create_error = "bad partition request";
+        return 1;
+    }
     dfr2d_handle *h = new dfr2d_handle();
     h->N = p->N; h->device = device; h->nParts = n_parts; h->part = part;
+    h->Kglobal = K_global; h->winOff = k_offset;
     int rc = create_impl(h, p);
     if (rc) {
         g_create_error = h->err;
@@ -703,11 +726,21 @@ extern "C" int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int d
     return 0;
 }
 
+extern "C" int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int device, dfr2d_handle **out) {
+    return create_common(p, p ? p->K : 0, 0, n_parts, part, device, out);
+}
+
+// Partition-local set-up: `p` describes only the window [k_offset, k_offset + p->K) of a mesh of K_global elements.
+extern "C" int dfr2d_create_window(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part,
+                                   int device, dfr2d_handle **out) {
+    return create_common(p, K_global, k_offset, n_parts, part, device, out);
+}
+
 // ---- state I/O -------------------------------------------------------------------------------------
 static int copy_in(dfr2d_handle *h, double *dst, const double *Q) {
     CK(cudaSetDevice(h->device));
     const size_t rows = (size_t)4 * h->NpInt;
-    CK(cudaMemcpy2DAsync(dst, (size_t)h->Kp * sizeof(double), Q + h->k0, (size_t)h->Kglobal * sizeof(double),
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->Kp * sizeof(double), Q + h->hostOff, (size_t)h->hostPitch * sizeof(double),
                          (size_t)h->K * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -715,7 +748,7 @@ static int copy_in(dfr2d_handle *h, double *dst, const double *Q) {
 static int copy_out(dfr2d_handle *h, const double *src, double *Q) {
     CK(cudaSetDevice(h->device));
     const size_t rows = (size_t)4 * h->NpInt;
-    CK(cudaMemcpy2DAsync(Q + h->k0, (size_t)h->Kglobal * sizeof(double), src, (size_t)h->Kp * sizeof(double),
+    CK(cudaMemcpy2DAsync(Q + h->hostOff, (size_t)h->hostPitch * sizeof(double), src, (size_t)h->Kp * sizeof(double),
                          (size_t)h->K * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -741,10 +774,10 @@ static int multi_copy(dfr2d_handle **hs, int n, double *Q, bool in) {
         const size_t rows = (size_t)4 * h->NpInt;
         if (in) {
             h->qfaceValid = false;
-            CK(cudaMemcpy2DAsync(h->q[0], (size_t)h->Kp * sizeof(double), Q + h->k0, (size_t)h->Kglobal * sizeof(double),
+            CK(cudaMemcpy2DAsync(h->q[0], (size_t)h->Kp * sizeof(double), Q + h->hostOff, (size_t)h->hostPitch * sizeof(double),
                                  (size_t)h->K * sizeof(double), rows, cudaMemcpyHostToDevice, h->stream));
         } else {
-            CK(cudaMemcpy2DAsync(Q + h->k0, (size_t)h->Kglobal * sizeof(double), h->q[0], (size_t)h->Kp * sizeof(double),
+            CK(cudaMemcpy2DAsync(Q + h->hostOff, (size_t)h->hostPitch * sizeof(double), h->q[0], (size_t)h->Kp * sizeof(double),
                                  (size_t)h->K * sizeof(double), rows, cudaMemcpyDeviceToHost, h->stream));
         }
     }
@@ -892,7 +925,12 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
     int ppt = h->edgePPT;
     if (ppt <= 0) ppt = (h->NE < 64 * h->sms * 256) ? 1 : h->N + 2;
     if ((h->N + 2) % ppt != 0) ppt = h->N + 2;
-    if (ppt != h->N + 2 && h->ph.localDT && (part & 1)) CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
+    // the boundary / cut-edge list is short (O(sqrt K) edges): one point per thread there, or a few dozen CTAs walk whole
+    // edges through the BC transcendental functions one point after the other (measured at C5: 57 us for 8,000 edges)
+    int pptList = (h->nBnd < 64 * h->sms * 256 && h->edgePPT <= 0) ? 1 : ppt;
+    if ((h->N + 2) % pptList != 0) pptList = h->N + 2;
+    if ((ppt != h->N + 2 || (h->edgeSplit && pptList != h->N + 2)) && h->ph.localDT && (part & 1))
+        CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
     a.list = nullptr; a.nlist = 0;
 #define EDGE_LAUNCH(KERN)                                                                      \
     DISPATCH_N(h->N, {                                                                          \
@@ -919,9 +957,12 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
         }
         if (!(part & 2) || h->nBnd == 0) return 0;
         a.list = h->bndList; a.nlist = h->nBnd;
-        const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
+        {
+            const int ppt = pptList;       // (EDGE_LAUNCH dispatches on `ppt`)
+            const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
 #define KB(NN_, P_) k_edge<NN_, P_><<<bb, 256, 0, h->stream>>>(a)
-        EDGE_LAUNCH(KB);
+            EDGE_LAUNCH(KB);
+        }
         return launch_check(h, "k_edge(boundary)");
     }
     if (!(part & 2)) return 0;          // single generic kernel: everything happens in the second part
@@ -1665,7 +1706,7 @@ extern "C" int dfr2d_get_field(dfr2d_handle *h, int which, double *out) {
         default: break;
     }
     if (!src) { h->err = "field not available for this configuration"; return 1; }
-    CK(cudaMemcpyAsync(out + h->k0, src, (size_t)h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out + h->hostOff, src, (size_t)h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1685,7 +1726,7 @@ extern "C" int dfr2d_init_state(dfr2d_handle *h, int init_case, int64_t nv, cons
     CK(cudaMemcpyAsync(vy, VY, (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(rs, R, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(rs + h->NpInt, S, (size_t)h->NpInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(etov, EToV + 3 * h->k0, (size_t)3 * h->K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(etov, EToV + 3 * h->hostOff, (size_t)3 * h->K * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     InitArgs ia{};
     ia.K = h->K; ia.Kp = h->Kp; ia.npInt = h->NpInt; ia.initCase = init_case;
     ia.vx = vx; ia.vy = vy; ia.etov = etov; ia.r = rs; ia.s = rs + h->NpInt; ia.q = h->q[0]; ia.ph = h->ph;
@@ -1722,7 +1763,7 @@ extern "C" int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double
     const int blocks = (h->K + kPlotThreads - 1) / kPlotThreads;
     DISPATCH_N(h->N, (k_plot_field<NN><<<blocks, kPlotThreads, 0, h->stream>>>(pa)));
     if (int rc = launch_check(h, "k_plot_field")) return rc;
-    CK(cudaMemcpyAsync(out + (size_t)h->k0 * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(out + (size_t)h->hostOff * NG, dout, nOut * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1737,7 +1778,7 @@ extern "C" int dfr2d_epsilon_field(dfr2d_handle *h, int c0, double *out) {
     double *tmp = (double *)h->scratch;
     DISPATCH_N(h->N, (k_epsilon_field<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(h->K, h->Kp, c0, h->ds.epsk, h->ds.epsV, h->ds.etov, tmp)));
     if (int rc = launch_check(h, "k_epsilon_field")) return rc;
-    CK(cudaMemcpy2DAsync(out + h->k0, (size_t)h->Kglobal * sizeof(double), tmp, (size_t)h->K * sizeof(double),
+    CK(cudaMemcpy2DAsync(out + h->hostOff, (size_t)h->hostPitch * sizeof(double), tmp, (size_t)h->K * sizeof(double),
                          (size_t)h->K * sizeof(double), (size_t)h->NpFlux, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
@@ -1791,14 +1832,24 @@ extern "C" int dfr2d_wavespeed_buffer(dfr2d_handle *h, void **p) {
 extern "C" int64_t dfr2d_launch_count(const dfr2d_handle *h) { return h ? h->launches : 0; }
 
 // ---- host-only plan API (CPU tests of the multi-partition bookkeeping) ---------------------------------------
-extern "C" int dfr2d_plan_create(const dfr2d_problem *p, int n_parts, int part, dfr2d_plan **out) {
-    if (!p || !out || n_parts < 1 || part < 0 || part >= n_parts || p->K < n_parts) { g_create_error = "bad plan request"; return 1; }
+static int plan_create_common(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part, dfr2d_plan **out) {
+    if (!p || !out || n_parts < 1 || part < 0 || part >= n_parts || K_global < n_parts || k_offset < 0 || k_offset + p->K > K_global) {
+        g_create_error = "bad plan request";
+        return 1;
+    }
     dfr2d_plan *pl = new dfr2d_plan();
-    pl->nParts = n_parts; pl->part = part;
+    pl->nParts = n_parts; pl->part = part; pl->Kglobal = K_global; pl->kOff = k_offset;
     int rc = build_plan(p, *pl);
     if (rc) { g_create_error = pl->err; delete pl; return rc; }
     *out = pl;
     return 0;
+}
+extern "C" int dfr2d_plan_create(const dfr2d_problem *p, int n_parts, int part, dfr2d_plan **out) {
+    return plan_create_common(p, p ? p->K : 0, 0, n_parts, part, out);
+}
+extern "C" int dfr2d_plan_create_window(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part,
+                                        dfr2d_plan **out) {
+    return plan_create_common(p, K_global, k_offset, n_parts, part, out);
 }
 extern "C" void dfr2d_plan_destroy(dfr2d_plan *pl) { delete pl; }
 extern "C" int dfr2d_plan_sizes(const dfr2d_plan *pl, int64_t out[8]) {

@@ -53,7 +53,7 @@ EXPORTS = [
     "dfr2d_step_finish", "dfr2d_launch_count", "dfr2d_stage_sensor", "dfr2d_stage_visc", "dfr2d_stage_edges_interior",
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
-    "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
+    "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_create_window", "dfr2d_plan_create_window", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -71,6 +71,8 @@ def load():
     lib = C.CDLL(LIB_PATH)
     H = C.c_void_p
     lib.dfr2d_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.dfr2d_create_window.argtypes = [C.POINTER(ProblemStruct), C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    lib.dfr2d_plan_create_window.argtypes = [C.POINTER(ProblemStruct), C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(H)]
     lib.dfr2d_destroy.argtypes = [H]
     lib.dfr2d_destroy.restype = None
     lib.dfr2d_last_error.argtypes = [H]
@@ -261,13 +263,18 @@ class Dfr2dError(RuntimeError):
 class Dfr2d:
     """One partition of the device solver.  Same surface as the oracle's OracleSolver."""
 
-    def __init__(self, problem, n_parts=1, part=0, device=0):
+    def __init__(self, problem, n_parts=1, part=0, device=0, window=None):
+        """window = (K_global, k_offset): `problem` describes only elements [k_offset, k_offset + problem.K) of the mesh
+        (dfr2d_create_window); host arrays then have the window's columns."""
         self.lib = load()
         self.p = problem
         self.shape = (4, problem.NpInt, problem.K)
         s, keep = problem_struct(problem)
         self.h = C.c_void_p()
-        rc = self.lib.dfr2d_create(C.byref(s), n_parts, part, device, C.byref(self.h))
+        if window is None:
+            rc = self.lib.dfr2d_create(C.byref(s), n_parts, part, device, C.byref(self.h))
+        else:
+            rc = self.lib.dfr2d_create_window(C.byref(s), int(window[0]), int(window[1]), n_parts, part, device, C.byref(self.h))
         del keep
         if rc != 0:
             raise Dfr2dError("dfr2d_create failed (%d): %s" % (rc, self.lib.dfr2d_last_error(None).decode()))
@@ -442,11 +449,14 @@ class Dfr2d:
 class Plan:
     """Host-only partition plan of one (n_parts, part): integer tables only, no CUDA needed."""
 
-    def __init__(self, problem, n_parts, part):
+    def __init__(self, problem, n_parts, part, window=None):
         lib = load()
         s, keep = problem_struct(problem)
         h = C.c_void_p()
-        rc = lib.dfr2d_plan_create(C.byref(s), n_parts, part, C.byref(h))
+        if window is None:
+            rc = lib.dfr2d_plan_create(C.byref(s), n_parts, part, C.byref(h))
+        else:
+            rc = lib.dfr2d_plan_create_window(C.byref(s), int(window[0]), int(window[1]), n_parts, part, C.byref(h))
         del keep
         if rc != 0:
             raise Dfr2dError("dfr2d_plan_create failed (%d): %s" % (rc, lib.dfr2d_last_error(None).decode()))

@@ -122,6 +122,18 @@ typedef struct dfr2d_handle dfr2d_handle;
  * n_parts = 1 is the whole mesh on one GPU.  Mirrors the tail of NewEuler + NewRungeKuttaSSP.
  */
 int dfr2d_create(const dfr2d_problem *p, int n_parts, int part, int device, dfr2d_handle **out);
+/*
+ * Partition-local set-up: the same, but `p` describes only a WINDOW of the mesh -- the elements
+ * [k_offset, k_offset + p->K) of a mesh of K_global elements -- so that no process has to materialise the global
+ * problem of an 8M-element run.  The window must contain the partition's own PartitionMap range and every element that
+ * shares an edge (with the PerssonC0 limiter: a vertex) with it.  Inside `p`, element indices (edge_kL, edge_kR, the
+ * rows of Jdet / Jinv / EToV / EtoEdge, the column stride of FaceNorm / IInII) are window-local; the edge table lists at
+ * least every edge touching an own element; vertex ids (EToV) and p->NV stay global.  Host arrays of set_state /
+ * get_state / get_field / plot_field then have the WINDOW's columns ([..][p->K]).  Results are bitwise those of
+ * dfr2d_create on the global problem (tests/test_window.py).
+ */
+int dfr2d_create_window(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part, int device,
+                        dfr2d_handle **out);
 void dfr2d_destroy(dfr2d_handle *h);
 const char *dfr2d_last_error(const dfr2d_handle *h); /* h may be NULL: error of the last failed create on this thread */
 
@@ -242,6 +254,7 @@ int dfr2d_multi_step_profile(dfr2d_handle **hs, int n, float *ms_out);
  * PartitionEdgesByK (parallelism.go:179-190) plus the ghost/halo lists that replace the goroutines' shared memory. */
 typedef struct dfr2d_plan dfr2d_plan;
 int dfr2d_plan_create(const dfr2d_problem *p, int n_parts, int part, dfr2d_plan **out);
+int dfr2d_plan_create_window(const dfr2d_problem *p, int64_t K_global, int64_t k_offset, int n_parts, int part, dfr2d_plan **out);
 void dfr2d_plan_destroy(dfr2d_plan *pl);
 /* out = {k_begin, k_end, n_ghost_columns, padded_columns, n_local_edges, padded_edges, n_cut_edges, n_boundary_edges} */
 int dfr2d_plan_sizes(const dfr2d_plan *pl, int64_t out[8]);
