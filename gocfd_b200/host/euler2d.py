@@ -302,7 +302,7 @@ class Euler:
         rate = elapsed * 1e6 / float(self.DFR.K * max(steps, 1))
         out("\nRate of execution = %8.5f us/(element*iteration) over %d iterations" % (rate, steps))
         if output_dir is not None:
-            from .output_final import output_final
+            from host_standin.output_final import output_final     # post-processing stays host-side (stand-in)
             output_final(self, self.Q, mesh_file=mesh_file, outdir=output_dir, out=out)
         return steps, elapsed
 

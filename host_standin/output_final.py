@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from .readfiles import BC_Wall
+from gocfd_b200.host.readfiles import BC_Wall
 from .sod_shock_tube import SODShockTube, shocktube_files
 
 # FlowFunction numbering of fluids.go:199-232 (the GetFlowFunction family is 0..13)
@@ -130,7 +130,7 @@ def wall_plot_data(c, q, field_names=None):
 
 def output_final(c, q, mesh_file="", outdir=".", out=print):
     """Write the files of OutputFinal for `c.Case`; returns the list of paths written."""
-    from .euler2d import FREESTREAM, SHOCKTUBE
+    from gocfd_b200.host.euler2d import FREESTREAM, SHOCKTUBE
     written = []
     if c.Case == SHOCKTUBE:
         st = SODShockTube(4 * c.DFR.K // 5, c.DFR)          # euler.go:771

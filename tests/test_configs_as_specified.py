@@ -34,7 +34,7 @@ def _sod_case(mesh):
 
 def _check_sod_profile(c, q, t):
     """OutputFinal's shock-tube post-processing (euler.go:221-250): centre-line samples against SOD_Exact."""
-    from gocfd_b200.host.sod_shock_tube import SODExact, SODShockTube
+    from host_standin.sod_shock_tube import SODExact, SODShockTube
     st = SODShockTube(4 * c.DFR.K // 5, c.DFR)
     st.interpolate_fields(q)
     sod = SODExact(t)

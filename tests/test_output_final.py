@@ -4,10 +4,10 @@ import numpy as np
 import pytest
 
 from conftest import mesh_path
-from gocfd_b200.host import output_final as of
+from host_standin import output_final as of
 from gocfd_b200.host.euler2d import Euler
 from gocfd_b200.host.input_parameters import InputParameters2D
-from gocfd_b200.host.sod_shock_tube import SODExact, SODShockTube, shocktube_files
+from host_standin.sod_shock_tube import SODExact, SODShockTube, shocktube_files
 
 
 def test_sod_exact_reference_kat():

@@ -21,7 +21,7 @@ from conftest import mesh_path
 from gocfd_b200.host.euler2d import Euler
 from gocfd_b200.host.input_parameters import InputParameters2D
 from gocfd_b200.host.meshgen import structured_tri_mesh
-from gocfd_b200.host.sod_shock_tube import SODExact, SODShockTube
+from host_standin.sod_shock_tube import SODExact, SODShockTube
 from oracle.c_oracle import COracleSolver
 from oracle.euler2d_oracle import avg_flux, flux_calc_base, lax_flux, riemann_bc, roe_er_flux, roe_flux
 

@@ -88,7 +88,7 @@ def test_windowed_partitions_run_bitwise_like_the_global_problem(diss):
     """3 partitions, each created from its own window (dfr2d_create_window), stepped with dfr2d_multi_step: the state equals
     the single-partition run of the global problem bit for bit; plot / per-element fields come back in window columns."""
     from gocfd_b200 import lib
-    ip = _ip(diss, PolynomialOrder=3)
+    ip = _ip(diss, PolynomialOrder=2 if diss else 3)
     c = Euler(ip, structured_tri_mesh(16, 13))
     if diss:
         c.Q[0] *= 1.0 + 0.3 * np.sign(np.sin(7.0 * c.DFR.solution_xy()[0]))
