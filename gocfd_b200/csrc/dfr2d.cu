@@ -55,6 +55,7 @@ struct dfr2d_handle {
     int64_t sendTotal = 0, recvTotal = 0;
     double *sendBuf = nullptr, *recvBuf = nullptr;
     int *sendElem = nullptr, *sendRow0 = nullptr, *recvCol = nullptr, *recvRow0 = nullptr;
+    int *cutSlot = nullptr, *cutSide = nullptr;
     int nSendEdges = 0, nRecvEdges = 0;
     int ePer = 0;                     // doubles per cut edge in the Q_Face message (4 NpEdge, +3 vertex eps with dissipation)
     // dissipation exchanges (multi-partition): shared-vertex max merge and DissX/DissY edge rows
@@ -73,8 +74,8 @@ struct dfr2d_handle {
     int pfTiles = 0;
     int elemKernel = 4;               // 1: row-per-thread DFMA, 2: split-row DFMA, 3: DMMA, 4: pipelined DMMA (default)
     double *mmaFrags = nullptr;
-    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 2: DMMA k_grad_mma, 3: pipelined persistent DMMA
-                                      // k_grad_pipe (DFR2D_GRAD_KERNEL)
+    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 3: pipelined persistent DMMA k_grad_pipe
+                                      // (DFR2D_GRAD_KERNEL; 2 was round 1's one-tile-per-CTA DMMA kernel, retired)
     double *gradTable = nullptr, *gradMxy = nullptr;
     int gradMG = 3;                   // m-tiles per accumulation group of k_grad_pipe (DFR2D_GRAD_MG = 2 | 3)
     int dissElemKernel = 1;           // element kernel of the PerssonC0 path: 1 = k_elem<N,true> (DFMA), 3 = k_elem_mma_diss
@@ -237,6 +238,7 @@ struct dfr2d_plan {
     int64_t kOff = 0;                      // window mode: the problem arrays describe elements [kOff, kOff + p->K) only
     int K = 0, G = 0, Kp = 0, NE = 0, NEp = 0, NV = 0, NBP = 0;
     std::vector<int> ekL, ekR, emeta, etoe, sendElem, sendRow0, recvCol, recvRow0, bndList;
+    std::vector<int> cutSlot, cutSide;     // per cut edge (message order): local edge slot, my side (0 = I own it)
     std::vector<double> enx, eny, eoohk, eooLen, bpx, bpy, Jdet, Jinv, IInII;
     std::vector<int64_t> ghostGlobal, edgeGlobal, sendCounts, recvCounts;
     int nSendEdges = 0, nRecvEdges = 0;
@@ -386,7 +388,7 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     pl.recvCounts.assign(pl.nParts, 0);
     auto &sendElem = pl.sendElem; auto &sendRow0 = pl.sendRow0; auto &recvCol = pl.recvCol; auto &recvRow0 = pl.recvRow0;
     if (pl.nParts > 1) {
-        struct Cut { int peer; int64_t ge; int myCol, myNum, ghCol, ghNum; };
+        struct Cut { int peer; int64_t ge; int myCol, myNum, ghCol, ghNum, slot, side; };
         std::vector<Cut> cuts;
         for (int s = 0; s < pl.NE; s++) {
             const int64_t e = led[s].ge;
@@ -403,6 +405,8 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
             c.myNum = lMine ? p->edge_numL[e] : p->edge_numR[e];
             c.ghCol = lMine ? led[s].r : led[s].l;
             c.ghNum = lMine ? p->edge_numR[e] : p->edge_numL[e];
+            c.slot = s;
+            c.side = lMine ? 0 : 1;
             cuts.push_back(c);
             pl.bndList.push_back(s);      // evaluated with the boundary edges after the halo exchange, so that the
                                           // interior-edge kernel can run while the halo is in flight
@@ -419,6 +423,8 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
             sendRow0.push_back(c.myNum * NEd);
             recvCol.push_back(c.ghCol);
             recvRow0.push_back(c.ghNum * NEd);
+            pl.cutSlot.push_back(c.slot);
+            pl.cutSide.push_back(c.side);
         }
         pl.nSendEdges = pl.nRecvEdges = (int)cuts.size();
         pl.sendTotal = pl.recvTotal = per * (int64_t)cuts.size();
@@ -561,7 +567,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         // wave inbox[32][2 slots][2]]; every region starts on a 16-word boundary
         auto up16 = [](int64_t w) { return (w + 15) & ~(int64_t)15; };
         const int64_t nE = h->recvTotal, nV = ph.dissipation ? 2 * (int64_t)h->nVtx : 0,
-                      nD = ph.dissipation ? (int64_t)8 * NEd * h->nRecvEdges : 0;
+                      nD = ph.dissipation ? (int64_t)4 * NEd * h->nRecvEdges : 0;
         h->mbOff[DFR2D_XCHG_EDGE] = 0;
         h->mbOff[DFR2D_XCHG_VERTEX] = up16(nE);
         h->mbOff[DFR2D_XCHG_DISS] = h->mbOff[DFR2D_XCHG_VERTEX] + up16(nV);
@@ -577,6 +583,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_upload(h, &h->sendRow0, sendRow0)) return rc;
         if (int rc = dev_upload(h, &h->recvCol, recvCol)) return rc;
         if (int rc = dev_upload(h, &h->recvRow0, recvRow0)) return rc;
+        if (int rc = dev_upload(h, &h->cutSlot, pl.cutSlot)) return rc;
+        if (int rc = dev_upload(h, &h->cutSide, pl.cutSide)) return rc;
     }
     if (ph.dissipation) {
         // vertices: keep global numbering (vertex arrays are small next to the element arrays)
@@ -609,15 +617,17 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_alloc(h, &d.epsV, (size_t)h->NV + 3 * (size_t)h->G)) return rc;
         CK(cudaMemset(d.epsV, 0, ((size_t)h->NV + 3 * (size_t)h->G) * sizeof(double)));
         if (h->nParts > 1) {
-            for (int pt = 0; pt < h->nParts; pt++) h->dissCounts[pt] = (h->sendCounts[pt] / h->ePer) * 8 * NEd;
+            for (int pt = 0; pt < h->nParts; pt++) h->dissCounts[pt] = (h->sendCounts[pt] / h->ePer) * 4 * NEd;
             if (int rc = dev_upload(h, &h->vtxList, pl.vtxList)) return rc;
             if (int rc = dev_alloc(h, &h->vSendBuf, (size_t)2 * h->nVtx)) return rc;
             h->vRecvBuf = (double *)(h->mailbox + h->mbOff[DFR2D_XCHG_VERTEX]);
-            if (int rc = dev_alloc(h, &h->dSendBuf, (size_t)8 * NEd * h->nSendEdges)) return rc;
+            if (int rc = dev_alloc(h, &h->dSendBuf, (size_t)4 * NEd * h->nSendEdges)) return rc;
             h->dRecvBuf = (double *)(h->mailbox + h->mbOff[DFR2D_XCHG_DISS]);
         }
-        if (int rc = dev_alloc(h, &d.dissX, (size_t)4 * h->NpFlux * Kp)) return rc;
-        if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * h->NpFlux * Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.dissX, (size_t)4 * NI * Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * NI * Kp)) return rc;
+        if (int rc = dev_alloc(h, &d.vn, (size_t)8 * NEd * h->NEp)) return rc;
+        CK(cudaMemset(d.vn, 0, (size_t)8 * NEd * h->NEp * sizeof(double)));
         if (int rc = dev_alloc(h, &d.vflux, (size_t)4 * NEd * h->NEp)) return rc;
         if (int rc = dev_alloc(h, &d.aggv, (size_t)h->NEp)) return rc;
         if (int rc = dev_alloc(h, &d.DTVisc, (size_t)Kp)) return rc;
@@ -626,8 +636,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         CK(cudaMemset(d.se, 0, (size_t)Kp * sizeof(double)));
         CK(cudaMemset(d.sigmaV, 0, (size_t)std::max(h->NV, 1) * sizeof(double)));
         CK(cudaMemset(d.epsV, 0, (size_t)std::max(h->NV, 1) * sizeof(double)));
-        CK(cudaMemset(d.dissX, 0, (size_t)4 * h->NpFlux * Kp * sizeof(double)));
-        CK(cudaMemset(d.dissY, 0, (size_t)4 * h->NpFlux * Kp * sizeof(double)));
+        CK(cudaMemset(d.dissX, 0, (size_t)4 * NI * Kp * sizeof(double)));
+        CK(cudaMemset(d.dissY, 0, (size_t)4 * NI * Kp * sizeof(double)));
         CK(cudaMemset(d.vflux, 0, (size_t)4 * NEd * h->NEp * sizeof(double)));
         CK(cudaMemset(d.aggv, 0, (size_t)h->NEp * sizeof(double)));
         CK(cudaMemset(d.DTVisc, 0, (size_t)Kp * sizeof(double)));
@@ -670,9 +680,12 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // kernel: its operators are 15 x 15, and its summation order is the one the 1e-11 parity bar at N = 1 relies on
     // (the RT2 divergence operator is ill conditioned, tests/test_noise_floor.py)
     h->gradKernel = (N >= 2) ? 3 : 1;
-    if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev);
+    if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev) >= 2 ? 3 : 1;
     if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
+    // measured (profiles/r02a_ab_N*.json, 2M triangles): the tensor-core element kernel wins at N = 4 (3.08 -> 2.80 ms) and
+    // loses at N = 2, 3 (operators of 6 / 10 rows: the 8 x 8 x 4 tiles are mostly padding)
+    h->dissElemKernel = (N == 4) ? 3 : 1;
     if (const char *ev = getenv("DFR2D_DISS_ELEM_KERNEL")) h->dissElemKernel = atoi(ev);
     if (ph.dissipation && h->dissElemKernel == 3) {
         std::vector<double> fr;
@@ -866,27 +879,21 @@ static int run_unpack(dfr2d_handle *h) {
     return launch_check(h, "k_halo_unpack");
 }
 
-// DissX then DissY edge rows of the cut edges (rows 2 NpInt + edge * NpEdge + i of the sender's element), one launch
+// viscous exchange: the owner-normal components of my side of every cut edge (k_vn_pack / k_vn_unpack, dfr2d_peer.cuh)
 static int run_pack_diss(dfr2d_handle *h) {
     if (h->nSendEdges == 0) return 0;
-    HaloPackArgs a{};
-    a.per = 8 * h->NpEdge; a.total = h->nSendEdges * a.per; a.npEdge = h->NpEdge; a.planeRows = h->NpFlux; a.rowBase = 2 * h->NpInt;
-    a.Kp = h->Kp; a.nTail = 0;
-    a.src = h->ds.dissX; a.src2 = h->ds.dissY; a.elem = h->sendElem; a.row0 = h->sendRow0; a.etov = nullptr; a.epsV = nullptr;
-    a.buf = h->dSendBuf; a.put = h->connected ? h->putTab[DFR2D_XCHG_DISS] : nullptr; a.seq = xchg_seq(h);
-    k_halo_pack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
-    return launch_check(h, "k_halo_pack(diss)");
+    const int total = h->nSendEdges * 4 * h->NpEdge;
+    k_vn_pack<<<(total + 255) / 256, 256, 0, h->stream>>>(h->nSendEdges, h->NpEdge, h->NEp, h->ds.vn, h->cutSlot, h->cutSide, h->dSendBuf,
+                                                          h->connected ? h->putTab[DFR2D_XCHG_DISS] : nullptr, xchg_seq(h));
+    return launch_check(h, "k_vn_pack");
 }
 
 static int run_unpack_diss(dfr2d_handle *h) {
     if (h->nRecvEdges == 0) return 0;
-    HaloUnpackArgs a{};
-    a.per = 8 * h->NpEdge; a.total = h->nRecvEdges * a.per; a.npEdge = h->NpEdge; a.planeRows = h->NpFlux; a.rowBase = 2 * h->NpInt;
-    a.Kp = h->Kp; a.nTail = 0; a.K = h->K; a.NV = h->NV;
-    a.dst = h->ds.dissX; a.dst2 = h->ds.dissY; a.col = h->recvCol; a.row0 = h->recvRow0; a.epsV = nullptr;
-    a.buf = h->dRecvBuf; a.wait = h->connected ? h->waitTab[DFR2D_XCHG_DISS] : nullptr; a.seq = xchg_seq(h);
-    k_halo_unpack<<<(a.total + 255) / 256, 256, 0, h->stream>>>(a);
-    return launch_check(h, "k_halo_unpack(diss)");
+    const int total = h->nRecvEdges * 4 * h->NpEdge;
+    k_vn_unpack<<<(total + 255) / 256, 256, 0, h->stream>>>(h->nRecvEdges, h->NpEdge, h->NEp, h->ds.vn, h->cutSlot, h->cutSide, h->dRecvBuf,
+                                                            h->connected ? h->waitTab[DFR2D_XCHG_DISS] : nullptr, xchg_seq(h));
+    return launch_check(h, "k_vn_unpack");
 }
 
 static int run_pack_vertex(dfr2d_handle *h) {
@@ -999,6 +1006,7 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     if (h->ph.dissipation && h->dissElemKernel == 3) {
         ElemMmaArgs ma{};
         ma.a = a;
+        ma.a.pfTiles = h->pfTiles;            // bulk L2 prefetch of the next tile (DFR2D_PREFETCH_TILES=0 switches it off)
         ma.frags = h->mmaDissFrags;
         ma.nTiles = blocks;
         DISPATCH_N(h->N, {
@@ -1161,6 +1169,7 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
     ga.Jdet = h->Jdet; ga.Jinv = h->Jinv; ga.IInII = h->IInII; ga.nxk = d.nxk; ga.nyk = d.nyk;
     ga.etov = d.etov; ga.epsV = d.epsV;
     ga.dissX = d.dissX; ga.dissY = d.dissY;
+    ga.enx = h->enx; ga.eny = h->eny; ga.vn = d.vn; ga.NEp = h->NEp;
     ga.sc = h->sc; ga.par = (int)(h->stepIndex & 1); ga.stepIndex = h->stepIndex; ga.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
     if (h->gradKernel == 3) {
@@ -1181,18 +1190,6 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
         });
         return launch_check(h, "k_grad_pipe");
     }
-    if (h->gradKernel == 2) {
-        DISPATCH_N(h->N, {
-            const size_t sm = GradMmaDim<NN>::kSmemBytes;
-            if (!h->gradAttrSet) {
-                cudaFuncSetAttribute(k_grad_mma<NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-                cudaFuncSetAttribute(k_grad_mma<NN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-                h->gradAttrSet = true;
-            }
-            k_grad_mma<NN><<<blocks, kGradMmaThreads, sm, h->stream>>>(ga, h->gradTable);
-        });
-        return launch_check(h, "k_grad_mma");
-    }
     DISPATCH_N(h->N, {
         const size_t sm = (size_t)4 * (Dim<NN>::NpInt + Dim<NN>::NF3) * kElemsPerBlock * sizeof(double);
         k_grad<NN><<<blocks, kElemThreads, sm, h->stream>>>(ga);
@@ -1207,7 +1204,7 @@ static int run_diss_visc(dfr2d_handle *h) {
     va.ne = h->NE; va.NEp = h->NEp; va.Kp = h->Kp;
     va.kL = h->ekL; va.kR = h->ekR; va.meta = h->emeta;
     va.nx = h->enx; va.ny = h->eny; va.oohk = h->eoohk; va.ooLen = d.eooLen;
-    va.qface = h->qface; va.dissX = d.dissX; va.dissY = d.dissY;
+    va.qface = h->qface; va.vn = d.vn;
     va.etov = d.etov; va.epsV = d.epsV;
     va.vflux = d.vflux; va.aggv = d.aggv;
     va.sc = h->sc; va.slot = (int)(h->stageCounter & 1); va.par = (int)(h->stepIndex & 1); va.stepIndex = h->stepIndex; va.ph = h->ph;

@@ -12,7 +12,9 @@ struct DissBuffers {
     double *eooLen = nullptr;            // [NEp] 1 / edge length
     double *sigma = nullptr, *epsk = nullptr, *se = nullptr;   // [Kp]
     double *sigmaV = nullptr, *epsV = nullptr;                  // [NV]
-    double *dissX = nullptr, *dissY = nullptr;                  // [4][NpFlux][Kp]
+    double *dissX = nullptr, *dissY = nullptr;                  // [4][NpInt][Kp]: interior rows of Epsilon (.) Grad
+    double *vn = nullptr;                // [2 sides][4][NpEdge][NEp]: owner-normal component of Epsilon (.) Grad on the edge
+                                         // points, in the OWNER's point order (side 0 = owner, 1 = neighbour)
     double *vflux = nullptr;             // [4][NpEdge][NEp]
     double *aggv = nullptr;              // [NEp]
     double *DTVisc = nullptr;            // [Kp]
@@ -196,12 +198,30 @@ struct GradArgs {
     const double *Jdet, *Jinv, *IInII, *nxk, *nyk;
     const int *etov;
     const double *epsV;
-    double *dissX, *dissY;             // [4][NpFlux][Kp]
+    double *dissX, *dissY;             // [4][NpInt][Kp]: rows [0, NpInt) of DissX / DissY (AddDissipation reads them)
+    // The 3 NpEdge edge rows of DissX / DissY have exactly one consumer, StoreEdgeViscousFlux, which only ever forms
+    // normalL . (DissX, DissY) of both sides with the OWNER's normal (normalR := normalL, edges.go:175).  So the gradient
+    // kernels store that one number per edge point straight into edge-indexed arrays, in the owner's point order:
+    // half the bytes of the two row sets, and the viscous edge kernel reads them fully coalesced instead of gathering
+    // 8-byte words from two element columns (its 25 % sector efficiency was item 3 of round 1's open list).
+    const double *enx, *eny;           // [NEp] owner normal of every local edge
+    double *vn;                        // [2][4][NpEdge][NEp]
+    int NEp;
     DevScalars *sc;
     int par;
     long long stepIndex;
     Phys ph;
 };
+
+// row (>= 2 NpInt) of element k, local edge le, point ii, conserved variable n: store nx dX + ny dY into the edge slot
+template <int N>
+__device__ __forceinline__ void store_vn(const GradArgs &a, int n, int le, int ii, int s, double dX, double dY) {
+    constexpr int NEd = Dim<N>::NpEdge;
+    const bool owner = s >= 0;
+    const int slot = owner ? s : -1 - s;
+    const double v = a.enx[slot] * dX + a.eny[slot] * dY;
+    a.vn[((size_t)((owner ? 0 : 4) + n) * NEd + (owner ? ii : NEd - 1 - ii)) * a.NEp + slot] = v;
+}
 
 template <int N>
 __global__ void __launch_bounds__(kElemThreads) k_grad(GradArgs a) {
@@ -221,9 +241,11 @@ __global__ void __launch_bounds__(kElemThreads) k_grad(GradArgs a) {
 #pragma unroll
     for (int i = 0; i < NI; i++) u[i * E] = a.q[((size_t)n * NI + i) * Kp + kc];
     const size_t qplane = (size_t)NF3 * Kp;
+    int sl[3];
 #pragma unroll
     for (int le = 0; le < 3; le++) {
         const int s = a.etoe[(size_t)le * Kp + kc];
+        sl[le] = s;
         if (s >= 0) {                   // owner: own edge values
 #pragma unroll
             for (int i = 0; i < NEd; i++) u[(NI + le * NEd + i) * E] = a.qface[n * qplane + (size_t)(le * NEd + i) * Kp + kc];
@@ -280,8 +302,13 @@ __global__ void __launch_bounds__(kElemThreads) k_grad(GradArgs a) {
             for (int r = 0; r < CH; r++) {
                 const int row = (c0 + r < NI) ? (c0 + r) : (c0 + r + NI);
                 const double eps = op.Bary[row][0] * ev0 + op.Bary[row][1] * ev1 + op.Bary[row][2] * ev2;
-                a.dissX[((size_t)n * NF + row) * Kp + k] = gx[r] * eps;
-                a.dissY[((size_t)n * NF + row) * Kp + k] = gy[r] * eps;
+                if (row < NI) {
+                    a.dissX[((size_t)n * NI + row) * Kp + k] = gx[r] * eps;
+                    a.dissY[((size_t)n * NI + row) * Kp + k] = gy[r] * eps;
+                } else {
+                    const int le = (row - 2 * NI) / NEd, ii = (row - 2 * NI) % NEd;
+                    store_vn<N>(a, n, le, ii, sl[le], gx[r] * eps, gy[r] * eps);
+                }
             }
         }
     }
@@ -293,7 +320,7 @@ struct ViscEdgeArgs {
     int ne, NEp, Kp;
     const int *kL, *kR, *meta;
     const double *nx, *ny, *oohk, *ooLen;
-    const double *qface, *dissX, *dissY;
+    const double *qface, *vn;          // vn: [2][4][NpEdge][NEp], see GradArgs
     const int *etov;
     const double *epsV;
     double *vflux, *aggv;
@@ -305,17 +332,17 @@ struct ViscEdgeArgs {
 
 template <int N>
 __global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
-    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
     const size_t Kp = a.Kp;
-    const size_t dplane = (size_t)NF * Kp, qplane = (size_t)NF3 * Kp, fplane = (size_t)NEd * a.NEp;
+    const size_t qplane = (size_t)NF3 * Kp, fplane = (size_t)NEd * a.NEp;
     double blockmax = 0.0;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.ne; e += gridDim.x * blockDim.x) {
         const int kL = a.kL[e], kRraw = a.kR[e], meta = a.meta[e];
         const bool shared = kRraw >= 0;
         const int kR = shared ? kRraw : 0;
         const int numL = meta & 3, numR = (meta >> 2) & 3;
-        const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
+        const double oohk = a.oohk[e];
         const double eL0 = a.epsV[a.etov[0 * Kp + kL]], eL1 = a.epsV[a.etov[1 * Kp + kL]], eL2 = a.epsV[a.etov[2 * Kp + kL]];
         double eR0 = 0, eR1 = 0, eR2 = 0;
         if (shared) { eR0 = a.epsV[a.etov[0 * Kp + kR]]; eR1 = a.epsV[a.etov[1 * Kp + kR]]; eR2 = a.epsV[a.etov[2 * Kp + kR]]; }
@@ -335,11 +362,12 @@ __global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
             }
 #pragma unroll
             for (int n = 0; n < 4; n++) {
-                const double vFL = nx * a.dissX[n * dplane + (size_t)rowL * Kp + kL] + ny * a.dissY[n * dplane + (size_t)rowL * Kp + kL];
+                // n . (DissX, DissY) of both sides with the owner's normal (normalR := normalL in the reference,
+                // edges.go:175), formed by the gradient kernel
+                const double vFL = a.vn[((size_t)n * NEd + i) * a.NEp + e];
                 double vf = vFL;
                 if (shared) {
-                    // normalR := normalL in the reference (edges.go:175)
-                    const double vFR = nx * a.dissX[n * dplane + (size_t)rowR * Kp + kR] + ny * a.dissY[n * dplane + (size_t)rowR * Kp + kR];
+                    const double vFR = a.vn[((size_t)(4 + n) * NEd + i) * a.NEp + e];
                     vf = 0.5 * (vFL + vFR);
                     // both "sides" of the jump resolve to the owner's stored edge values (edges.go:225-236)
                     const double qa = a.qface[n * qplane + (size_t)(numL * NEd + i) * Kp + kL];

@@ -99,6 +99,39 @@ __global__ void __launch_bounds__(kElemThreads, DFR2D_MMA_MINBLOCKS) k_elem_mma_
         const bool fullTile = k0 + E <= a.K;
         __syncthreads();       // previous tile fully consumed before sQ / sF are overwritten
 
+        if (a.pfTiles > 0) {
+            // bulk L2 prefetch of this CTA's NEXT tile (the kernel is load -> barrier -> compute -> store per tile, ncu:
+            // 26 % DRAM throughput, long-scoreboard bound): stage input, interior DissX / DissY, the extra RK registers,
+            // geometry, and the neighbourhood of the edge-flux / viscous-flux slots
+            const long long kt = (long long)(tile + gridDim.x) * E;
+            if (kt + E <= a.K) {
+                constexpr unsigned RB = E * sizeof(double);
+                for (int r = threadIdx.x; r < 4 * NI; r += kElemThreads) {
+                    prefetch_l2(a.qs + (size_t)r * Kp + kt, RB);
+                    prefetch_l2(a.dissX + (size_t)r * Kp + kt, RB);
+                    prefetch_l2(a.dissY + (size_t)r * Kp + kt, RB);
+                    if (a.rk >= 1) prefetch_l2(a.q0 + (size_t)r * Kp + kt, RB);
+                    if (a.rk == 4) {
+                        prefetch_l2(a.q2 + (size_t)r * Kp + kt, RB);
+                        prefetch_l2(a.q3 + (size_t)r * Kp + kt, RB);
+                        prefetch_l2(a.R + (size_t)r * Kp + kt, RB);
+                    }
+                }
+                if (threadIdx.x < 4) prefetch_l2(a.Jinv + (size_t)threadIdx.x * Kp + kt, RB);
+                else if (threadIdx.x < 7) prefetch_l2(a.IInII + (size_t)(threadIdx.x - 4) * Kp + kt, RB);
+                else if (threadIdx.x < 10) prefetch_l2(a.etoe + (size_t)(threadIdx.x - 7) * Kp + kt, E * sizeof(int));
+                else if (threadIdx.x == 10) prefetch_l2(a.Jdet + kt, RB);
+                else if (threadIdx.x == 11) prefetch_l2(a.sigma + kt, RB);
+                else if (threadIdx.x >= 32 && threadIdx.x < 32 + 4 * NEd) {
+                    const long long s0 = ((kt * 3 / 2) / 16) * 16;       // owner slots follow the element numbering (1.5 per element)
+                    if (s0 + 64 <= a.NEp) {
+                        prefetch_l2(a.eflux + (size_t)(threadIdx.x - 32) * a.NEp + s0, 64 * sizeof(double));
+                        prefetch_l2(a.vflux + (size_t)(threadIdx.x - 32) * a.NEp + s0, 64 * sizeof(double));
+                    }
+                }
+            }
+        }
+
         // ---- phase 1: stage input row, edge DOFs of (F - F_visc), dt, -1/J, limiter factor ------------------------
 #pragma unroll
         for (int i = 0; i < NI; i++) myQ[i * SE + lane] = a.qs[((size_t)n * NI + i) * Kp + kc];
@@ -158,8 +191,8 @@ __global__ void __launch_bounds__(kElemThreads, DFR2D_MMA_MINBLOCKS) k_elem_mma_
                     for (int m = 0; m < 4; m++) {
                         double frr = jdet * (j0 * Fx[m] + j1 * Fy[m]);
                         double fss = jdet * (j2 * Fx[m] + j3 * Fy[m]);
-                        const double dix = a.dissX[((size_t)m * NF + j) * Kp + kc];
-                        const double diy = a.dissY[((size_t)m * NF + j) * Kp + kc];
+                        const double dix = a.dissX[((size_t)m * NI + j) * Kp + kc];
+                        const double diy = a.dissY[((size_t)m * NI + j) * Kp + kc];
                         frr -= jdet * (j0 * dix + j1 * diy);                 // dissipation.go:310-315
                         fss -= jdet * (j2 * dix + j3 * diy);
                         sF[(m * MD::FROWS + j) * SE + lane] = frr;

@@ -12,10 +12,10 @@
 //   2  S_r is a DMMA.8x8x4 product: A = Div rows (only the rows consumed later: [0,NpInt) and the 3 NpEdge edge rows),
 //      zero padded to 8 x 4 tiles per block r and kept in shared memory in A-fragment lane order; B = U of one variable
 //      for 8 elements (k = RT point, n = element), read from the same stride-36 shared-memory rows as k_elem_mma.
-// CTA = 32 elements x 8 warps; warp = (conserved variable, 16-element half of the tile).  The metric combination,
-// the Epsilon product (Bary . vertex eps, InterpolateEpsilonSigma dissipation.go:219-242) and the 128-bit stores of
-// DissX / DissY happen in the accumulator fragment layout.  DFR2D_GRAD_KERNEL=2; measured 3.52 ms against 3.86 ms of the
-// DFMA kernel (k_edge + gradient, 2M triangles, N=4) -- the pipelined k_grad_pipe below (2.74 ms) is the default for N >= 2.
+// Warp = (conserved variable, 16-element half of the tile).  The metric combination, the Epsilon product (Bary . vertex
+// eps, InterpolateEpsilonSigma dissipation.go:219-242) and the stores happen in the accumulator fragment layout.  Round 1
+// measured a one-tile-per-CTA version of this (k_grad_mma: 3.52 ms against 3.86 ms of the DFMA kernel for k_edge +
+// gradient, 2M triangles, N=4; profiles/r01l_*); the pipelined persistent k_grad_pipe below (2.74 ms) replaced it.
 #pragma once
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
@@ -42,145 +42,6 @@ template <int N> struct GradMmaDim {
     __host__ __device__ static constexpr int blk_k0(int r) { return r < 2 ? r * KI : 2 * KI + (r - 2) * KE; }
     __host__ __device__ static constexpr int blk_urow0(int r) { return r < 2 ? 0 : 4 * KI + (r - 2) * 4 * KE; }
 };
-
-constexpr int kGradMmaThreads = 8 * kElemsPerBlock;
-
-template <int N>
-__global__ void __launch_bounds__(kGradMmaThreads, 2) k_grad_mma(GradArgs a, const double *__restrict__ table) {
-    using GD = GradMmaDim<N>;
-    constexpr int NI = GD::NI, NEd = GD::NEd, NF = GD::NF, NF3 = GD::NF3, E = kElemsPerBlock, SE = GD::SE;
-    constexpr int MT = GD::MT, KS = GD::KS, KI = GD::KI, KE = GD::KE, MG = GD::MG, UROWS = GD::UROWS;
-    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
-    extern __shared__ double smem[];
-    double *sU = smem;                                 // [4][UROWS][SE]
-    double *sT = sU + 4 * UROWS * SE;                  // A fragments [MT][KS][32], then Bary [8 MT][3]
-    double *sMet = sT + GD::kTableDoubles;             // [5 blocks][x|y][E]
-    double *sEv = sMet + 10 * E;                       // [3][E] vertex epsilon
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, n = w & 3, half = w >> 2;
-    const int k0 = blockIdx.x * E, k = k0 + lane;
-    const int kc = k < a.K ? k : a.K - 1;
-    const size_t Kp = a.Kp;
-
-    for (int t = tid; t < GD::kTableDoubles; t += kGradMmaThreads) sT[t] = table[t];
-    double *myU = sU + (size_t)n * UROWS * SE;
-    // distinct solution values of the RT points: interior rows (both interior blocks read them), then per edge the
-    // owner's Q_Face values (EdgeQValues), reversed for the non-owner (euler.go:896-912); rows split between the halves
-#pragma unroll
-    for (int i = 0; i < 4 * KI; i++)
-        if ((i & 1) == half) myU[i * SE + lane] = (i < NI) ? a.q[((size_t)n * NI + i) * Kp + kc] : 0.0;
-    const size_t qplane = (size_t)NF3 * Kp;
-#pragma unroll
-    for (int le = 0; le < 3; le++) {
-        const int s = a.etoe[(size_t)le * Kp + kc];
-        const bool owner = s >= 0;
-        int kS = kc, numS = le;
-        if (!owner) {
-            const int slot = -1 - s;
-            kS = a.ekL[slot];
-            numS = a.emeta[slot] & 3;
-        }
-        const double *src = a.qface + n * qplane + (size_t)(numS * NEd) * Kp + kS;
-#pragma unroll
-        for (int i = 0; i < 4 * KE; i++)
-            if ((i & 1) == half) {
-                double v = 0.0;
-                if (i < NEd) v = src[(size_t)(owner ? i : NEd - 1 - i) * Kp];
-                myU[(4 * KI + le * 4 * KE + i) * SE + lane] = v;
-            }
-    }
-    if (w == 0) {
-        // metric of each block (DXMetric / DYMetric, DG2D/dfr_startup.go:213-254)
-        const double oojd = 1.0 / a.Jdet[kc];
-        sMet[0 * E + lane] = a.Jinv[0 * Kp + kc];
-        sMet[1 * E + lane] = a.Jinv[1 * Kp + kc];
-        sMet[2 * E + lane] = a.Jinv[2 * Kp + kc];
-        sMet[3 * E + lane] = a.Jinv[3 * Kp + kc];
-#pragma unroll
-        for (int le = 0; le < 3; le++) {
-            const double iin = a.IInII[(size_t)le * Kp + kc];
-            sMet[(4 + 2 * le) * E + lane] = oojd * a.nxk[(size_t)le * Kp + kc] * iin;
-            sMet[(5 + 2 * le) * E + lane] = oojd * a.nyk[(size_t)le * Kp + kc] * iin;
-        }
-    } else if (w == 4) {
-#pragma unroll
-        for (int v = 0; v < 3; v++) sEv[v * E + lane] = a.epsV[a.etov[(size_t)v * Kp + kc]];
-    }
-    __syncthreads();
-
-    const int fr = lane >> 2, fc = lane & 3;
-    const int nt0 = 2 * half;
-#pragma unroll
-    for (int m0 = 0; m0 < MT; m0 += MG) {
-        double gx[MG][2][2], gy[MG][2][2];
-#pragma unroll
-        for (int mt = 0; mt < MG; mt++)
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) gx[mt][nt][0] = gx[mt][nt][1] = gy[mt][nt][0] = gy[mt][nt][1] = 0.0;
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            double S[MG][2][2];
-#pragma unroll
-            for (int mt = 0; mt < MG; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) S[mt][nt][0] = S[mt][nt][1] = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < (KI > KE ? KI : KE); ks++) {
-                if (ks >= GD::blk_ks(r)) continue;
-                double b[2];
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) b[nt] = myU[(GD::blk_urow0(r) + 4 * ks + fc) * SE + 8 * (nt0 + nt) + fr];
-#pragma unroll
-                for (int mt = 0; mt < MG; mt++)
-                    if (m0 + mt < MT) {
-                        const double av = sT[((m0 + mt) * KS + GD::blk_k0(r) + ks) * 32 + lane];
-#pragma unroll
-                        for (int nt = 0; nt < 2; nt++) dmma884(S[mt][nt][0], S[mt][nt][1], av, b[nt]);
-                    }
-            }
-#pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-                const int e0 = 8 * (nt0 + nt) + 2 * fc;
-                const double2 mX = *reinterpret_cast<const double2 *>(&sMet[(2 * r) * E + e0]);
-                const double2 mY = *reinterpret_cast<const double2 *>(&sMet[(2 * r + 1) * E + e0]);
-#pragma unroll
-                for (int mt = 0; mt < MG; mt++)
-                    if (m0 + mt < MT) {
-                        gx[mt][nt][0] = fma(mX.x, S[mt][nt][0], gx[mt][nt][0]);
-                        gx[mt][nt][1] = fma(mX.y, S[mt][nt][1], gx[mt][nt][1]);
-                        gy[mt][nt][0] = fma(mY.x, S[mt][nt][0], gy[mt][nt][0]);
-                        gy[mt][nt][1] = fma(mY.y, S[mt][nt][1], gy[mt][nt][1]);
-                    }
-            }
-        }
-        // Diss = Epsilon (.) Grad on the rows of this group; lane holds row 8 mt + fr, elements e0, e0 + 1
-#pragma unroll
-        for (int mt = 0; mt < MG; mt++) {
-            const int m = 8 * (m0 + mt) + fr;
-            if (m0 + mt < MT && m < GD::NOUT) {
-                const int row = GD::out_row(m);
-                const double b0 = sT[GD::kFragDoubles + m * 3 + 0], b1 = sT[GD::kFragDoubles + m * 3 + 1],
-                             b2 = sT[GD::kFragDoubles + m * 3 + 2];
-#pragma unroll
-                for (int nt = 0; nt < 2; nt++) {
-                    const int e0 = 8 * (nt0 + nt) + 2 * fc;
-                    const double2 v0 = *reinterpret_cast<const double2 *>(&sEv[0 * E + e0]);
-                    const double2 v1 = *reinterpret_cast<const double2 *>(&sEv[1 * E + e0]);
-                    const double2 v2 = *reinterpret_cast<const double2 *>(&sEv[2 * E + e0]);
-                    const double epsA = b0 * v0.x + b1 * v1.x + b2 * v2.x;
-                    const double epsB = b0 * v0.y + b1 * v1.y + b2 * v2.y;
-                    const size_t o = ((size_t)n * NF + row) * Kp + k0 + e0;
-                    if (k0 + e0 + 1 < a.K) {
-                        *reinterpret_cast<double2 *>(a.dissX + o) = make_double2(gx[mt][nt][0] * epsA, gx[mt][nt][1] * epsB);
-                        *reinterpret_cast<double2 *>(a.dissY + o) = make_double2(gy[mt][nt][0] * epsA, gy[mt][nt][1] * epsB);
-                    } else if (k0 + e0 < a.K) {
-                        a.dissX[o] = gx[mt][nt][0] * epsA;
-                        a.dissY[o] = gy[mt][nt][0] * epsA;
-                    }
-                }
-            }
-        }
-    }
-}
 
 // Host side: Div -> A-operand fragments per (m-tile, k-step) in lane order (lane l holds A[l/4][l%4]), k-steps grouped
 // by metric block and zero padded per block; then the Bary rows of the produced RT rows.
@@ -222,7 +83,8 @@ template <int N> struct GradPipeDim {
     static constexpr int E = kElemsPerBlock;
     static constexpr int kGroups = 2, kGroupThreads = 8 * E, kThreads = kGroups * kGroupThreads;
     static constexpr int kUDoubles = 4 * GD::UROWS * GD::SE;
-    static constexpr int kStageDoubles = kUDoubles + 10 * E + 3 * E;      // U, metric rows, vertex epsilon
+    static constexpr int kStageDoubles = kUDoubles + 10 * E + 3 * E + 9 * E;  // U, metric rows, vertex epsilon, and per local
+                                                                          // edge: owner normal (x, y) and the etoe entry
     static constexpr size_t kSmemBytes = (size_t)(GD::kTableDoubles + 2 * kGroups * kStageDoubles) * sizeof(double);
 };
 
@@ -286,7 +148,7 @@ template <int N, int MG, int M0>
 __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU, const double *pA, const double *pM,
                                             const double *pB, int n, int fr, int fc, int nt0, int k0, size_t KpL) {
     using GD = GradMmaDim<N>;
-    constexpr int E = kElemsPerBlock, SE = GD::SE, KI = GD::KI, KE = GD::KE, MT = GD::MT, NF = GD::NF;
+    constexpr int E = kElemsPerBlock, SE = GD::SE, KI = GD::KI, KE = GD::KE, MT = GD::MT;
     double gx[MG][2][2], gy[MG][2][2];
 #pragma unroll
     for (int mt = 0; mt < MG; mt++)
@@ -310,18 +172,41 @@ __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU,
         if (M0 + mt < MT && m < GD::NOUT) {
             const int row = GD::out_row(m);
             const double b0 = pB[8 * (M0 + mt) * 3], b1 = pB[8 * (M0 + mt) * 3 + 1], b2 = pB[8 * (M0 + mt) * 3 + 2];
+            constexpr int NI = GD::NI, NEd = GD::NEd;
 #pragma unroll
             for (int nt = 0; nt < 2; nt++) {
                 const int e0 = 8 * (nt0 + nt) + 2 * fc;
                 const double epsA = b0 * ev[nt][0].x + b1 * ev[nt][1].x + b2 * ev[nt][2].x;
                 const double epsB = b0 * ev[nt][0].y + b1 * ev[nt][1].y + b2 * ev[nt][2].y;
-                const size_t o = ((size_t)n * NF + row) * KpL + k0 + e0;
-                if (k0 + e0 + 1 < a.K) {
-                    *reinterpret_cast<double2 *>(a.dissX + o) = make_double2(gx[mt][nt][0] * epsA, gx[mt][nt][1] * epsB);
-                    *reinterpret_cast<double2 *>(a.dissY + o) = make_double2(gy[mt][nt][0] * epsA, gy[mt][nt][1] * epsB);
-                } else if (k0 + e0 < a.K) {
-                    a.dissX[o] = gx[mt][nt][0] * epsA;
-                    a.dissY[o] = gy[mt][nt][0] * epsA;
+                if (m < NI) {
+                    // interior rows: DissX / DissY [4][NpInt][Kp], read back by AddDissipation in the element kernel
+                    const size_t o = ((size_t)n * NI + row) * KpL + k0 + e0;
+                    if (k0 + e0 + 1 < a.K) {
+                        *reinterpret_cast<double2 *>(a.dissX + o) = make_double2(gx[mt][nt][0] * epsA, gx[mt][nt][1] * epsB);
+                        *reinterpret_cast<double2 *>(a.dissY + o) = make_double2(gy[mt][nt][0] * epsA, gy[mt][nt][1] * epsB);
+                    } else if (k0 + e0 < a.K) {
+                        a.dissX[o] = gx[mt][nt][0] * epsA;
+                        a.dissY[o] = gy[mt][nt][0] * epsA;
+                    }
+                } else {
+                    // edge rows: owner-normal component into the edge slot (GradArgs::vn), owner's point order
+                    const int le = (m - NI) / NEd, ii = (m - NI) - le * NEd;
+                    const double2 nxo = *reinterpret_cast<const double2 *>(&pM[(13 + le) * E + 8 * nt]);
+                    const double2 nyo = *reinterpret_cast<const double2 *>(&pM[(16 + le) * E + 8 * nt]);
+                    const double2 sl = *reinterpret_cast<const double2 *>(&pM[(19 + le) * E + 8 * nt]);
+                    const long long sA = __double_as_longlong(sl.x), sB = __double_as_longlong(sl.y);
+                    if (k0 + e0 < a.K) {
+                        const bool own = sA >= 0;
+                        const size_t slot = (size_t)(own ? sA : -1 - sA);
+                        a.vn[((size_t)((own ? 0 : 4) + n) * NEd + (own ? ii : NEd - 1 - ii)) * a.NEp + slot] =
+                            nxo.x * (gx[mt][nt][0] * epsA) + nyo.x * (gy[mt][nt][0] * epsA);
+                    }
+                    if (k0 + e0 + 1 < a.K) {
+                        const bool own = sB >= 0;
+                        const size_t slot = (size_t)(own ? sB : -1 - sB);
+                        a.vn[((size_t)((own ? 0 : 4) + n) * NEd + (own ? ii : NEd - 1 - ii)) * a.NEp + slot] =
+                            nxo.y * (gx[mt][nt][1] * epsB) + nyo.y * (gy[mt][nt][1] * epsB);
+                    }
                 }
             }
         }
@@ -363,6 +248,7 @@ __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradP
                                  // time, one iteration after the loads were posted, so that nothing waits on them
     int eKc = 0;                 // this lane's (clamped) element of that tile
     unsigned evIdx = 0;          // vertex of this lane's element (warps 5..7 of the group: vertex wg - 5)
+    int eSlot = 0;               // etoe entry of local edge wg - 5 of this lane's element (same warps): where the edge rows go
 
     auto elem_of = [&](int tile) {
         const int tc = tile < nTiles ? tile : nTiles - 1;
@@ -386,7 +272,10 @@ __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradP
                 eMeta[le] = a.emeta[-1 - s];
             }
         }
-        if (wg >= 5) evIdx = (unsigned)a.etov[(size_t)(wg - 5) * Kp + eKc];
+        if (wg >= 5) {
+            evIdx = (unsigned)a.etov[(size_t)(wg - 5) * Kp + eKc];
+            eSlot = (wg == 5) ? sIdx[0] : ((wg == 6) ? sIdx[1] : sIdx[2]);
+        }
     };
     auto issue = [&](int tile, int st) {    // every byte of `tile` -> stage st, asynchronously
         if (tile < nTiles) {
@@ -422,6 +311,12 @@ __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradP
                 cp_async16_u32(uB + (unsigned)((PD::kUDoubles + row * E + 2 * ch) * sizeof(double)), src);
             } else {
                 cp_async8_u32(uB + (unsigned)((PD::kUDoubles + 10 * E + (wg - 5) * E + lane) * sizeof(double)), a.epsV + evIdx);
+                // local edge wg - 5 of this lane's element: owner normal of its slot and the etoe entry itself (as the
+                // bit pattern of a 64-bit integer, so that the epilogue reads it with the same double2 pattern)
+                const int slot = eSlot >= 0 ? eSlot : -1 - eSlot;
+                cp_async8_u32(uB + (unsigned)((PD::kUDoubles + (13 + (wg - 5)) * E + lane) * sizeof(double)), a.enx + slot);
+                cp_async8_u32(uB + (unsigned)((PD::kUDoubles + (16 + (wg - 5)) * E + lane) * sizeof(double)), a.eny + slot);
+                base[PD::kUDoubles + (19 + (wg - 5)) * E + lane] = __longlong_as_double((long long)eSlot);
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");

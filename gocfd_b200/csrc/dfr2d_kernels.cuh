@@ -268,7 +268,7 @@ struct ElemArgs {
     double *DT, *DTVisc;                    // [Kp] (local time stepping)
     const double *Jdet, *Jinv, *IInII;      // [Kp], [4][Kp], [3][Kp]
     const int *etoe;                        // [3][Kp]: edge slot, or -1 - slot when the neighbour owns it
-    const double *dissX, *dissY;            // [4][NpFlux][Kp] (dissipation)
+    const double *dissX, *dissY;            // [4][NpInt][Kp]: interior rows of Epsilon (.) Grad (dissipation)
     const double *sigma;                    // [Kp] vertex-averaged sigma (dissipation)
     double *rhsOut;                         // test hook: RHSQ only, no update
     DevScalars *sc;
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
                 double fr = jdet * (j0 * Fx[m] + j1 * Fy[m]);
                 double fs = jdet * (j2 * Fx[m] + j3 * Fy[m]);
                 if (DISS) {   // interior dissipation DOFs (dissipation.go:310-315)
-                    const double dix = a.dissX[((size_t)m * Dim<N>::NpFlux + j) * Kp + kc];
-                    const double diy = a.dissY[((size_t)m * Dim<N>::NpFlux + j) * Kp + kc];
+                    const double dix = a.dissX[((size_t)m * NI + j) * Kp + kc];
+                    const double diy = a.dissY[((size_t)m * NI + j) * Kp + kc];
                     fr -= jdet * (j0 * dix + j1 * diy);
                     fs -= jdet * (j2 * dix + j3 * diy);
                 }

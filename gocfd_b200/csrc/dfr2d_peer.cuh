@@ -178,6 +178,28 @@ __global__ void k_halo_unpack(HaloUnpackArgs a) {
     }
 }
 
+// Viscous exchange: for every cut edge the 4 x NpEdge owner-normal components of Epsilon (.) Grad of MY side
+// (GradArgs::vn, already in the owner's point order) -> the partner's copy of the other side.
+__global__ void k_vn_pack(int nCut, int npEdge, int NEp, const double *vn, const int *slot, const int *side, double *buf,
+                          const PutTab *put, unsigned long long seq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 4 * npEdge;
+    if (t < nCut * per) {
+        const int c = t / per, r = t % per;              // r = n * NpEdge + i
+        put_store(put, buf, (long long)t, vn[((size_t)side[c] * per + r) * NEp + slot[c]]);
+    }
+    put_signal(put, seq);
+}
+__global__ void k_vn_unpack(int nCut, int npEdge, int NEp, double *vn, const int *slot, const int *side, const double *buf,
+                            const WaitTab *wait, unsigned long long seq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int per = 4 * npEdge;
+    if (t >= nCut * per) return;
+    wait_segment(wait, (long long)t, seq);
+    const int c = t / per, r = t % per;
+    vn[((size_t)(1 - side[c]) * per + r) * NEp + slot[c]] = __ldcg(buf + t);
+}
+
 // shared-vertex exchange of the element -> vertex max merge: message = (sigma, eps) per listed vertex
 __global__ void k_vertex_pack(int n, const int *vid, const double *sigmaV, const double *epsV, double *buf, const PutTab *put,
                               unsigned long long seq) {
