@@ -87,6 +87,7 @@ struct dfr2d_handle {
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
+    int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int tmaCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_TMA_CW)
     int edgePPT = 0;
     // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
@@ -628,7 +629,6 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         if (int rc = dev_alloc(h, &d.dissY, (size_t)4 * NI * Kp)) return rc;
         if (int rc = dev_alloc(h, &d.vn, (size_t)8 * NEd * h->NEp)) return rc;
         CK(cudaMemset(d.vn, 0, (size_t)8 * NEd * h->NEp * sizeof(double)));
-        if (int rc = dev_alloc(h, &d.vflux, (size_t)4 * NEd * h->NEp)) return rc;
         if (int rc = dev_alloc(h, &d.aggv, (size_t)h->NEp)) return rc;
         if (int rc = dev_alloc(h, &d.DTVisc, (size_t)Kp)) return rc;
         CK(cudaMemset(d.sigma, 0, (size_t)Kp * sizeof(double)));
@@ -638,7 +638,6 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         CK(cudaMemset(d.epsV, 0, (size_t)std::max(h->NV, 1) * sizeof(double)));
         CK(cudaMemset(d.dissX, 0, (size_t)4 * NI * Kp * sizeof(double)));
         CK(cudaMemset(d.dissY, 0, (size_t)4 * NI * Kp * sizeof(double)));
-        CK(cudaMemset(d.vflux, 0, (size_t)4 * NEd * h->NEp * sizeof(double)));
         CK(cudaMemset(d.aggv, 0, (size_t)h->NEp * sizeof(double)));
         CK(cudaMemset(d.DTVisc, 0, (size_t)Kp * sizeof(double)));
     }
@@ -663,6 +662,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
     if (const char *ev = getenv("DFR2D_TMA_STAGES")) h->tmaStages = atoi(ev);
     if (const char *ev = getenv("DFR2D_TMA_CW")) h->tmaCW = atoi(ev) == 12 ? 12 : 8;
+    if (const char *ev = getenv("DFR2D_DISS_PREFETCH")) h->dissPrefetch = atoi(ev) > 0 ? 1 : 0;
     {
         std::vector<double> fr;
         switch (N) {
@@ -989,7 +989,7 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     a.qs = h->q[rk];
     a.q0 = h->q[0]; a.q1 = h->q[1]; a.q2 = h->q[2]; a.q3 = h->q[3]; a.q4 = h->q[4]; a.R = h->R;
     a.qface = fuseInterp ? h->qface : nullptr;
-    a.eflux = h->eflux; a.vflux = h->ds.vflux;
+    a.eflux = h->eflux;
     a.agg = h->agg; a.aggv = h->ds.aggv;
     a.DT = h->DT; a.DTVisc = h->ds.DTVisc;
     a.Jdet = h->Jdet; a.Jinv = h->Jinv; a.IInII = h->IInII;
@@ -1006,7 +1006,8 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     if (h->ph.dissipation && h->dissElemKernel == 3) {
         ElemMmaArgs ma{};
         ma.a = a;
-        ma.a.pfTiles = h->pfTiles;            // bulk L2 prefetch of the next tile (DFR2D_PREFETCH_TILES=0 switches it off)
+        ma.a.pfTiles = h->dissPrefetch;       // bulk L2 prefetch of the next tile: measured SLOWER (3.00 vs 2.84 ms, 2M triangles,
+                                              // profiles/r02i_*), so off unless DFR2D_DISS_PREFETCH=1
         ma.frags = h->mmaDissFrags;
         ma.nTiles = blocks;
         DISPATCH_N(h->N, {
@@ -1206,10 +1207,10 @@ static int run_diss_visc(dfr2d_handle *h) {
     va.nx = h->enx; va.ny = h->eny; va.oohk = h->eoohk; va.ooLen = d.eooLen;
     va.qface = h->qface; va.vn = d.vn;
     va.etov = d.etov; va.epsV = d.epsV;
-    va.vflux = d.vflux; va.aggv = d.aggv;
+    va.eflux = h->eflux; va.aggv = d.aggv;
     va.sc = h->sc; va.slot = (int)(h->stageCounter & 1); va.par = (int)(h->stepIndex & 1); va.stepIndex = h->stepIndex; va.ph = h->ph;
-    const int eb = std::max(1, std::min(h->edgeBlocks, (h->NE + 255) / 256));
-    DISPATCH_N(h->N, (k_visc_edge<NN><<<eb, 256, 0, h->stream>>>(va)));
+    const int eb = std::max(1, std::min(4 * h->edgeBlocks, (h->NE + kViscEdges - 1) / kViscEdges));
+    DISPATCH_N(h->N, (k_visc_edge<NN><<<eb, dim3(kViscEdges, 4), 0, h->stream>>>(va)));
     return launch_check(h, "k_visc_edge");
 }
 

@@ -15,7 +15,6 @@ struct DissBuffers {
     double *dissX = nullptr, *dissY = nullptr;                  // [4][NpInt][Kp]: interior rows of Epsilon (.) Grad
     double *vn = nullptr;                // [2 sides][4][NpEdge][NEp]: owner-normal component of Epsilon (.) Grad on the edge
                                          // points, in the OWNER's point order (side 0 = owner, 1 = neighbour)
-    double *vflux = nullptr;             // [4][NpEdge][NEp]
     double *aggv = nullptr;              // [NEp]
     double *DTVisc = nullptr;            // [Kp]
 };
@@ -323,21 +322,29 @@ struct ViscEdgeArgs {
     const double *qface, *vn;          // vn: [2][4][NpEdge][NEp], see GradArgs
     const int *etov;
     const double *epsV;
-    double *vflux, *aggv;
+    double *eflux, *aggv;              // eflux: numerical normal flux, the viscous one is subtracted in place
     DevScalars *sc;
     int slot, par;
     long long stepIndex;
     Phys ph;
 };
 
+// Thread = (edge, conserved variable): block (64 edges, 4 variables), every warp walks 32 consecutive edges of one variable,
+// so all vn / eflux accesses are full 256-byte rows (one thread per edge with 50+ dependent loads was latency bound:
+// 45 % DRAM throughput, 38 long-scoreboard stall cycles per instruction, profiles/r02i_*).  The viscous normal flux is
+// SUBTRACTED FROM THE STORED NUMERICAL FLUX in place: its only consumer, the element kernel, needs F - F_visc on the edge
+// DOFs (AddDissipation, dissipation.go:316-333, folded into the DivInt contraction), so it gathers one array, not two.
+constexpr int kViscEdges = 64;
+
 template <int N>
-__global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
+__global__ void __launch_bounds__(4 * kViscEdges) k_visc_edge(ViscEdgeArgs a) {
     constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
     const size_t Kp = a.Kp;
     const size_t qplane = (size_t)NF3 * Kp, fplane = (size_t)NEd * a.NEp;
+    const int n = threadIdx.y;
     double blockmax = 0.0;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < a.ne; e += gridDim.x * blockDim.x) {
+    for (int e = blockIdx.x * kViscEdges + threadIdx.x; e < a.ne; e += gridDim.x * kViscEdges) {
         const int kL = a.kL[e], kRraw = a.kR[e], meta = a.meta[e];
         const bool shared = kRraw >= 0;
         const int kR = shared ? kRraw : 0;
@@ -348,6 +355,10 @@ __global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
         if (shared) { eR0 = a.epsV[a.etov[0 * Kp + kR]]; eR1 = a.epsV[a.etov[1 * Kp + kR]]; eR2 = a.epsV[a.etov[2 * Kp + kR]]; }
         const double ooLen = a.ooLen[e];
         double vmax = -1.7976931348623157e308;
+        const double *qrow = a.qface + n * qplane + (size_t)(numL * NEd) * Kp + kL;
+        double qv[NEd];
+#pragma unroll
+        for (int i = 0; i < NEd; i++) qv[i] = shared ? qrow[(size_t)i * Kp] : 0.0;
 #pragma unroll
         for (int i = 0; i < NEd; i++) {
             const int rowL = 2 * NI + numL * NEd + i;
@@ -355,39 +366,35 @@ __global__ void __launch_bounds__(256) k_visc_edge(ViscEdgeArgs a) {
             const Ops<N> &op = ops<N>();
             const double epsL = op.Bary[rowL][0] * eL0 + op.Bary[rowL][1] * eL1 + op.Bary[rowL][2] * eL2;
             vmax = fmax(oohk * oohk * epsL, vmax);
-            double lam = 0.0;
+            // n . (DissX, DissY) of both sides with the owner's normal (normalR := normalL in the reference,
+            // edges.go:175), formed by the gradient kernel
+            const size_t idx = ((size_t)n * NEd + i) * a.NEp + e;
+            const double vFL = a.vn[idx];
+            double vf = vFL;
             if (shared) {
                 const double epsR = op.Bary[rowR][0] * eR0 + op.Bary[rowR][1] * eR1 + op.Bary[rowR][2] * eR2;
-                lam = 0.5 * (epsL + epsR);
+                const double lam = 0.5 * (epsL + epsR);
+                const double vFR = a.vn[idx + 4 * fplane];
+                vf = 0.5 * (vFL + vFR);
+                // both "sides" of the jump resolve to the owner's stored edge values (edges.go:225-236)
+                vf -= (a.ph.Omega * lam * ooLen) * (qv[i] - qv[NEd - 1 - i]);
             }
-#pragma unroll
-            for (int n = 0; n < 4; n++) {
-                // n . (DissX, DissY) of both sides with the owner's normal (normalR := normalL in the reference,
-                // edges.go:175), formed by the gradient kernel
-                const double vFL = a.vn[((size_t)n * NEd + i) * a.NEp + e];
-                double vf = vFL;
-                if (shared) {
-                    const double vFR = a.vn[((size_t)(4 + n) * NEd + i) * a.NEp + e];
-                    vf = 0.5 * (vFL + vFR);
-                    // both "sides" of the jump resolve to the owner's stored edge values (edges.go:225-236)
-                    const double qa = a.qface[n * qplane + (size_t)(numL * NEd + i) * Kp + kL];
-                    const double qb = a.qface[n * qplane + (size_t)(numL * NEd + (NEd - 1 - i)) * Kp + kL];
-                    vf -= (a.ph.Omega * lam * ooLen) * (qa - qb);
-                }
-                a.vflux[n * fplane + (size_t)i * a.NEp + e] = vf;
-            }
+            a.eflux[n * fplane + (size_t)i * a.NEp + e] -= vf;
         }
-        a.aggv[e] = vmax;
-        blockmax = fmax(blockmax, vmax);
+        if (n == 0) {
+            a.aggv[e] = vmax;
+            blockmax = fmax(blockmax, vmax);
+        }
     }
     __shared__ double smax[8];
+    const int tid = threadIdx.y * kViscEdges + threadIdx.x;
     blockmax = warp_max(blockmax);
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    if ((tid & 31) == 0) smax[tid >> 5] = blockmax;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
+    if (tid < 32) {
+        double v = tid < 8 ? smax[tid] : 0.0;
         v = warp_max(v);
-        if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][1], v);
+        if (tid == 0) atomic_max_nonneg(&a.sc->wave[a.slot][1], v);
     }
 }
 

@@ -126,7 +126,6 @@ __global__ void __launch_bounds__(kElemThreads, DFR2D_MMA_MINBLOCKS) k_elem_mma_
                     const long long s0 = ((kt * 3 / 2) / 16) * 16;       // owner slots follow the element numbering (1.5 per element)
                     if (s0 + 64 <= a.NEp) {
                         prefetch_l2(a.eflux + (size_t)(threadIdx.x - 32) * a.NEp + s0, 64 * sizeof(double));
-                        prefetch_l2(a.vflux + (size_t)(threadIdx.x - 32) * a.NEp + s0, 64 * sizeof(double));
                     }
                 }
             }
@@ -144,14 +143,13 @@ __global__ void __launch_bounds__(kElemThreads, DFR2D_MMA_MINBLOCKS) k_elem_mma_
                 const int slot = owner ? s : -1 - s;
                 const double iin = a.IInII[(size_t)le * Kp + kc];
                 const double *f = a.eflux + ((size_t)n * NEd) * a.NEp + slot;
-                const double *fv = a.vflux + ((size_t)n * NEd) * a.NEp + slot;
 #pragma unroll
                 for (int i = 0; i < NEd; i++) {
                     const size_t o = (size_t)(owner ? i : NEd - 1 - i) * a.NEp;
-                    const double v = f[o], vv = fv[o];
-                    double fe = owner ? v * iin : -v * iin;                 // SetRTFluxOnEdges (edges.go:454-483)
-                    fe -= owner ? vv * iin : vv * iin * -1.0;               // AddDissipation edge DOFs (dissipation.go:316-333)
-                    myF[(2 * NI + le * NEd + i) * SE + lane] = fe;
+                    // SetRTFluxOnEdges (edges.go:454-483) on F - F_visc: k_visc_edge subtracted the viscous normal flux from
+                    // eflux in place (AddDissipation's edge DOFs, dissipation.go:316-333)
+                    const double v = f[o];
+                    myF[(2 * NI + le * NEd + i) * SE + lane] = owner ? v * iin : -v * iin;
                 }
                 if (a.ph.localDT && n == 0) {
                     wmaxk = fmax(wmaxk, a.agg[slot]);

@@ -263,7 +263,6 @@ struct ElemArgs {
     double *q0, *q1, *q2, *q3, *q4, *R;     // c.Q, Q1..Q4, Residual
     double *qface;                          // [4][3NpEdge][Kp], written for the next stage when non-null
     const double *eflux;                    // [4][NpEdge][NEp] numerical normal flux
-    const double *vflux;                    // [4][NpEdge][NEp] viscous normal flux (dissipation)
     const double *agg, *aggv;               // [NEp]
     double *DT, *DTVisc;                    // [Kp] (local time stepping)
     const double *Jdet, *Jinv, *IInII;      // [Kp], [4][Kp], [3][Kp]
@@ -354,16 +353,8 @@ __global__ void __launch_bounds__(kElemThreads) k_elem(ElemArgs a) {
                 const double v = f[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
                 fe[le * NEd + i] = owner ? v * iin : -v * iin;
             }
-            if (DISS) {
-                // AddDissipation edge DOFs (dissipation.go:316-333): edgeFlux[ii] * IInII * sign; folded into the
-                // same contraction with the opposite sign (RHS = -(1/J) DivInt (F - F_visc))
-                const double *fv = a.vflux + ((size_t)n * NEd) * a.NEp + slot;
-#pragma unroll
-                for (int i = 0; i < NEd; i++) {
-                    const double v = fv[(size_t)(owner ? i : NEd - 1 - i) * a.NEp];
-                    fe[le * NEd + i] -= owner ? v * iin : v * iin * -1.0;
-                }
-            }
+            // (DISS: k_visc_edge has already subtracted the viscous normal flux from eflux in place -- AddDissipation's
+            // edge DOFs, dissipation.go:316-333, enter the same contraction with the opposite sign)
             if (a.ph.localDT) {
                 wmaxk = fmax(wmaxk, a.agg[slot]);
                 if (DISS) vmaxk = fmax(vmaxk, a.aggv[slot]);
