@@ -15,7 +15,7 @@
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
 #include "dfr2d_elem_pipe.cuh"
-#include "dfr2d_elem_tma.cuh"
+#include "dfr2d_elem_ws.cuh"
 #include "dfr2d_grad_mma.cuh"
 #include "dfr2d_elem_mma_diss.cuh"
 
@@ -86,9 +86,9 @@ struct dfr2d_handle {
     bool gradAttrSet = false;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
-    int tmaStages = 0;                // DFR2D_TMA_STAGES override of the ring depth of kernel 5
+    int wsStages = 0;                // DFR2D_WS_STAGES override of the ring depth of kernel 5
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
-    int tmaCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_TMA_CW)
+    int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
     int edgePPT = 0;
     // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
     // single IPC handle / peer pointer gives a partner everything it writes
@@ -660,8 +660,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // (operators of 3 x 15 / 1 x 8 entries: the 8 x 8 x 4 tiles would be mostly padding)
     h->elemKernel = (N >= 2) ? 5 : 1;
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
-    if (const char *ev = getenv("DFR2D_TMA_STAGES")) h->tmaStages = atoi(ev);
-    if (const char *ev = getenv("DFR2D_TMA_CW")) h->tmaCW = atoi(ev) == 12 ? 12 : 8;
+    if (const char *ev = getenv("DFR2D_WS_STAGES")) h->wsStages = atoi(ev);
+    if (const char *ev = getenv("DFR2D_WS_CW")) h->wsCW = atoi(ev) == 12 ? 12 : 8;
     if (const char *ev = getenv("DFR2D_DISS_PREFETCH")) h->dissPrefetch = atoi(ev) > 0 ? 1 : 0;
     {
         std::vector<double> fr;
@@ -1034,36 +1034,36 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
         });
     } else {
         if (h->elemKernel == 5) {
-            ElemTmaArgs ta{};
+            ElemWsArgs ta{};
             ta.a = a;
             ta.nTiles = blocks;
             ta.nExtra = (rk == 0 || rhsOut != nullptr) ? 0 : (rk == 4 ? 4 : 1);
             DISPATCH_N(h->N, {
-                using TD = TmaDim<NN>;
+                using TD = WsDim<NN>;
                 const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words
                 int stages = (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1));
-                stages = std::max(2, std::min(stages, kTmaMaxStages));     // two consumer groups: a waiter may be at most one phase ahead
+                stages = std::max(2, std::min(stages, kWsMaxStages));     // two consumer groups: a waiter may be at most one phase ahead
                 // measured (profiles/r01i_ring_depth.txt): a deeper ring is SLOWER -- the shared memory it takes comes out
                 // of L1, and the 8-byte edge-flux gather lives on L1 hits (neighbouring elements share sectors and
                 // edges).  3 stages for rk 0-2 (121-173 KB), 2 for rk 3 (115 KB) and rk 4 (219 KB, all that fits)
                 stages = std::min(stages, (rk >= 3 && rhsOut == nullptr) ? 2 : 3);
-                if (h->tmaStages > 1) stages = std::min(std::max(2, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))), h->tmaStages);
+                if (h->wsStages > 1) stages = std::min(std::max(2, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))), h->wsStages);
                 ta.nStages = stages;
                 // three consumer groups (12 warps, 152 registers each) need a ring of >= 3 stages: every stage but the last
-                // (rk 4: 109 KB per stage, two fit).  DFR2D_TMA_CW=12 selects them; measured A/B in profiles/r02f_*
-                const bool cw12 = h->tmaCW == 12 && (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1)) >= 3;
-                if (cw12) stages = std::max(3, std::min(h->tmaStages > 1 ? h->tmaStages : 3, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))));
+                // (rk 4: 109 KB per stage, two fit).  DFR2D_WS_CW=12 selects them; measured A/B in profiles/r02f_*
+                const bool cw12 = h->wsCW == 12 && (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1)) >= 3;
+                if (cw12) stages = std::max(3, std::min(h->wsStages > 1 ? h->wsStages : 3, (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1))));
                 ta.nStages = stages;
                 const size_t sm = TD::smem_bytes(ta.nExtra, stages);
                 if (!h->smemAttrSet) {
-                    cudaFuncSetAttribute(k_elem_tma<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
-                    cudaFuncSetAttribute(k_elem_tma<NN, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                    cudaFuncSetAttribute(k_elem_ws<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                    cudaFuncSetAttribute(k_elem_ws<NN, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
                 }
-                if (cw12) k_elem_tma<NN, 12><<<std::min(blocks, h->sms), (12 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
-                else k_elem_tma<NN, 8><<<std::min(blocks, h->sms), (8 + kTmaProdWarps) * 32, sm, h->stream>>>(ta);
+                if (cw12) k_elem_ws<NN, 12><<<std::min(blocks, h->sms), (12 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
+                else k_elem_ws<NN, 8><<<std::min(blocks, h->sms), (8 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
             });
             h->smemAttrSet = true;
-            return launch_check(h, "k_elem_tma");
+            return launch_check(h, "k_elem_ws");
         }
         if (h->elemKernel == 4) {
             ElemMmaArgs ma{};

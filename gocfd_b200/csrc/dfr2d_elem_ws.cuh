@@ -1,15 +1,18 @@
-// k_elem_tma<N>: the inviscid element kernel as a warp-specialised producer/consumer pipeline (kernel #5).
+// k_elem_ws<N>: the inviscid element kernel as a Warp-Specialised producer/consumer pipeline (kernel #5).  (Round 1 called
+// it k_elem_tma; it never used the TMA engine -- the data moves by per-thread cp.async that complete on mbarriers -- so
+// round 2 renamed it.  Profiles r01* / r02a-j still carry the old name.)
 //
 // What the measurements of kernel #4 (k_elem_pipe) said (profiles/r01e_*): per 32-element tile an SM spent
 // ~7,700 cycles = (HBM time of the tile's 97 KB at the SM's bandwidth share, ~4,400) + (DMMA floor, ~2,150) + (flux and
 // epilogue ALU work) -- the parts ADD because every warp does all of them in lock-step phases separated by CTA
 // barriers, so when HBM back-pressures the LSU queue the tensor pipe idles and vice versa.  Here they overlap:
 //
-//   * ONE producer warp per CTA moves every byte asynchronously: the [row][32 elements] slabs of the stage input, of the
-//     RK registers and of the metrics arrive by bulk async copies (cp.async.bulk, the TMA engine, one 256-byte row per
-//     copy so that smem rows can keep the bank-conflict-free stride of 36 doubles), the edge-flux gather by 8-byte
-//     cp.async; both complete on the stage's mbarrier.  No load ever occupies a register or an issue slot of a warp
-//     that does arithmetic.
+//   * FOUR producer warps per CTA move every byte asynchronously: the [row][32 elements] slabs of the stage input, of
+//     the RK registers and of the metrics arrive by coalesced 16-byte cp.async (two 256-byte rows per warp instruction,
+//     shared-memory rows at a stride of 36 doubles), the edge-flux gather by 8-byte cp.async; all complete on the
+//     stage's mbarrier (cp.async.mbarrier.arrive.noinc).  No load ever occupies a register or an issue slot of a warp
+//     that does arithmetic.  (One cp.async.bulk -- the TMA engine -- per 256-byte row was measured first: 13 ms, a bulk
+//     copy is a uniform-datapath instruction and lane-dependent addresses serialise.)
 //   * 8 consumer warps work in two groups of 4 on two different tiles; inside a group every warp owns 8 columns
 //     (= one DMMA n-tile) of the tile for ALL four conserved variables and never synchronises with another warp:
 //     no __syncthreads in the steady state, phases of different warps drift apart and fill each other's bubbles.
@@ -27,11 +30,11 @@
 
 namespace dfr2d {
 
-constexpr int kTmaProdWarps = 4;                         // warp 0: row slabs + dt; warps 1-3: gather of local edge 0-2
-constexpr int kTmaFullCount = kTmaProdWarps * 64;        // per producer lane: its cp.async completions + one plain arrive
-constexpr int kTmaMaxStages = 6;
+constexpr int kWsProdWarps = 4;                         // warp 0: row slabs + dt; warps 1-3: gather of local edge 0-2
+constexpr int kWsFullCount = kWsProdWarps * 64;        // per producer lane: its cp.async completions + one plain arrive
+constexpr int kWsMaxStages = 6;
 
-template <int N> struct TmaDim {
+template <int N> struct WsDim {
     static constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF3 = Dim<N>::NF3;
     static constexpr int SE = 36;                                  // row stride of the slabs (doubles): 4 k-rows x 8 n conflict free
     static constexpr int M1 = (NI + 7) / 8, KI = (NI + 3) / 4;
@@ -66,9 +69,6 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned coun
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
     unsigned done;
@@ -76,15 +76,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     } while (!done);
-}
-// global -> shared bulk async copy (TMA engine), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(double *dst, const double *src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_u32(unsigned dst, const double *src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async16_u32(unsigned dst, const double *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -110,17 +101,17 @@ __device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-struct ElemTmaArgs {
+struct ElemWsArgs {
     ElemArgs a;
     int nTiles, nStages, nExtra;
 };
 
 // CW = consumer warps (8: two groups of four, 224 registers each; 12: three groups, 152 registers each)
 template <int N, int CW>
-__global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemTmaArgs args) {
-    constexpr int kTmaConsWarps = CW, kTmaThreads = (CW + kTmaProdWarps) * 32, kGroups = CW / 4;
+__global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsArgs args) {
+    constexpr int kWsConsWarps = CW, kWsThreads = (CW + kWsProdWarps) * 32, kGroups = CW / 4;
     constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = (CW == 8) ? 224 : 152;
-    using TD = TmaDim<N>;
+    using TD = WsDim<N>;
     constexpr int NI = TD::NI, NEd = TD::NEd, NF3 = TD::NF3, SE = TD::SE, E = kElemsPerBlock;
     constexpr int M1 = TD::M1, KI = TD::KI, KE = TD::KE, K1 = TD::K1, M2 = TD::M2, K2 = TD::K2;
     const ElemArgs &a = args.a;
@@ -131,16 +122,16 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
         }
         return;
     }
-    extern __shared__ __align__(128) double smem_tma[];
-    double *smem = smem_tma;
-    __shared__ __align__(8) unsigned long long fullBar[kTmaMaxStages], emptyBar[kTmaMaxStages];
+    extern __shared__ __align__(128) double smem_ws[];
+    double *smem = smem_ws;
+    __shared__ __align__(8) unsigned long long fullBar[kWsMaxStages], emptyBar[kWsMaxStages];
     const int S = args.nStages, nExtra = args.nExtra;
     const int stageDoubles = TD::xOff + nExtra * TD::xSize;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t Kp = a.Kp;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
-            mbar_init(&fullBar[s], kTmaFullCount);
+            mbar_init(&fullBar[s], kWsFullCount);
             mbar_init(&emptyBar[s], 4);              // the four consumer warps of the tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -150,8 +141,8 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
     {
         const Ops<N> &op = ops<N>();
         constexpr int NFL = Dim<N>::NpFlux;
-        for (int t = threadIdx.x; t < NI * NFL; t += kTmaThreads) smem[t] = op.DivInt[t / NFL][t % NFL];
-        for (int t = threadIdx.x; t < NF3 * NI; t += kTmaThreads) smem[NI * NFL + t] = op.FEI[t / NI][t % NI];
+        for (int t = threadIdx.x; t < NI * NFL; t += kWsThreads) smem[t] = op.DivInt[t / NFL][t % NFL];
+        for (int t = threadIdx.x; t < NF3 * NI; t += kWsThreads) smem[NI * NFL + t] = op.FEI[t / NI][t % NI];
     }
     __syncthreads();
 
@@ -164,12 +155,12 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
     }
     const int nLocal = (args.nTiles > (int)blockIdx.x) ? (args.nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp >= kTmaConsWarps) {
+    if (warp >= kWsConsWarps) {
         // =================================== producer warps ==================================================
         // 168 registers per thread are allotted at launch (12 warps x 168 x 32 = 64,512); the producers keep 56 and
         // hand the rest to the consumers (setmaxnreg, 4 x 56 + 8 x 224 = the same total)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));
-        const int pw = warp - kTmaConsWarps;
+        const int pw = warp - kWsConsWarps;
         if (pw == 0) {
             // ---- row slabs by the TMA engine; dt per element (lane = element) -------------------------------------
             int c0 = 0, c1 = 0, c2 = 0;
@@ -183,7 +174,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
                 }
             };
             load_dt(0);
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");      // consumers hold their operator fragments
+            asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");      // consumers hold their operator fragments
             int s = 0;
             unsigned ph = 1;                        // parity of the previous phase of emptyBar[s]
             for (int n = 0; n < nLocal; n++) {
@@ -228,7 +219,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
             load_slot(1, ns);
             load_iin(1, iinN);
             load_slot(2, ns2);
-            asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");
             const size_t srcStep = (size_t)a.NEp;
             int s = 0;
             unsigned ph = 1;                        // parity of the previous phase of emptyBar[s]
@@ -312,7 +303,7 @@ __global__ void __launch_bounds__((CW + kTmaProdWarps) * 32, 1) k_elem_tma(ElemT
                 a2[mt][ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
             }
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kTmaThreads) : "memory");      // operator table consumed: the ring may be filled
+        asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");      // operator table consumed: the ring may be filled
         bool bad = false;
         double *dst = (a.rk == 0) ? a.q1 : (a.rk == 1) ? a.q2 : (a.rk == 2) ? a.q3 : (a.rk == 3) ? a.q4 : a.q0;
 

@@ -19,7 +19,7 @@
 #pragma once
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
-#include "dfr2d_elem_tma.cuh"
+#include "dfr2d_elem_ws.cuh"
 
 namespace dfr2d {
 

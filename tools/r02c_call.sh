@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round 2, call c (1 GPU): config tests as specified, the N=1 bench line (with C2/C3 under "also"), the reference arm on the
-# full mesh, and an ncu --set full capture of k_elem_tma WITH source attribution (bank conflicts per SASS line).
+# full mesh, and an ncu --set full capture of k_elem_ws WITH source attribution (bank conflicts per SASS line).
 tag=${1:-r02c}
 o=gpurun_out
 mkdir -p $o
@@ -10,6 +10,6 @@ timeout 600 python bench.py --steps 20 --warmup 3 > $o/${tag}_bench_c5.json 2> $
 cat $o/${tag}_bench_c5.json
 timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $o/${tag}_bench_reference.json 2> $o/${tag}_bench_reference.err; echo "ref rc=$?"; tail -3 $o/${tag}_bench_reference.err
 cat $o/${tag}_bench_reference.json
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_elem_tma' -s 6 -c 2 -f -o $o/${tag}_elem_tma \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_elem_ws' -s 6 -c 2 -f -o $o/${tag}_elem_tma \
     python bench.py --nx 1000 --steps 2 --warmup 3 --no-cpu-baseline --no-also > $o/${tag}_ncu_elem.log 2>&1
 tail -2 $o/${tag}_ncu_elem.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, call e (1 GPU): full GPU suite after the padding cut of k_elem_tma + new plot fields, bench line.
+# Round 2, call e (1 GPU): full GPU suite after the padding cut of k_elem_ws + new plot fields, bench line.
 tag=${1:-r02e}
 o=gpurun_out
 mkdir -p $o
