@@ -524,6 +524,7 @@ class Runner:
         self.barrier()
         t0 = time.perf_counter()
         dev.set_state(self.q_host)
+        t1 = time.perf_counter()
         info = None
         for _ in range(steps):
             if self.world == 1 or driver == "peer":
@@ -531,17 +532,21 @@ class Runner:
             else:
                 self.nccl_step()
                 info = dev.step_finish(sync=True)
+        t2 = time.perf_counter()
         dev.get_state(self.q_host)
         self.barrier()
         el = self.reduce_max(time.perf_counter() - t0)
+        el_loop = self.reduce_max(t2 - t1)
         qb = 4 * self.p.NpInt * (self.k1 - self.k0) * 8
         # checksum of the state after exactly `steps` steps from the initial condition: identical at every N
         own = self.q_host[:, :, self.k0 - self.k_off:self.k1 - self.k_off]
         sq = self.reduce_list([float((own[v] * own[v]).sum()) for v in range(4)], self.dist.ReduceOp.SUM if self.world > 1 else None)
         return ({"value": self.dof_per_step * steps / el, "unit": "DOF-stage-updates/s",
                  "h2d_bytes_per_step": qb / steps, "d2h_bytes_per_step": qb / steps + 40,
+                 "step_loop_value": self.dof_per_step * steps / el_loop,
                  "what": "per rank: dfr2d_set_state(pinned host Q, own columns) + %d x dfr2d_step(1, info) + dfr2d_get_state; "
-                         "state copies happen once per run (device-resident solver), bytes are total / steps" % steps},
+                         "state copies happen once per run (device-resident solver), bytes are total / steps; step_loop_value = the "
+                         "%d host-synchronised steps alone, without the two state copies" % (steps, steps)},
                 {"after_steps": steps, "time": info["time"], "l2": [float(np.sqrt(v)) for v in sq]})
 
     def close(self):

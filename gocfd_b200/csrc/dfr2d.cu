@@ -929,8 +929,11 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
     // points per thread: DFR2D_EDGE_PPT overrides (must divide N+2); agg is combined by atomicMax when an edge is split
     // measured (tools/sweep_edge_ppt.sh): whole edges per thread on big meshes, one point per thread when there are
     // too few edges to fill the machine (C2: 300K edges)
+    // (r2) the switch-over was 64 sms 256 = 2.4M edges in round 1, bracketed only by C2 (300K edges: one point per
+    // thread wins) and C5 (12M: whole edges win).  The 8-GPU partitions of C5 (1.5M edges) fell on the wrong side:
+    // 0.285 ms where whole edges take 0.19 ms (profiles/r02h_*).  16 sms 256 = 606K edges.
     int ppt = h->edgePPT;
-    if (ppt <= 0) ppt = (h->NE < 64 * h->sms * 256) ? 1 : h->N + 2;
+    if (ppt <= 0) ppt = (h->NE < 16 * h->sms * 256) ? 1 : h->N + 2;
     if ((h->N + 2) % ppt != 0) ppt = h->N + 2;
     // the boundary / cut-edge list is short (O(sqrt K) edges): one point per thread there, or a few dozen CTAs walk whole
     // edges through the BC transcendental functions one point after the other (measured at C5: 57 us for 8,000 edges)
