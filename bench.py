@@ -597,9 +597,11 @@ class Runner:
             d.set_clock(0.0, 0)
         t0 = time.perf_counter()
         lib.multi_set_state(devs, q_host)
+        t1 = time.perf_counter()
         info = None
         for _ in range(steps):
             info = lib.multi_step(devs, 1, sync=True)
+        t2 = time.perf_counter()
         lib.multi_get_state(devs, q_host)
         sync_all()
         el = time.perf_counter() - t0
@@ -611,6 +613,7 @@ class Runner:
         return {"value": self.dof_per_step * steps / (ms * 1e-3), "ms_per_step": ms / steps, "gpu_launches": int(launches),
                 "host_issue_ms_per_step": t_issue * 1e3 / steps, "create_s": create_s, "host_problem_build_s": build_s,
                 "e2e": {"value": self.dof_per_step * steps / el, "unit": "DOF-stage-updates/s",
+                        "step_loop_value": self.dof_per_step * steps / (t2 - t1),
                         "what": "one process: dfr2d_multi_set_state + %d x dfr2d_multi_step(1, info) + dfr2d_multi_get_state" % steps},
                 "checksum": {"after_steps": steps, "time": info["time"], "l2": l2},
                 "timeline_ms": {"phases": list(lib.PROFILE_PHASES),
