@@ -78,7 +78,7 @@ struct dfr2d_handle {
                                       // (DFR2D_GRAD_KERNEL; 2 was round 1's one-tile-per-CTA DMMA kernel, retired)
     double *gradTable = nullptr, *gradMxy = nullptr;
     int gradMG = 3;                   // m-tiles per accumulation group of k_grad_pipe (DFR2D_GRAD_MG = 2 | 3)
-    int dissElemKernel = 1;           // element kernel of the PerssonC0 path: 1 = k_elem<N,true> (DFMA), 3 = k_elem_mma_diss
+    int dissElemKernel = 1;           // element kernel of the PerssonC0 path: 1 = k_elem<N,true> (DFMA), 3 = k_elem_mma_diss, 5 = k_elem_ws<N,8,true>
                                       // (DMMA, opt-in until measured; DFR2D_DISS_ELEM_KERNEL)
     double *mmaDissFrags = nullptr;
     int mmaDissGrid = 0;
@@ -87,6 +87,7 @@ struct dfr2d_handle {
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int wsStages = 0;                // DFR2D_WS_STAGES override of the ring depth of kernel 5
+    bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
     int edgePPT = 0;
@@ -1006,6 +1007,28 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     a.stepIndex = h->stepIndex;
     a.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->ph.dissipation && h->dissElemKernel == 5) {
+        // the warp-specialised ring of kernel 5 with the PerssonC0 terms (k_elem_ws<N, 8, true>, dfr2d_elem_ws.cuh)
+        ElemWsArgs ta{};
+        ta.a = a;
+        ta.nTiles = blocks;
+        ta.nExtra = (rk == 0 || rhsOut != nullptr) ? 0 : (rk == 4 ? 4 : 1);
+        DISPATCH_N(h->N, {
+            using TD = WsDim<NN>;
+            const size_t maxSmem = 232448 - 256;
+            const int nExtraS = TD::extras_in_smem(ta.nExtra, true);
+            int stages = (int)(maxSmem / TD::smem_bytes_diss(nExtraS, 1));
+            stages = std::max(2, std::min(stages, h->wsStages > 1 ? h->wsStages : 2));
+            if (TD::smem_bytes_diss(nExtraS, stages) > maxSmem) { h->err = "k_elem_ws<diss>: ring does not fit"; return 2; }
+            ta.nStages = stages;
+            if (!h->dissWsAttrSet) {
+                cudaFuncSetAttribute(k_elem_ws<NN, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                h->dissWsAttrSet = true;
+            }
+            k_elem_ws<NN, 8, true><<<std::min(blocks, h->sms), (8 + kWsProdWarps) * 32, TD::smem_bytes_diss(nExtraS, stages), h->stream>>>(ta);
+        });
+        return launch_check(h, "k_elem_ws<diss>");
+    }
     if (h->ph.dissipation && h->dissElemKernel == 3) {
         ElemMmaArgs ma{};
         ma.a = a;
@@ -1059,11 +1082,11 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
                 ta.nStages = stages;
                 const size_t sm = TD::smem_bytes(ta.nExtra, stages);
                 if (!h->smemAttrSet) {
-                    cudaFuncSetAttribute(k_elem_ws<NN, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
-                    cudaFuncSetAttribute(k_elem_ws<NN, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                    cudaFuncSetAttribute(k_elem_ws<NN, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                    cudaFuncSetAttribute(k_elem_ws<NN, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
                 }
-                if (cw12) k_elem_ws<NN, 12><<<std::min(blocks, h->sms), (12 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
-                else k_elem_ws<NN, 8><<<std::min(blocks, h->sms), (8 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
+                if (cw12) k_elem_ws<NN, 12, false><<<std::min(blocks, h->sms), (12 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
+                else k_elem_ws<NN, 8, false><<<std::min(blocks, h->sms), (8 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
             });
             h->smemAttrSet = true;
             return launch_check(h, "k_elem_ws");

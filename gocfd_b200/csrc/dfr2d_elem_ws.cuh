@@ -59,6 +59,13 @@ template <int N> struct WsDim {
     static constexpr int xSize = 4 * NI * SE;
     static int stage_doubles(int nExtra) { return xOff + nExtra * xSize; }
     static size_t smem_bytes(int nExtra, int stages) { return (size_t)stage_doubles(nExtra) * stages * sizeof(double); }
+    // PerssonC0 variant (DISS): one more metric row (1 - sin(pi sigma / 2) of the limiter) and two more slabs, the interior
+    // rows of DissX and DissY.  At rk 4 only q0 and q2 are staged; q3 and R are read from global memory in the epilogue
+    // (four extra slabs would not leave room for a second ring stage).
+    static constexpr int xOffD = gOff + 10 * 32;
+    __host__ __device__ static int extras_in_smem(int nExtra, bool diss) { return (diss && nExtra == 4) ? 2 : nExtra; }
+    __host__ __device__ static int stage_doubles_diss(int nExtraS) { return xOffD + (nExtraS + 2) * xSize; }
+    static size_t smem_bytes_diss(int nExtraS, int stages) { return (size_t)stage_doubles_diss(nExtraS) * stages * sizeof(double); }
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
@@ -107,7 +114,12 @@ struct ElemWsArgs {
 };
 
 // CW = consumer warps (8: two groups of four, 224 registers each; 12: three groups, 152 registers each)
-template <int N, int CW>
+// DISS = the element kernel of the PerssonC0 path (AddDissipation, dissipation.go:274-346, and LimitFilterSolution on
+// RHSQ, euler.go:496-501, dissipation.go:520-542) on the same ring: the interior dissipation DOFs join Fr / Fs before
+// the DivInt contraction (the edge DOFs already carry F - F_visc: k_visc_edge subtracts in place), the modal limiter is
+// two more DMMA products through the warp's own columns of the dead DissX / DissY slabs, the viscous dt limit joins the
+// dt logic (euler.go:945-1002), and there is no fused interpolation (k_diss_prepare needs the vertex-merged sigma first).
+template <int N, int CW, bool DISS>
 __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsArgs args) {
     constexpr int kWsConsWarps = CW, kWsThreads = (CW + kWsProdWarps) * 32, kGroups = CW / 4;
     constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = (CW == 8) ? 224 : 152;
@@ -126,7 +138,10 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     double *smem = smem_ws;
     __shared__ __align__(8) unsigned long long fullBar[kWsMaxStages], emptyBar[kWsMaxStages];
     const int S = args.nStages, nExtra = args.nExtra;
-    const int stageDoubles = TD::xOff + nExtra * TD::xSize;
+    const int nExtraS = TD::extras_in_smem(nExtra, DISS);           // extra RK registers staged in the ring
+    constexpr int XO = DISS ? TD::xOffD : TD::xOff;                  // first extra slab
+    const int dOff = XO + nExtraS * TD::xSize;                      // DISS: DissX slab, DissY behind it
+    const int stageDoubles = DISS ? TD::stage_doubles_diss(nExtraS) : TD::xOff + nExtra * TD::xSize;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t Kp = a.Kp;
     if (threadIdx.x == 0) {
@@ -142,7 +157,14 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
         const Ops<N> &op = ops<N>();
         constexpr int NFL = Dim<N>::NpFlux;
         for (int t = threadIdx.x; t < NI * NFL; t += kWsThreads) smem[t] = op.DivInt[t / NFL][t % NFL];
-        for (int t = threadIdx.x; t < NF3 * NI; t += kWsThreads) smem[NI * NFL + t] = op.FEI[t / NI][t % NI];
+        if (!DISS) {
+            for (int t = threadIdx.x; t < NF3 * NI; t += kWsThreads) smem[NI * NFL + t] = op.FEI[t / NI][t % NI];
+        } else {
+            for (int t = threadIdx.x; t < NI * NI; t += kWsThreads) {
+                smem[NI * NFL + t] = op.Vinv[t / NI][t % NI];
+                smem[NI * NFL + NI * NI + t] = op.V[t / NI][t % NI];
+            }
+        }
     }
     __syncthreads();
 
@@ -150,6 +172,10 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     if (!a.ph.localDT) {
         const double gw = __longlong_as_double((long long)a.sc->wave[a.slot][0]);
         dtGlobal = a.ph.CFL / gw;
+        if (DISS) {              // calculateGlobalDT with the viscous limit (euler.go:956-966)
+            const double gv = __longlong_as_double((long long)a.sc->wave[a.slot][1]);
+            dtGlobal = fmin(dtGlobal, a.ph.Cdiff / gv);
+        }
         const double t = a.sc->time[a.par];
         if (t + dtGlobal > a.ph.FinalTime) dtGlobal = a.ph.FinalTime - t;
     }
@@ -164,13 +190,20 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
         if (pw == 0) {
             // ---- row slabs by the TMA engine; dt per element (lane = element) -------------------------------------
             int c0 = 0, c1 = 0, c2 = 0;
-            double g0 = 0, g1 = 0, g2 = 0, dtOld = 0;
+            double g0 = 0, g1 = 0, g2 = 0, dtOld = 0, gvMax = 0, dtvOld = 0, sig = 0;
             auto load_dt = [&](int n) {
-                if (a.ph.localDT && n < nLocal) {
-                    const size_t kk = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E + lane;
+                if (n >= nLocal) return;
+                const size_t kk = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E + lane;
+                if (DISS) sig = a.sigma[kk];
+                if (a.ph.localDT) {
                     c0 = a.etoe[kk]; c1 = a.etoe[Kp + kk]; c2 = a.etoe[2 * Kp + kk];
-                    g0 = a.agg[c0 >= 0 ? c0 : -1 - c0]; g1 = a.agg[c1 >= 0 ? c1 : -1 - c1]; g2 = a.agg[c2 >= 0 ? c2 : -1 - c2];
+                    c0 = c0 >= 0 ? c0 : -1 - c0; c1 = c1 >= 0 ? c1 : -1 - c1; c2 = c2 >= 0 ? c2 : -1 - c2;
+                    g0 = a.agg[c0]; g1 = a.agg[c1]; g2 = a.agg[c2];
                     dtOld = a.DT[kk];
+                    if (DISS) {
+                        gvMax = fmax(fmax(a.aggv[c0], a.aggv[c1]), a.aggv[c2]);
+                        dtvOld = a.DTVisc[kk];
+                    }
                 }
             };
             load_dt(0);
@@ -184,17 +217,24 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 const unsigned stU = smem_u32(st);
                 // stage input, the stage-3 residual (rk 4) and the metrics: coalesced 16-byte async copies
                 slab_g2s<4 * NI, SE>(stU + (unsigned)(TD::qOff * sizeof(double)), a.qs + k0, Kp, lane);
-                if (nExtra == 4) slab_g2s<4 * NI, SE>(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)), a.R + k0, Kp, lane);
+                if (!DISS && nExtra == 4) slab_g2s<4 * NI, SE>(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)), a.R + k0, Kp, lane);
                 if (lane < 16) cp_async16_u32(stU + (unsigned)((TD::gOff + 2 * lane) * sizeof(double)), a.Jdet + k0 + 2 * lane);
                 slab_g2s<4, 32>(stU + (unsigned)((TD::gOff + 32) * sizeof(double)), a.Jinv + k0, Kp, lane);
                 double dtk = dtGlobal;
                 if (a.ph.localDT) {
+                    // InitializeDT at stage 0, DT = max(DT, aggregates), CalculateLocalDT (euler.go:637-643, :973-1002)
                     const double wmaxk = fmax(fmax(g0, g1), g2);
                     const double d = (a.rk == 0) ? -100.0 : dtOld;
                     dtk = a.ph.CFL / fmax(d, wmaxk);
-                    if (a.rhsOut == nullptr) a.DT[k0 + lane] = dtk;
+                    if (DISS) {
+                        double dtv = fmax(dtvOld, gvMax);
+                        if (dtv > 1.e-9) { dtv = a.ph.Cdiff / dtv; dtk = fmin(dtk, dtv); }
+                        if (a.rhsOut == nullptr && k0 + lane < (size_t)a.K) a.DTVisc[k0 + lane] = dtv;
+                    }
+                    if (a.rhsOut == nullptr && (!DISS || k0 + lane < (size_t)a.K)) a.DT[k0 + lane] = dtk;
                 }
                 st[TD::gOff + 8 * 32 + lane] = dtk;
+                if (DISS) st[TD::gOff + 9 * 32 + lane] = 1.0 - sin(0.5 * 3.14159265358979323846 * sig);
                 cp_async_arrive_noinc(&fullBar[s]);
                 mbar_arrive(&fullBar[s]);
                 load_dt(n + 1);
@@ -226,11 +266,17 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
             for (int n = 0; n < nLocal; n++) {
                 if (n >= S) mbar_wait(&emptyBar[s], ph);
                 double *st = smem + (size_t)s * stageDoubles;
-                if (le < (nExtra == 4 ? 3 : nExtra)) {
+                if (le < (DISS ? nExtraS : (nExtra == 4 ? 3 : nExtra))) {
                     // RK register slab number `le` of this stage (q0, q2, q3); R travels with the stage input in warp 0
                     const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
-                    slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((TD::xOff + le * TD::xSize) * sizeof(double)),
+                    slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((XO + le * TD::xSize) * sizeof(double)),
                                          (le == 0 ? a.q0 : (le == 1 ? a.q2 : a.q3)) + k0, Kp, lane);
+                }
+                if (DISS && le >= 1) {
+                    // interior rows of DissX (gather warp 1) and DissY (gather warp 2)
+                    const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
+                    slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((dOff + (le - 1) * TD::xSize) * sizeof(double)),
+                                         (le == 1 ? a.dissX : a.dissY) + k0, Kp, lane);
                 }
                 const bool own = cs >= 0;
                 st[TD::gOff + (5 + le) * 32 + lane] = own ? iin : -iin;
@@ -272,7 +318,24 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
         const double *opD = smem, *opF = smem + NI * NFL;
         // operator fragments, A[row = fr][k = fc] of every (m-tile, k-step); k-steps 2m / 2m+1 carry Fr / Fs of points
         // 4m..4m+3, k-steps 2KI.. the edge rows
-        double a1[M1][K1], a2[M2][K2];
+        double a1[M1][K1], a2[DISS ? 1 : M2][DISS ? 1 : K2];
+        // DISS: Vinv and V (LimitFilterSolution, dissipation.go:606-622) as A fragments, both with the permuted row order;
+        // mfRow = ModeFilter of this lane's modes (mode 0 is never scaled)
+        double aVi[DISS ? M1 : 1][DISS ? KI : 1], aV[DISS ? M1 : 1][DISS ? KI : 1], mfRow[DISS ? M1 : 1];
+        if (DISS) {
+            const double *opVi = smem + NI * NFL, *opV = opVi + NI * NI;
+#pragma unroll
+            for (int mt = 0; mt < M1; mt++) {
+                const int row = 8 * mt + frP;
+                mfRow[mt] = (row >= 1 && row < NI) ? ops<N>().mf[row] : 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KI; ks++) {
+                    const int j = 4 * ks + fc;
+                    aVi[mt][ks] = (row < NI && j < NI) ? opVi[row * NI + j] : 0.0;
+                    aV[mt][ks] = (row < NI && j < NI) ? opV[row * NI + j] : 0.0;
+                }
+            }
+        }
 #pragma unroll
         for (int mt = 0; mt < M1; mt++) {
             const int row = 8 * mt + frP;
@@ -294,13 +357,15 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 a1[mt][2 * KI + ke] = (row < NI && r < TD::NE3k) ? opD[row * NFL + 2 * NI + r] : 0.0;
             }
         }
+        if (!DISS) {
 #pragma unroll
-        for (int mt = 0; mt < M2; mt++) {
-            const int row = 8 * mt + fr;
+            for (int mt = 0; mt < M2; mt++) {
+                const int row = 8 * mt + fr;
 #pragma unroll
-            for (int ks = 0; ks < K2; ks++) {
-                const int j = 4 * ks + fc;
-                a2[mt][ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
+                for (int ks = 0; ks < K2; ks++) {
+                    const int j = 4 * ks + fc;
+                    a2[DISS ? 0 : mt][DISS ? 0 : ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
+                }
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");      // operator table consumed: the ring may be filled
@@ -337,6 +402,15 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                     for (int v = 0; v < 4; v++) {
                         Fr[v] = jd * (j0 * Fx[v] + j1 * Fy[v]);
                         Fs[v] = jd * (j2 * Fx[v] + j3 * Fy[v]);
+                    }
+                    if (DISS) {          // AddDissipation interior DOFs (dissipation.go:310-315), opposite sign
+                        const double *sDX = st + dOff, *sDY = sDX + TD::xSize;
+#pragma unroll
+                        for (int v = 0; v < 4; v++) {
+                            const double dix = sDX[(v * NI + p) * SE + eB], diy = sDY[(v * NI + p) * SE + eB];
+                            Fr[v] -= jd * (j0 * dix + j1 * diy);
+                            Fs[v] -= jd * (j2 * dix + j3 * diy);
+                        }
                     }
                 } else if (TD::nMoved > 0) {
                     // idle point slot of the last interior k-steps: the numerical flux of edge rows NE3k + t (Fr slot) and
@@ -383,8 +457,72 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
             // ---- epilogue in accumulator layout: rows 8 mt + fr, columns eC, eC + 1 ------------------------------
             const double2 jdc = *reinterpret_cast<const double2 *>(&g[eC]);
             const double2 dt = *reinterpret_cast<const double2 *>(&g[8 * 32 + eC]);
-            const double mo0 = -(1.0 / jdc.x), mo1 = -(1.0 / jdc.y);
-            const double *sX = st + TD::xOff;
+            double mo0 = -(1.0 / jdc.x), mo1 = -(1.0 / jdc.y);
+            const double *sX = st + XO;
+            if (DISS) {
+                // LimitFilterSolution(RHSQ): RHS = -(1/J) C1 -> Vinv -> modes i >= 1 times mf_i (1 - sin(pi sigma / 2)) -> V,
+                // through this warp's own 8 columns of the DissX slab (RHS) and the DissY slab (modes): both are dead
+                // once the flux loop above has read them, and no other warp ever touches these columns
+                double *sR = st + dOff, *sU = sR + TD::xSize;
+                const double2 oma = *reinterpret_cast<const double2 *>(&g[9 * 32 + eC]);
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) {
+                        const int i = 8 * mt + frP;
+                        if (i < NI)
+                            *reinterpret_cast<double2 *>(&sR[(v * NI + i) * SE + eC]) = make_double2(c1[v][mt][0] * mo0, c1[v][mt][1] * mo1);
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) c1[v][mt][0] = c1[v][mt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KI; ks++) {
+                    const int j = 4 * ks + fc;
+                    double b[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (4 * ks + 3 < NI || j < NI) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) b[v] = sR[(v * NI + j) * SE + eB];
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+#pragma unroll
+                        for (int mt = 0; mt < M1; mt++) dmma884(c1[v][mt][0], c1[v][mt][1], aVi[mt][ks], b[v]);
+                }
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) {
+                        const int i = 8 * mt + frP;
+                        if (i < NI) {
+                            double2 uh = make_double2(c1[v][mt][0], c1[v][mt][1]);
+                            if (i >= 1) { uh.x *= mfRow[mt] * oma.x; uh.y *= mfRow[mt] * oma.y; }
+                            *reinterpret_cast<double2 *>(&sU[(v * NI + i) * SE + eC]) = uh;
+                        }
+                    }
+                __syncwarp();
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M1; mt++) c1[v][mt][0] = c1[v][mt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KI; ks++) {
+                    const int j = 4 * ks + fc;
+                    double b[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (4 * ks + 3 < NI || j < NI) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) b[v] = sU[(v * NI + j) * SE + eB];
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+#pragma unroll
+                        for (int mt = 0; mt < M1; mt++) dmma884(c1[v][mt][0], c1[v][mt][1], aV[mt][ks], b[v]);
+                }
+                mo0 = mo1 = 1.0;         // c1 now holds the limited RHS itself
+            }
 #pragma unroll
             for (int v = 0; v < 4; v++) {
 #pragma unroll
@@ -414,8 +552,11 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                         } else {
                             const double2 q0v = *reinterpret_cast<const double2 *>(&sX[so]);
                             const double2 q2v = *reinterpret_cast<const double2 *>(&sX[so + 1 * TD::xSize]);
-                            const double2 q3v = *reinterpret_cast<const double2 *>(&sX[so + 2 * TD::xSize]);
-                            const double2 rv = *reinterpret_cast<const double2 *>(&sX[so + 3 * TD::xSize]);
+                            // (DISS: q3 and the stage-3 residual are not staged at rk 4 -- no room for two ring stages)
+                            const double2 q3v = DISS ? *reinterpret_cast<const double2 *>(a.q3 + o)
+                                                     : *reinterpret_cast<const double2 *>(&sX[so + 2 * TD::xSize]);
+                            const double2 rv = DISS ? *reinterpret_cast<const double2 *>(a.R + o)
+                                                    : *reinterpret_cast<const double2 *>(&sX[so + 3 * TD::xSize]);
                             double2 r;
                             r.x = -q0v.x + RK4_A * q2v.x + RK4_B * q3v.x + RK4_C * qs.x + RK4_D * (dt.x * rv.x) + RK4_E * (dt.x * rhs0);
                             r.y = -q0v.y + RK4_A * q2v.y + RK4_B * q3v.y + RK4_C * qs.y + RK4_D * (dt.y * rv.y) + RK4_E * (dt.y * rhs1);
@@ -429,7 +570,7 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                     }
                 }
             }
-            const bool doInterp = a.rhsOut == nullptr && a.qface != nullptr;
+            const bool doInterp = !DISS && a.rhsOut == nullptr && a.qface != nullptr;
             double c2[4][M2][2];
             double tail[TD::NTail > 0 ? TD::NTail : 1];
             if (doInterp) {
@@ -450,7 +591,7 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
 #pragma unroll
                     for (int v = 0; v < 4; v++)
 #pragma unroll
-                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[mt][ks], b[v]);
+                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[DISS ? 0 : mt][DISS ? 0 : ks], b[v]);
                 }
                 // ragged last rows of FluxEdgeInterp by DFMA: lane = (variable, column) of the warp's 8 columns
                 if (TD::NTail > 0) {

@@ -239,9 +239,11 @@ def test_diss_elem_mma_sod_steps(n, monkeypatch):
     dev.close()
 
 
+@pytest.mark.parametrize("kernel", [3, 5])
 @pytest.mark.parametrize("n,rk", [(4, 2), (1, 0), (1, 2), (2, 0), (3, 0), (3, 2), (4, 0)])
-def test_diss_elem_mma_rhs(n, rk, monkeypatch):
-    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", "3")
+def test_diss_elem_mma_rhs(n, rk, kernel, monkeypatch):
+    """kernel 3 = k_elem_mma_diss, 5 = the warp-specialised ring with the PerssonC0 terms (k_elem_ws<N, 8, true>)."""
+    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", str(kernel))
     c = _sod(n)
     q = _smeared_sod_state(c, 0.004 if n == 1 else 0.002)
     dev, ora = pair(c)
@@ -252,14 +254,33 @@ def test_diss_elem_mma_rhs(n, rk, monkeypatch):
     dev.close()
 
 
-def test_diss_elem_mma_naca_transonic_local_dt(monkeypatch):
-    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", "3")
+@pytest.mark.parametrize("kernel", [3, 5])
+def test_diss_elem_mma_naca_transonic_local_dt(kernel, monkeypatch):
+    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", str(kernel))
     c = make(dict(PolynomialOrder=2, CFL=1.0, LocalTimeStepping=True, MaxIterations=12, Minf=0.8, Alpha=2.0,
                   Limiter="PerssonC0", Kappa=4.5), mesh_path("mesh_NACA0012_inv.su2"))
     dev, ora = pair(c)
     dev.step(12), ora.step(12)
     assert rel_l2(dev.get_state(), ora.get_state()) < TOL
     np.testing.assert_allclose(dev.get_field(0), ora.DT, rtol=1e-10)
+    dev.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 3, 5])
+@pytest.mark.parametrize("n", [1, 2, 3, 4])
+def test_sod_steps_with_dissipation_element_kernels(n, kernel, monkeypatch):
+    """10 Sod steps from a smeared front with every element kernel of the PerssonC0 path: all five RK stages (rk 4 of
+    kernel 5 reads q3 and the stage-3 residual from global memory), viscous global dt, active limiter."""
+    monkeypatch.setenv("DFR2D_DISS_ELEM_KERNEL", str(kernel))
+    c = _sod(n)
+    q = _smeared_sod_state(c, 0.004 if n == 1 else 0.002)
+    dev, ora = pair(c)
+    dev.set_state(q)
+    ora.set_state(q)
+    dev.step(10), ora.step(10)
+    assert ora.SigmaScalar.max() > 0.02 and np.isfinite(ora.get_state()).all()
+    assert rel_l2(dev.get_state(), ora.get_state()) < (2e-10 if n == 1 else TOL)
+    np.testing.assert_allclose(dev.residual(), ora.residual(), rtol=1e-7, atol=1e-11)
     dev.close()
 
 

@@ -143,7 +143,7 @@ def test_peer_connected_processes_match_single_partition(world, diss, tmp_path):
     one.close()
 
 
-@pytest.mark.parametrize("diss_elem", [1, 3])
+@pytest.mark.parametrize("diss_elem", [1, 3, 5])
 def test_naca_front_local_dt_active_dissipation_on_device(diss_elem, monkeypatch):
     """Local time stepping with an ACTIVE sensor (tests/test_c_oracle.py::_naca_front_case: ~400 elements above
     sigma = 0.05 in the first steps, DTVisc > 1e-9 in ~500): viscous dt limit and DTVisc carry-over on the device."""
