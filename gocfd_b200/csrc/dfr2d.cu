@@ -684,9 +684,10 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev) >= 2 ? 3 : 1;
     if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
-    // measured (profiles/r02a_ab_N*.json, 2M triangles): the tensor-core element kernel wins at N = 4 (3.08 -> 2.80 ms) and
-    // loses at N = 2, 3 (operators of 6 / 10 rows: the 8 x 8 x 4 tiles are mostly padding)
-    h->dissElemKernel = (N == 4) ? 3 : 1;
+    // measured (2M triangles, profiles/r02l_ab_N*.json): the warp-specialised ring with the PerssonC0 terms
+    // (k_elem_ws<N,8,true>) wins at every N >= 2 -- N=4: 1.54 ms against 2.37 (k_elem_mma_diss) / 2.60 (k_elem<4,true>);
+    // N=3: 1.23 / 1.85 / 1.54; N=2: 0.77 / 1.19 / 0.82.  N = 1 keeps the DFMA kernel (3 x 15 operators).
+    h->dissElemKernel = (N >= 2) ? 5 : 1;
     if (const char *ev = getenv("DFR2D_DISS_ELEM_KERNEL")) h->dissElemKernel = atoi(ev);
     if (ph.dissipation && h->dissElemKernel == 3) {
         std::vector<double> fr;

@@ -277,8 +277,10 @@ def test_sod_steps_with_dissipation_element_kernels(n, kernel, monkeypatch):
     dev, ora = pair(c)
     dev.set_state(q)
     ora.set_state(q)
-    dev.step(10), ora.step(10)
-    assert ora.SigmaScalar.max() > 0.02 and np.isfinite(ora.get_state()).all()
+    dev.step(1), ora.step(1)
+    assert ora.SigmaScalar.max() > 0.02          # the sensor is on while the front is still under-resolved
+    dev.step(9), ora.step(9)
+    assert np.isfinite(ora.get_state()).all()
     assert rel_l2(dev.get_state(), ora.get_state()) < (2e-10 if n == 1 else TOL)
     np.testing.assert_allclose(dev.residual(), ora.residual(), rtol=1e-7, atol=1e-11)
     dev.close()
