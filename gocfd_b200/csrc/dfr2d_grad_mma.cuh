@@ -25,7 +25,13 @@ namespace dfr2d {
 
 template <int N> struct GradMmaDim {
     static constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
-    static constexpr int NOUT = NI + NF3, MT = (NOUT + 7) / 8;          // produced rows, m-tiles
+    static constexpr int NOUT = NI + NF3;                                // produced rows
+    // (r2) the produced rows fill NOUT / 8 m-tiles plus NOUT mod 8 ragged rows (N=4: 33 = 4 x 8 + 1; N=3: 25 = 3 x 8 + 1;
+    // N=2: 18 = 2 x 8 + 2).  One or two ragged rows are evaluated by plain DFMA (grad_tail) instead of a DMMA m-tile that
+    // is 7/8 zeros: 20-33 % fewer DMMA and A-fragment loads in a kernel that is bound by DMMA issue (ncu: mio_throttle on
+    // the DMMA, shared FP64 pipe 52 % busy, profiles/r02i_*).
+    static constexpr int NTAIL = (NOUT % 8 >= 1 && NOUT % 8 <= 2) ? NOUT % 8 : 0;
+    static constexpr int MT = (NOUT - NTAIL + 7) / 8;                   // m-tiles on the tensor cores
     static constexpr int KI = (NI + 3) / 4, KE = (NEd + 3) / 4;         // k-steps of an interior / an edge block
     static constexpr int KS = 2 * KI + 3 * KE;                          // k-steps of all five blocks
     static constexpr int UROWS = 4 * KI + 12 * KE;                      // B rows per variable (interior block stored once)
@@ -53,11 +59,11 @@ template <int N> void build_grad_table(const double *Div, const double *Bary, st
             for (int ks = 0; ks < GD::blk_ks(r); ks++)
                 for (int l = 0; l < 32; l++) {
                     const int m = 8 * mt + l / 4, c = 4 * ks + l % 4;
-                    if (m < GD::NOUT && c < GD::blk_cols(r))
+                    if (m < GD::NOUT - GD::NTAIL && c < GD::blk_cols(r))
                         out[((size_t)mt * GD::KS + GD::blk_k0(r) + ks) * 32 + l] =
                             Div[(size_t)GD::out_row(m) * GD::NF + GD::blk_col0(r) + c];
                 }
-    for (int m = 0; m < GD::NOUT; m++)
+    for (int m = 0; m < GD::NOUT - GD::NTAIL; m++)
         for (int c = 0; c < 3; c++) out[GD::kFragDoubles + m * 3 + c] = Bary[(size_t)GD::out_row(m) * 3 + c];
 }
 
@@ -169,7 +175,7 @@ __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU,
 #pragma unroll
     for (int mt = 0; mt < MG; mt++) {
         const int m = 8 * (M0 + mt) + fr;
-        if (M0 + mt < MT && m < GD::NOUT) {
+        if (M0 + mt < MT && m < GD::NOUT - GD::NTAIL) {
             const int row = GD::out_row(m);
             const double b0 = pB[8 * (M0 + mt) * 3], b1 = pB[8 * (M0 + mt) * 3 + 1], b2 = pB[8 * (M0 + mt) * 3 + 2];
             constexpr int NI = GD::NI, NEd = GD::NEd;
@@ -211,6 +217,47 @@ __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU,
             }
         }
     }
+}
+
+// The NTAIL ragged rows (all of them edge rows) of one tile by DFMA.  Warp = (variable n, 16-element half); lane l works
+// on element 16 half + (l & 15); the two half warps split the five metric blocks (part 0: interior block 0 and edges 0, 1;
+// part 1: interior block 1 and edge 2) and combine with one shuffle.  Div and Bary entries are constant-bank operands
+// (compile-time indices), the U values / metrics / vertex epsilons / slot data are read from the tile's stage.
+template <int N>
+__device__ __forceinline__ void grad_tail(const GradArgs &a, const double *pUn /* stage U rows of variable n */,
+                                          const double *pMs /* stage metric block */, int n, int half, int lane, int k0) {
+    using GD = GradMmaDim<N>;
+    constexpr int NI = GD::NI, NEd = GD::NEd, E = kElemsPerBlock, SE = GD::SE, KI = GD::KI, KE = GD::KE;
+    const Ops<N> &op = ops<N>();
+    const int e = 16 * half + (lane & 15), part = lane >> 4;
+#pragma unroll
+    for (int t = 0; t < GD::NTAIL; t++) {
+        const int m = 8 * GD::MT + t;
+        const int row = GD::out_row(m);
+        const int le = (m - NI) / NEd, ii = (m - NI) - le * NEd;
+        double gx = 0.0, gy = 0.0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            if ((r == 0 || r == 2 || r == 3) != (part == 0)) continue;
+            double S = 0.0;
+            const int urow0 = GD::blk_urow0(r), col0 = GD::blk_col0(r);
+#pragma unroll
+            for (int j = 0; j < GD::blk_cols(r); j++) S = fma(op.Div[row][col0 + j], pUn[(urow0 + j) * SE + e], S);
+            gx = fma(pMs[(2 * r) * E + e], S, gx);
+            gy = fma(pMs[(2 * r + 1) * E + e], S, gy);
+        }
+        gx += __shfl_xor_sync(0xffffffffu, gx, 16);
+        gy += __shfl_xor_sync(0xffffffffu, gy, 16);
+        if (part == 0 && k0 + e < a.K) {
+            const double eps = op.Bary[row][0] * pMs[10 * E + e] + op.Bary[row][1] * pMs[11 * E + e] + op.Bary[row][2] * pMs[12 * E + e];
+            const long long s = __double_as_longlong(pMs[(19 + le) * E + e]);
+            const bool own = s >= 0;
+            const size_t slot = (size_t)(own ? s : -1 - s);
+            a.vn[((size_t)((own ? 0 : 4) + n) * NEd + (own ? ii : NEd - 1 - ii)) * a.NEp + slot] =
+                pMs[(13 + le) * E + e] * (gx * eps) + pMs[(16 + le) * E + e] * (gy * eps);
+        }
+    }
+    (void)KI; (void)KE;
 }
 
 template <int N, int MG>      // MG: m-tiles accumulated at a time (2 or 3)
@@ -363,6 +410,11 @@ __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradP
         if (MG < MT) grad_mgroup<N, MG, MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
         if (2 * MG < MT) grad_mgroup<N, MG, 2 * MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
         static_assert(3 * MG >= MT, "m-groups");
+        if (GD::NTAIL > 0) {
+            unsigned oT = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles;
+            asm volatile("" : "+r"(oT));
+            grad_tail<N>(a, smem + oT + n * UROWS * SE, smem + oT + PD::kUDoubles, n, half, lane, k0);
+        }
         asm volatile("cp.async.wait_all;" ::: "memory");
         group_bar(group);          // stage st^1 is complete and every warp of the group has finished reading stage st
     }

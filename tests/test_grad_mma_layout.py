@@ -22,7 +22,8 @@ def _dims(n):
     ni, ned = (n + 1) * (n + 2) // 2, n + 2
     nf = (n + 2) * (n + 4)
     nout = ni + 3 * ned
-    mt, ki, ke = (nout + 7) // 8, (ni + 3) // 4, (ned + 3) // 4
+    ntail = nout % 8 if 1 <= nout % 8 <= 2 else 0        # ragged rows: plain DFMA (grad_tail), not a padded m-tile
+    mt, ki, ke = (nout - ntail + 7) // 8, (ni + 3) // 4, (ned + 3) // 4
     return ni, ned, nf, nout, mt, ki, ke, 2 * ki + 3 * ke, 4 * ki + 12 * ke
 
 
@@ -46,6 +47,7 @@ def test_grad_mma_tile_replay_matches_dense_gradient(n):
     c = Euler(ip, structured_tri_mesh(2, 2, tag="far"))
     p = c.problem
     ni, ned, nf, nout, mt_n, ki, ke, ks_n, urows = _dims(n)
+    ntail = nout - 8 * mt_n if nout % 8 in (1, 2) else 0
     assert (ni, ned, nf) == (p.NpInt, p.NpEdge, p.NpFlux)
     table = lib.grad_mma_table(p)
     nfrag = mt_n * ks_n * 32
@@ -99,7 +101,7 @@ def test_grad_mma_tile_replay_matches_dense_gradient(n):
                     gy[:, cc] += met[r, 1, e0 + cc] * s[:, cc]
             for l in range(32):
                 m = 8 * mt + fr[l]
-                if m >= nout:
+                if m >= nout - ntail:
                     continue
                 row = m if m < ni else m + ni
                 b3 = table[nfrag + 3 * m:nfrag + 3 * m + 3]
@@ -108,6 +110,25 @@ def test_grad_mma_tile_replay_matches_dense_gradient(n):
                     epsv = b3[0] * ev[0, e] + b3[1] * ev[1, e] + b3[2] * ev[2, e]
                     got_x[row, e] = gx[l, cc] * epsv
                     got_y[row, e] = gy[l, cc] * epsv
+    # the ragged rows: grad_tail's block-wise DFMA sums over the same shared-memory image (part 0: blocks 0, 2, 3;
+    # part 1: blocks 1, 4; one shuffle adds the halves), Div / Bary taken from the dense operators
+    blk_cols = [ni, ni, ned, ned, ned]
+    blk_col0 = [0, ni, 2 * ni, 2 * ni + ned, 2 * ni + 2 * ned]
+    for t in range(ntail):
+        m = 8 * mt_n + t
+        row = m + ni
+        for e in range(E):
+            parts = []
+            for blocks in ((0, 2, 3), (1, 4)):
+                gxp = gyp = 0.0
+                for r in blocks:
+                    sr = sum(div[row, blk_col0[r] + j] * s_u[blk_u0[r] + j, e] for j in range(blk_cols[r]))
+                    gxp += met[r, 0, e] * sr
+                    gyp += met[r, 1, e] * sr
+                parts.append((gxp, gyp))
+            epsv = bary[row] @ ev[:, e]
+            got_x[row, e] = (parts[0][0] + parts[1][0]) * epsv
+            got_y[row, e] = (parts[0][1] + parts[1][1]) * epsv
     rows = list(range(ni)) + list(range(2 * ni, nf))
     scale = np.abs(want_x[rows]).max()
     assert np.abs(got_x[rows] - want_x[rows]).max() < 1e-12 * scale
