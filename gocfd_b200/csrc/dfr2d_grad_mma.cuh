@@ -27,10 +27,11 @@ template <int N> struct GradMmaDim {
     static constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
     static constexpr int NOUT = NI + NF3;                                // produced rows
     // (r2) the produced rows fill NOUT / 8 m-tiles plus NOUT mod 8 ragged rows (N=4: 33 = 4 x 8 + 1; N=3: 25 = 3 x 8 + 1;
-    // N=2: 18 = 2 x 8 + 2).  One or two ragged rows are evaluated by plain DFMA (grad_tail) instead of a DMMA m-tile that
-    // is 7/8 zeros: 20-33 % fewer DMMA and A-fragment loads in a kernel that is bound by DMMA issue (ncu: mio_throttle on
-    // the DMMA, shared FP64 pipe 52 % busy, profiles/r02i_*).
-    static constexpr int NTAIL = (NOUT % 8 >= 1 && NOUT % 8 <= 2) ? NOUT % 8 : 0;
+    // N=2: 18 = 2 x 8 + 2).  A single ragged row is evaluated by plain DFMA (grad_tail) instead of a DMMA m-tile that is
+    // 7/8 zeros: 20-25 % fewer DMMA and A-fragment loads.
+    // measured (2M triangles, profiles/r02m_ab_N*.json): N=4 2.44 -> 2.34 ms, N=3 1.84 -> 1.65 ms; with TWO ragged rows
+    // (N=2) the DFMA pass costs more than the m-tile it replaces (1.12 -> 1.15 ms), so only a single ragged row is cut.
+    static constexpr int NTAIL = (NOUT % 8 == 1) ? 1 : 0;
     static constexpr int MT = (NOUT - NTAIL + 7) / 8;                   // m-tiles on the tensor cores
     static constexpr int KI = (NI + 3) / 4, KE = (NEd + 3) / 4;         // k-steps of an interior / an edge block
     static constexpr int KS = 2 * KI + 3 * KE;                          // k-steps of all five blocks

@@ -22,7 +22,7 @@ def _dims(n):
     ni, ned = (n + 1) * (n + 2) // 2, n + 2
     nf = (n + 2) * (n + 4)
     nout = ni + 3 * ned
-    ntail = nout % 8 if 1 <= nout % 8 <= 2 else 0        # ragged rows: plain DFMA (grad_tail), not a padded m-tile
+    ntail = 1 if nout % 8 == 1 else 0                    # a single ragged row: plain DFMA (grad_tail), not a padded m-tile
     mt, ki, ke = (nout - ntail + 7) // 8, (ni + 3) // 4, (ned + 3) // 4
     return ni, ned, nf, nout, mt, ki, ke, 2 * ki + 3 * ke, 4 * ki + 12 * ke
 
@@ -47,7 +47,7 @@ def test_grad_mma_tile_replay_matches_dense_gradient(n):
     c = Euler(ip, structured_tri_mesh(2, 2, tag="far"))
     p = c.problem
     ni, ned, nf, nout, mt_n, ki, ke, ks_n, urows = _dims(n)
-    ntail = nout - 8 * mt_n if nout % 8 in (1, 2) else 0
+    ntail = 1 if nout % 8 == 1 else 0
     assert (ni, ned, nf) == (p.NpInt, p.NpEdge, p.NpFlux)
     table = lib.grad_mma_table(p)
     nfrag = mt_n * ks_n * 32
