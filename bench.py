@@ -433,8 +433,11 @@ class Runner:
         if self.world > 1:
             dev.peer_enable(driver == "peer")
         evs = []
-        names = ["k_sensor", "k_diss_prepare", "k_edge(interior)", "halo + boundary/cut edges + RT gradient", "k_visc_edge",
-                 "wave", "element kernel"]
+        # (PerssonC0 path: the interior edges run inside stage_edges, after the RT gradient, with the viscous flux fused in;
+        # stage_visc is the boundary / cut-edge list of the same fused kernel)
+        names = ["k_sensor", "k_diss_prepare", "k_edge(interior)",
+                 "stage_edges: halo + boundary/cut edges | PerssonC0: RT gradient + interior edges incl. viscous flux",
+                 "stage_visc: PerssonC0 boundary/cut edges incl. viscous flux", "wave", "element kernel"]
         for _ in range(2):
             for rk in range(5):
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
@@ -482,7 +485,7 @@ class Runner:
         if self.diss:
             bv = algorithmic_bytes_visc(n)
             ach = bv * self.k_global * 5 * steps / (ms * 1e-3) / 1e9
-            return {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_edge, k_grad_pipe [DMMA], k_visc_edge, element kernel)",
+            return {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_grad_pipe [DMMA], k_edge_int/k_edge with the viscous flux fused in, k_elem_ws<N,8,true>)",
                     "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
                     "peak_source": peak_src, "bytes_per_element_stage": bv, "phase_ms": phases, "per_gpu": True}
         te = phases["element kernel"] * 1e-3

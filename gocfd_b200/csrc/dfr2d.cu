@@ -87,6 +87,7 @@ struct dfr2d_handle {
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int wsStages = 0;                // DFR2D_WS_STAGES override of the ring depth of kernel 5
+    int edgeViscFused = 1;            // PerssonC0: viscous edge flux inside the edge kernels (DFR2D_EDGE_VISC_FUSED=0: k_visc_edge)
     bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
@@ -664,6 +665,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (const char *ev = getenv("DFR2D_WS_STAGES")) h->wsStages = atoi(ev);
     if (const char *ev = getenv("DFR2D_WS_CW")) h->wsCW = atoi(ev) == 12 ? 12 : 8;
     if (const char *ev = getenv("DFR2D_DISS_PREFETCH")) h->dissPrefetch = atoi(ev) > 0 ? 1 : 0;
+    if (const char *ev = getenv("DFR2D_EDGE_VISC_FUSED")) h->edgeViscFused = atoi(ev) != 0 ? 1 : 0;
     {
         std::vector<double> fr;
         switch (N) {
@@ -916,12 +918,15 @@ static int run_unpack_vertex(dfr2d_handle *h) {
 // part: 1 = interior edges (no ghost column involved: may run while the halo is in flight), 2 = boundary + cut edges
 // (after the halo has been unpacked), 3 = both
 static int run_edges(dfr2d_handle *h, int rk, int part) {
+    // PerssonC0 path with the fused viscous edge flux: the VISC instantiations, run AFTER the gradient kernel
+    const bool visc = h->ph.dissipation && h->edgeViscFused;
     EdgeArgs a{};
     a.ne = h->NE; a.NEp = h->NEp; a.Kp = h->Kp; a.Kown = h->K;
     a.kL = h->ekL; a.kR = h->ekR; a.meta = h->emeta;
     a.nx = h->enx; a.ny = h->eny; a.oohk = h->eoohk;
     a.bpx = h->bpx; a.bpy = h->bpy;
     a.qface = h->qface; a.eflux = h->eflux; a.agg = h->agg;
+    a.vn = h->ds.vn; a.etov = h->ds.etov; a.epsV = h->ds.epsV; a.ooLen = h->ds.eooLen; a.aggv = h->ds.aggv;
     a.sc = h->sc;
     a.slot = (int)(h->stageCounter & 1);
     a.par = (int)(h->stepIndex & 1);
@@ -942,7 +947,10 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
     int pptList = (h->nBnd < 64 * h->sms * 256 && h->edgePPT <= 0) ? 1 : ppt;
     if ((h->N + 2) % pptList != 0) pptList = h->N + 2;
     if ((ppt != h->N + 2 || (h->edgeSplit && pptList != h->N + 2)) && h->ph.localDT && (part & 1))
+    {
         CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
+        if (visc) CK(cudaMemsetAsync(h->ds.aggv, 0, (size_t)h->NEp * sizeof(double), h->stream));
+    }
     a.list = nullptr; a.nlist = 0;
 #define EDGE_LAUNCH(KERN)                                                                      \
     DISPATCH_N(h->N, {                                                                          \
@@ -956,10 +964,10 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
         const int ib = std::max(1, std::min(h->edgeBlocks * 2, (int)(((long long)h->NEp * ((h->N + 2) / ppt) + 255) / 256)));
         if (part & 1) {
         switch (h->ph.fluxType) {
-#define KI_AVG(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_Average, P_><<<ib, 256, 0, h->stream>>>(a)
-#define KI_LAX(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_><<<ib, 256, 0, h->stream>>>(a)
-#define KI_ROE(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_Roe, P_><<<ib, 256, 0, h->stream>>>(a)
-#define KI_RER(NN_, P_) k_edge_int<NN_, DFR2D_FLUX_RoeER, P_><<<ib, 256, 0, h->stream>>>(a)
+#define KI_AVG(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_Average, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_Average, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
+#define KI_LAX(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
+#define KI_ROE(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_Roe, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_Roe, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
+#define KI_RER(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_RoeER, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_RoeER, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
             case DFR2D_FLUX_Average: EDGE_LAUNCH(KI_AVG); break;
             case DFR2D_FLUX_LaxFriedrichs: EDGE_LAUNCH(KI_LAX); break;
             case DFR2D_FLUX_Roe: EDGE_LAUNCH(KI_ROE); break;
@@ -972,13 +980,13 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
         {
             const int ppt = pptList;       // (EDGE_LAUNCH dispatches on `ppt`)
             const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
-#define KB(NN_, P_) k_edge<NN_, P_><<<bb, 256, 0, h->stream>>>(a)
+#define KB(NN_, P_) do { if (visc) k_edge<NN_, P_, true><<<bb, 256, 0, h->stream>>>(a); else k_edge<NN_, P_, false><<<bb, 256, 0, h->stream>>>(a); } while (0)
             EDGE_LAUNCH(KB);
         }
         return launch_check(h, "k_edge(boundary)");
     }
     if (!(part & 2)) return 0;          // single generic kernel: everything happens in the second part
-#define KG(NN_, P_) k_edge<NN_, P_><<<blocks, 256, 0, h->stream>>>(a)
+#define KG(NN_, P_) do { if (visc) k_edge<NN_, P_, true><<<blocks, 256, 0, h->stream>>>(a); else k_edge<NN_, P_, false><<<blocks, 256, 0, h->stream>>>(a); } while (0)
     a.Kown = 0x7fffffff;
     EDGE_LAUNCH(KG);
     (void)rk;
@@ -1272,6 +1280,7 @@ static int stage_edges_interior(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     if (h->interiorDone || !h->edgeSplit) return 0;
+    if (h->ph.dissipation && h->edgeViscFused) return 0;      // fused viscous edges run after the gradient (stage_edges)
     if (int rc = run_edges(h, rk, 1)) return rc;
     h->interiorDone = true;
     return 0;
@@ -1281,6 +1290,13 @@ static int stage_edges(dfr2d_handle *h, int rk) {
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     if (int rc = run_unpack(h)) return rc;
+    if (h->ph.dissipation && h->edgeViscFused) {
+        // gradient first (it needs Q_Face only), its cut-edge values go out, and the interior edges -- numerical flux
+        // minus viscous flux in one kernel -- overlap that exchange; the boundary / cut-edge list follows in stage_visc
+        if (int rc = run_diss_grad(h, rk)) return rc;
+        if (int rc = run_pack_diss(h)) return rc;
+        return run_edges(h, rk, h->edgeSplit ? 1 : 0);
+    }
     if (int rc = run_edges(h, rk, h->interiorDone ? 2 : 3)) return rc;
     h->interiorDone = false;
     if (h->ph.dissipation) {
@@ -1291,11 +1307,11 @@ static int stage_edges(dfr2d_handle *h, int rk) {
 }
 
 static int stage_visc(dfr2d_handle *h, int rk) {
-    (void)rk;
     if (!h->ph.dissipation) return 0;
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     if (int rc = run_unpack_diss(h)) return rc;
+    if (h->edgeViscFused) return run_edges(h, rk, h->edgeSplit ? 2 : 3);
     return run_diss_visc(h);
 }
 

@@ -25,6 +25,13 @@ struct EdgeArgs {
     const double *qface;                // [4][3NpEdge][Kp]
     double *eflux;                      // [4][NpEdge][NEp]
     double *agg;                        // [NEp] edge max wave speed
+    // VISC instantiations (PerssonC0 path, run after the gradient kernel): StoreEdgeViscousFlux (edges.go:151-244) is
+    // evaluated on the spot and F - F_visc is what gets stored -- no separate viscous edge kernel, no read-modify-write
+    const double *vn;                   // [2][4][NpEdge][NEp] owner-normal component of Epsilon (.) Grad (GradArgs::vn)
+    const int *etov;                    // [3][Kp]
+    const double *epsV;                 // vertex epsilon (ghost columns: private slots)
+    const double *ooLen;                // [NEp] 1 / edge length
+    double *aggv;                       // [NEp] viscous aggregate
     DevScalars *sc;
     int slot, par;
     long long stepIndex;
@@ -71,7 +78,56 @@ __device__ __forceinline__ bool step_is_noop(const DevScalars *sc, const Phys &p
 // the points of an edge are split over NpEdge/PPT threads in different warps -- fewer registers, more warps in flight
 // for this latency-bound gather kernel; the per-edge aggregate (only consumed with local time stepping) is then
 // combined with atomicMax on the bit pattern (agg is zeroed by the host beforehand).
-template <int N, int PPT>
+// Viscous state of one edge for the VISC edge kernels: vertex epsilons of both elements (InterpolateEpsilonSigma,
+// dissipation.go:219-242, re-derived with Bary at the edge rows), penalty coefficient, viscous aggregate.
+template <int N>
+struct EdgeVisc {
+    double eL0, eL1, eL2, eR0, eR1, eR2, ooLen, oohk2, vmax;
+    int numL, numR;
+    bool shared;
+    __device__ __forceinline__ void load(const EdgeArgs &a, int e, int kL, int kR, int nL, int nR, double oohk) {
+        const size_t Kp = a.Kp;
+        shared = kR >= 0;
+        numL = nL; numR = nR;
+        eL0 = a.epsV[a.etov[kL]]; eL1 = a.epsV[a.etov[Kp + kL]]; eL2 = a.epsV[a.etov[2 * Kp + kL]];
+        eR0 = eR1 = eR2 = 0.0;
+        if (shared) { eR0 = a.epsV[a.etov[kR]]; eR1 = a.epsV[a.etov[Kp + kR]]; eR2 = a.epsV[a.etov[2 * Kp + kR]]; }
+        ooLen = a.ooLen[e];
+        oohk2 = oohk * oohk;
+        vmax = -1.7976931348623157e308;
+    }
+    // F[n] -= viscous normal flux at owner point i; QLpre = the owner's stored edge values (EdgeQValues, pre-BC)
+    __device__ __forceinline__ void apply(const EdgeArgs &a, int e, int i, int kL, const double (&QLpre)[4], double (&F)[4]) {
+        constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge;
+        const Ops<N> &op = ops<N>();
+        const int rowL = 2 * NI + numL * NEd + i;
+        const double epsL = op.Bary[rowL][0] * eL0 + op.Bary[rowL][1] * eL1 + op.Bary[rowL][2] * eL2;
+        vmax = fmax(oohk2 * epsL, vmax);
+        const size_t fplane = (size_t)NEd * a.NEp, qplane = (size_t)Dim<N>::NF3 * a.Kp;
+        double lam = 0.0;
+        if (shared) {
+            const int rowR = 2 * NI + numR * NEd + (NEd - 1 - i);
+            const double epsR = op.Bary[rowR][0] * eR0 + op.Bary[rowR][1] * eR1 + op.Bary[rowR][2] * eR2;
+            lam = 0.5 * (epsL + epsR);
+        }
+#pragma unroll
+        for (int n = 0; n < 4; n++) {
+            const size_t idx = ((size_t)n * NEd + i) * a.NEp + e;
+            const double vFL = a.vn[idx];
+            double vf = vFL;
+            if (shared) {
+                const double vFR = a.vn[idx + 4 * fplane];
+                vf = 0.5 * (vFL + vFR);
+                // both "sides" of the jump resolve to the owner's stored edge values (edges.go:225-236)
+                const double qb = a.qface[n * qplane + (size_t)(numL * NEd + (NEd - 1 - i)) * a.Kp + kL];
+                vf -= (a.ph.Omega * lam * ooLen) * (QLpre[n] - qb);
+            }
+            F[n] -= vf;
+        }
+    }
+};
+
+template <int N, int PPT, bool VISC>
 __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) {
     constexpr int NE_ = Dim<N>::NpEdge;
     constexpr int G = NE_ / PPT;
@@ -80,7 +136,7 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
     const double gamma = a.ph.gamma;
     const size_t qplane = (size_t)Dim<N>::NF3 * a.Kp;
     const size_t fplane = (size_t)NE_ * a.NEp;
-    double blockmax = 0.0;
+    double blockmax = 0.0, blockmaxV = 0.0;
     const int span = a.list ? a.nlist : a.NEp;
     const long long total = (long long)G * span;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -91,15 +147,17 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
         const int numL = meta & 3, numR = (meta >> 2) & 3, bc = (meta >> 4) & 15;
         const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
         double wmax = -1.7976931348623157e308;
+        EdgeVisc<N> ev;
+        if (VISC) ev.load(a, e, kL, kR >= 0 ? kR : -1, numL, numR, oohk);
 #pragma unroll
         for (int ii = 0; ii < PPT; ii++) {
             const int i = g * PPT + ii;
-            double QL[4], F[4];
+            double QL[4], F[4], QLpre[4];
             double wL = 0.0;
             bool haveW = false;
             const size_t offL = (size_t)(numL * NE_ + i) * a.Kp + kL;
 #pragma unroll
-            for (int n = 0; n < 4; n++) QL[n] = a.qface[n * qplane + offL];
+            for (int n = 0; n < 4; n++) { QL[n] = a.qface[n * qplane + offL]; QLpre[n] = QL[n]; }
             if (kR >= 0) {
                 double QR[4];
                 const size_t offR = (size_t)(numR * NE_ + (NE_ - 1 - i)) * a.Kp + kR;
@@ -142,6 +200,7 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
                     for (int n = 0; n < 4; n++) F[n] = nx * Fx[n] + ny * Fy[n];
                 }
             }
+            if (VISC) ev.apply(a, e, i, kL, QLpre, F);
 #pragma unroll
             for (int n = 0; n < 4; n++) a.eflux[n * fplane + (size_t)i * a.NEp + e] = F[n];
             // StoreEdgeAggregates: owner side, post-BC state (edges.go:260-273)
@@ -152,30 +211,41 @@ __global__ void __launch_bounds__(256, DFR2D_EDGE_MINBLOCKS) k_edge(EdgeArgs a) 
         if (G == 1) a.agg[e] = wmax;
         else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.agg[e]), wmax);
         blockmax = fmax(blockmax, wmax);
+        if (VISC) {
+            if (G == 1) a.aggv[e] = ev.vmax;
+            else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.aggv[e]), fmax(ev.vmax, 0.0));
+            blockmaxV = fmax(blockmaxV, ev.vmax);
+        }
     }
-    __shared__ double smax[8];
+    __shared__ double smax[8], smaxV[8];
     blockmax = warp_max(blockmax);
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    if (VISC) blockmaxV = warp_max(blockmaxV);
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = blockmax; if (VISC) smaxV[threadIdx.x >> 5] = blockmaxV; }
     __syncthreads();
     if (threadIdx.x < 32) {
         double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
         v = warp_max(v);
         if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][0], v);
+        if (VISC) {
+            double vv = threadIdx.x < (blockDim.x >> 5) ? smaxV[threadIdx.x] : 0.0;
+            vv = warp_max(vv);
+            if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][1], vv);
+        }
     }
 }
 
 // Interior (shared) edges only, flux type fixed at compile time: none of the boundary-condition code (pow/exp, three
 // free-stream records) is in this kernel, which halves its register count and doubles the warps in flight.
 // Boundary edges are skipped here and handled by k_edge<N,PPT> over the compact boundary list.
-template <int N, int FLUX, int PPT>
-__global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeArgs a) {
+template <int N, int FLUX, int PPT, bool VISC>
+__global__ void __launch_bounds__(256, VISC ? 2 : DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeArgs a) {
     constexpr int NE_ = Dim<N>::NpEdge;
     constexpr int G = NE_ / PPT;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
     const double gamma = a.ph.gamma;
     const size_t qplane = (size_t)Dim<N>::NF3 * a.Kp;
     const size_t fplane = (size_t)NE_ * a.NEp;
-    double blockmax = 0.0;
+    double blockmax = 0.0, blockmaxV = 0.0;
     const long long total = (long long)G * a.NEp;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const int e = (int)(t % a.NEp), g = (int)(t / a.NEp);
@@ -187,6 +257,8 @@ __global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeA
         const int numL = meta & 3, numR = (meta >> 2) & 3;
         const double nx = a.nx[e], ny = a.ny[e], oohk = a.oohk[e];
         double wmax = -1.7976931348623157e308;
+        EdgeVisc<N> ev;
+        if (VISC) ev.load(a, e, kL, kR, numL, numR, oohk);
 #pragma unroll
         for (int ii = 0; ii < PPT; ii++) {
             const int i = g * PPT + ii;
@@ -202,6 +274,7 @@ __global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeA
                 else roe_er_flux(gamma, QL, QR, nx, ny, F);
                 wL = speed_plus_sound(gamma, QL[0], QL[1], QL[2], QL[3]);
             }
+            if (VISC) ev.apply(a, e, i, kL, QL, F);
 #pragma unroll
             for (int n = 0; n < 4; n++) a.eflux[n * fplane + (size_t)i * a.NEp + e] = F[n];
             const double w = oohk * wL;
@@ -210,15 +283,26 @@ __global__ void __launch_bounds__(256, DFR2D_EDGEINT_MINBLOCKS) k_edge_int(EdgeA
         if (G == 1) a.agg[e] = wmax;
         else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.agg[e]), wmax);
         blockmax = fmax(blockmax, wmax);
+        if (VISC) {
+            if (G == 1) a.aggv[e] = ev.vmax;
+            else if (a.ph.localDT) atomic_max_nonneg(reinterpret_cast<unsigned long long *>(&a.aggv[e]), fmax(ev.vmax, 0.0));
+            blockmaxV = fmax(blockmaxV, ev.vmax);
+        }
     }
-    __shared__ double smax[8];
+    __shared__ double smax[8], smaxV[8];
     blockmax = warp_max(blockmax);
-    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = blockmax;
+    if (VISC) blockmaxV = warp_max(blockmaxV);
+    if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = blockmax; if (VISC) smaxV[threadIdx.x >> 5] = blockmaxV; }
     __syncthreads();
     if (threadIdx.x < 32) {
         double v = threadIdx.x < (blockDim.x >> 5) ? smax[threadIdx.x] : 0.0;
         v = warp_max(v);
         if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][0], v);
+        if (VISC) {
+            double vv = threadIdx.x < (blockDim.x >> 5) ? smaxV[threadIdx.x] : 0.0;
+            vv = warp_max(vv);
+            if (threadIdx.x == 0) atomic_max_nonneg(&a.sc->wave[a.slot][1], vv);
+        }
     }
 }
 
