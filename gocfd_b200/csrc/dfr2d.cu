@@ -11,6 +11,8 @@
 #include <vector>
 #include <unistd.h>
 
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "dfr2d_kernels.cuh"
 #include "dfr2d_diss_kernels.cuh"
 #include "dfr2d_elem_mma.cuh"
@@ -87,6 +89,7 @@ struct dfr2d_handle {
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int wsStages = 0;                // DFR2D_WS_STAGES override of the ring depth of kernel 5
+    void *tmaps = nullptr;            // DFR2D_WS_TMA=1: four CUtensorMap (q0, q2, q3, R) for the TMA variant of kernel 5
     int edgeViscFused = 1;            // PerssonC0: viscous edge flux inside the edge kernels (DFR2D_EDGE_VISC_FUSED=0: k_visc_edge)
     bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
@@ -475,6 +478,35 @@ static int build_plan(const dfr2d_problem *p, dfr2d_plan &pl) {
     return 0;
 }
 
+// Tensor maps of the RK registers for the TMA variant of kernel 5 (ElemWsArgs::tmaps): rank 2, inner dimension = element
+// columns, outer = the 4 NpInt rows of a register, box = one [4 NpInt x 32] slab, no swizzle (dense 256-byte rows).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_tmaps(dfr2d_handle *h) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled is not available in this driver"; return 2; }
+    alignas(64) CUtensorMap maps[4];
+    double *base[4] = {h->q[0], h->q[2], h->q[3], h->R};
+    const cuuint64_t dims[2] = {(cuuint64_t)h->Kp, (cuuint64_t)(4 * h->NpInt)};
+    const cuuint64_t strides[1] = {(cuuint64_t)h->Kp * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)kElemsPerBlock, (cuuint32_t)(4 * h->NpInt)};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < 4; i++) {
+        CUresult r = ((EncodeTiledFn)fn)(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base[i], dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return 2; }
+    }
+    unsigned char *d = nullptr;
+    if (int rc = dev_alloc(h, &d, sizeof(maps))) return rc;
+    CK(cudaMemcpy(d, maps, sizeof(maps), cudaMemcpyHostToDevice));
+    h->tmaps = d;
+    return 0;
+}
+
 static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     const int N = p->N;
     h->NpInt = (N + 1) * (N + 2) / 2;
@@ -718,6 +750,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         }
         if (int rc = dev_upload(h, &h->gradMxy, mxy)) return rc;
     }
+    if (const char *ev = getenv("DFR2D_WS_TMA"))
+        if (atoi(ev) > 0 && !ph.dissipation && h->elemKernel == 5)
+            if (int rc = make_tmaps(h)) return rc;
     CK(cudaDeviceSynchronize());
     return 0;
 }
@@ -1073,6 +1108,7 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
             ta.a = a;
             ta.nTiles = blocks;
             ta.nExtra = (rk == 0 || rhsOut != nullptr) ? 0 : (rk == 4 ? 4 : 1);
+            ta.tmaps = h->tmaps;
             DISPATCH_N(h->N, {
                 using TD = WsDim<NN>;
                 const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words

@@ -111,7 +111,23 @@ __device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long *bar) {
 struct ElemWsArgs {
     ElemArgs a;
     int nTiles, nStages, nExtra;
+    // (r2) measured variant DFR2D_WS_TMA=1: the extra RK-register slabs (q0, q2, q3, R) are fetched by the TMA engine --
+    // one cp.async.bulk.tensor.2d per [4 NpInt rows x 32 columns] slab, issued by one lane (UTMALDG in SASS), completing
+    // by byte count on the stage's mbarrier -- instead of 4 NpInt / 2 coalesced LDGSTS warp instructions.  tmaps = four
+    // CUtensorMap objects (q0, q2, q3, R) in global memory, nullptr = off.  TMA lands dense 256-byte rows, so these slabs
+    // then have a row stride of 32 doubles; only the epilogue reads them (LDS.128 in accumulator layout), never the DMMA
+    // B-operand path whose 4 k-rows x 8 columns pattern needs the stride of 36.
+    const void *tmaps;
 };
+
+// 2D tile {c0 = column, c1 = row} of a tensor map -> shared memory, completion by bytes on the mbarrier
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void *tmap, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 
 // CW = consumer warps (8: two groups of four, 224 registers each; 12: three groups, 152 registers each)
 // DISS = the element kernel of the PerssonC0 path (AddDissipation, dissipation.go:274-346, and LimitFilterSolution on
@@ -139,6 +155,8 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     __shared__ __align__(8) unsigned long long fullBar[kWsMaxStages], emptyBar[kWsMaxStages];
     const int S = args.nStages, nExtra = args.nExtra;
     const int nExtraS = TD::extras_in_smem(nExtra, DISS);           // extra RK registers staged in the ring
+    const bool useTma = !DISS && args.tmaps != nullptr;
+    const int SEX = useTma ? E : SE;                                // row stride of the extra slabs
     constexpr int XO = DISS ? TD::xOffD : TD::xOff;                  // first extra slab
     const int dOff = XO + nExtraS * TD::xSize;                      // DISS: DissX slab, DissY behind it
     const int stageDoubles = DISS ? TD::stage_doubles_diss(nExtraS) : TD::xOff + nExtra * TD::xSize;
@@ -217,7 +235,17 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 const unsigned stU = smem_u32(st);
                 // stage input, the stage-3 residual (rk 4) and the metrics: coalesced 16-byte async copies
                 slab_g2s<4 * NI, SE>(stU + (unsigned)(TD::qOff * sizeof(double)), a.qs + k0, Kp, lane);
-                if (!DISS && nExtra == 4) slab_g2s<4 * NI, SE>(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)), a.R + k0, Kp, lane);
+                if (!DISS && nExtra == 4) {
+                    if (useTma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&fullBar[s], (unsigned)(4 * NI * E * sizeof(double)));
+                            tma_load_2d(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)),
+                                        (const char *)args.tmaps + 3 * 128, (int)k0, 0, smem_u32(&fullBar[s]));
+                        }
+                    } else {
+                        slab_g2s<4 * NI, SE>(stU + (unsigned)((TD::xOff + 3 * TD::xSize) * sizeof(double)), a.R + k0, Kp, lane);
+                    }
+                }
                 if (lane < 16) cp_async16_u32(stU + (unsigned)((TD::gOff + 2 * lane) * sizeof(double)), a.Jdet + k0 + 2 * lane);
                 slab_g2s<4, 32>(stU + (unsigned)((TD::gOff + 32) * sizeof(double)), a.Jinv + k0, Kp, lane);
                 double dtk = dtGlobal;
@@ -269,8 +297,16 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 if (le < (DISS ? nExtraS : (nExtra == 4 ? 3 : nExtra))) {
                     // RK register slab number `le` of this stage (q0, q2, q3); R travels with the stage input in warp 0
                     const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
-                    slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((XO + le * TD::xSize) * sizeof(double)),
-                                         (le == 0 ? a.q0 : (le == 1 ? a.q2 : a.q3)) + k0, Kp, lane);
+                    if (useTma) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&fullBar[s], (unsigned)(4 * NI * E * sizeof(double)));
+                            tma_load_2d(smem_u32(st) + (unsigned)((XO + le * TD::xSize) * sizeof(double)),
+                                        (const char *)args.tmaps + le * 128, (int)k0, 0, smem_u32(&fullBar[s]));
+                        }
+                    } else {
+                        slab_g2s<4 * NI, SE>(smem_u32(st) + (unsigned)((XO + le * TD::xSize) * sizeof(double)),
+                                             (le == 0 ? a.q0 : (le == 1 ? a.q2 : a.q3)) + k0, Kp, lane);
+                    }
                 }
                 if (DISS && le >= 1) {
                     // interior rows of DissX (gather warp 1) and DissY (gather warp 2)
@@ -536,13 +572,14 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                             continue;
                         }
                         const int so = (v * NI + i) * SE + eC;
+                        const int sx = (v * NI + i) * SEX + eC;          // extra slabs: stride 32 when the TMA engine wrote them
                         const double2 qs = *reinterpret_cast<const double2 *>(&sQ[so]);
                         double2 qn;
                         if (a.rk == 0) {
                             qn.x = qs.x + RK0_A * (dt.x * rhs0);
                             qn.y = qs.y + RK0_A * (dt.y * rhs1);
                         } else if (a.rk < 4) {
-                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[so]);
+                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[sx]);
                             const double ca = (a.rk == 1) ? RK1_A : (a.rk == 2) ? RK2_A : RK3_A;
                             const double cb = (a.rk == 1) ? RK1_B : (a.rk == 2) ? RK2_B : RK3_B;
                             const double cc = (a.rk == 1) ? RK1_C : (a.rk == 2) ? RK2_C : RK3_C;
@@ -550,13 +587,13 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                             qn.y = ca * q0v.y + cb * qs.y + cc * (dt.y * rhs1);
                             if (a.rk == 3) *reinterpret_cast<double2 *>(a.R + o) = make_double2(rhs0, rhs1);
                         } else {
-                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[so]);
-                            const double2 q2v = *reinterpret_cast<const double2 *>(&sX[so + 1 * TD::xSize]);
+                            const double2 q0v = *reinterpret_cast<const double2 *>(&sX[sx]);
+                            const double2 q2v = *reinterpret_cast<const double2 *>(&sX[sx + 1 * TD::xSize]);
                             // (DISS: q3 and the stage-3 residual are not staged at rk 4 -- no room for two ring stages)
                             const double2 q3v = DISS ? *reinterpret_cast<const double2 *>(a.q3 + o)
-                                                     : *reinterpret_cast<const double2 *>(&sX[so + 2 * TD::xSize]);
+                                                     : *reinterpret_cast<const double2 *>(&sX[sx + 2 * TD::xSize]);
                             const double2 rv = DISS ? *reinterpret_cast<const double2 *>(a.R + o)
-                                                    : *reinterpret_cast<const double2 *>(&sX[so + 3 * TD::xSize]);
+                                                    : *reinterpret_cast<const double2 *>(&sX[sx + 3 * TD::xSize]);
                             double2 r;
                             r.x = -q0v.x + RK4_A * q2v.x + RK4_B * q3v.x + RK4_C * qs.x + RK4_D * (dt.x * rv.x) + RK4_E * (dt.x * rhs0);
                             r.y = -q0v.y + RK4_A * q2v.y + RK4_B * q3v.y + RK4_C * qs.y + RK4_D * (dt.y * rv.y) + RK4_E * (dt.y * rhs1);
