@@ -485,7 +485,7 @@ class Runner:
         if self.diss:
             bv = algorithmic_bytes_visc(n)
             ach = bv * self.k_global * 5 * steps / (ms * 1e-3) / 1e9
-            return {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_grad_pipe [DMMA], k_edge_int/k_edge with the viscous flux fused in, k_elem_ws<N,8,true>)",
+            return {"bound": "hbm", "kernel": "whole PerssonC0 stage (k_sensor, k_diss_prepare, k_grad_ws [DMMA], k_edge_int/k_edge with the viscous flux fused in, k_elem_ws<N,8,true>)",
                     "achieved": ach / world, "peak": peak, "unit": "GB/s", "frac": ach / peak / world, "traffic": None,
                     "peak_source": peak_src, "bytes_per_element_stage": bv, "phase_ms": phases, "per_gpu": True}
         te = phases["element kernel"] * 1e-3

@@ -76,7 +76,7 @@ struct dfr2d_handle {
     int pfTiles = 0;
     int elemKernel = 4;               // 1: row-per-thread DFMA, 2: split-row DFMA, 3: DMMA, 4: pipelined DMMA (default)
     double *mmaFrags = nullptr;
-    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 3: pipelined persistent DMMA k_grad_pipe
+    int gradKernel = 1;               // 1: constant-operand DFMA k_grad, 3: pipelined persistent DMMA k_grad_pipe, 4: k_grad_ws
                                       // (DFR2D_GRAD_KERNEL; 2 was round 1's one-tile-per-CTA DMMA kernel, retired)
     double *gradTable = nullptr, *gradMxy = nullptr;
     int gradMG = 3;                   // m-tiles per accumulation group of k_grad_pipe (DFR2D_GRAD_MG = 2 | 3)
@@ -85,7 +85,7 @@ struct dfr2d_handle {
     double *mmaDissFrags = nullptr;
     int mmaDissGrid = 0;
     int gradSkewNs = 0;               // start delay of k_grad_pipe's second warp group (DFR2D_GRAD_SKEW_NS)
-    bool gradAttrSet = false;
+    bool gradAttrSet = false, gradWsAttrSet = false;
     int sms = 148, mmaGrid = 148;
     int pipeOcc[3] = {0, 0, 0};
     int wsStages = 0;                // DFR2D_WS_STAGES override of the ring depth of kernel 5
@@ -714,8 +714,11 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // N = 4 (k_edge + gradient 3.86 -> 2.74 ms), N = 3 (2.32 -> 2.15) and N = 2 (1.56 -> 1.43).  N = 1 keeps the DFMA
     // kernel: its operators are 15 x 15, and its summation order is the one the 1e-11 parity bar at N = 1 relies on
     // (the RT2 divergence operator is ill conditioned, tests/test_noise_floor.py)
-    h->gradKernel = (N >= 2) ? 3 : 1;
-    if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev) >= 2 ? 3 : 1;
+    // (r2, profiles/r02t_ab_N*.json) the warp-specialised form of the same kernel (k_grad_ws: producer warps own the copies
+    // and the index chain) is bitwise identical and faster at every N >= 2: stage 5.15 -> 4.88 ms at N=4, 3.86 -> 3.75 at
+    // N=3, 2.72 -> 2.53 at N=2 (2M triangles); k_grad_pipe stays selectable as 3 (2 maps to it as well)
+    h->gradKernel = (N >= 2) ? 4 : 1;
+    if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev) >= 4 ? 4 : (atoi(ev) >= 2 ? 3 : 1);
     if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
     // measured (2M triangles, profiles/r02l_ab_N*.json): the warp-specialised ring with the PerssonC0 terms
@@ -1244,6 +1247,25 @@ static int run_diss_grad(dfr2d_handle *h, int rk) {
     ga.enx = h->enx; ga.eny = h->eny; ga.vn = d.vn; ga.NEp = h->NEp;
     ga.sc = h->sc; ga.par = (int)(h->stepIndex & 1); ga.stepIndex = h->stepIndex; ga.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (h->gradKernel == 4) {
+        DISPATCH_N(h->N, {
+            using PD = GradPipeDim<NN>;
+            using WD = GradWsDim<NN>;
+            if (!h->gradWsAttrSet) {
+                cudaFuncSetAttribute(k_grad_ws<NN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD::kSmemBytes);
+                cudaFuncSetAttribute(k_grad_ws<NN, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k_grad_ws<NN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PD::kSmemBytes);
+                cudaFuncSetAttribute(k_grad_ws<NN, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                h->gradWsAttrSet = true;
+            }
+            GradPipeArgs pa{};
+            pa.a = ga; pa.table = h->gradTable; pa.mxy = h->gradMxy; pa.nTiles = blocks; pa.skewNs = 0;
+            const int grid = std::max(1, std::min(h->sms, (blocks + PD::kGroups - 1) / PD::kGroups));
+            if (h->gradMG == 2) k_grad_ws<NN, 2><<<grid, WD::kThreads, PD::kSmemBytes, h->stream>>>(pa);
+            else k_grad_ws<NN, 3><<<grid, WD::kThreads, PD::kSmemBytes, h->stream>>>(pa);
+        });
+        return launch_check(h, "k_grad_ws");
+    }
     if (h->gradKernel == 3) {
         DISPATCH_N(h->N, {
             using PD = GradPipeDim<NN>;

@@ -421,4 +421,179 @@ __global__ void __launch_bounds__(GradPipeDim<N>::kThreads, 1) k_grad_pipe(GradP
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_grad_ws<N, MG> (DFR2D_GRAD_KERNEL=4): k_grad_pipe with the data movement taken out of the tensor-core warps, the way
+// k_elem_ws did it for the element kernel.  ncu on k_grad_pipe (profiles/r02i_*, r02z_*): the shared FP64/DMMA pipe is only
+// 45 % busy and the 16 warps issue 0.31 instructions per cycle and scheduler; every warp spends its tile on 1,850
+// instructions of which only 112 are DMMA -- the rest is the copy list of the next tile with its index chain, address
+// arithmetic, and two group-wide synchronisations (cp.async.wait_all + bar.sync) that keep the eight warps of a group in
+// lock step, so that they all want the pipe at once (math_pipe_throttle) and then all leave it idle.  Here
+//   * TWO producer warps per group issue every copy of the group's next tile -- one streams the dense rows, the other owns
+//     the index chain (etoe -> edge table -> Q_Face rows, vertex ids, slots) and the gathers; the copies complete on the
+//     stage's FULL mbarrier;
+//   * the eight consumer warps of a group (variable, 16-element half) only wait for FULL, run the unchanged DMMA / epilogue
+//     / ragged-row code, and arrive on EMPTY.  They never write shared memory and never synchronise with each other, so
+//     their DMMA bursts drift apart.
+// Same stage layout, table, accumulation groups and results (bitwise) as k_grad_pipe.
+template <int N> struct GradWsDim {
+    using PD = GradPipeDim<N>;
+    // two producer warps per group (register files are handed out per 4 warps: 18 warps would be allotted as 20 anyway):
+    // role 0 streams the dense rows (solution, metrics), role 1 owns the index chain and the 8-byte gathers
+    static constexpr int kConsWarps = 16, kProdWarps = 2 * PD::kGroups, kThreads = (kConsWarps + kProdWarps) * 32;
+    static constexpr int kFullCount = 128;         // per producer lane (2 warps): its cp.async completions + one plain arrive
+    // 640 threads are allotted 96 registers each; the producers keep 40 and hand the rest to the consumers
+    static constexpr int kProdRegs = 40, kConsRegs = 104;
+};
+
+template <int N, int MG>
+__global__ void __launch_bounds__(GradWsDim<N>::kThreads, 1) k_grad_ws(GradPipeArgs args) {
+    using GD = GradMmaDim<N>;
+    using PD = GradPipeDim<N>;
+    using WD = GradWsDim<N>;
+    constexpr int NI = GD::NI, NEd = GD::NEd, NF3 = GD::NF3, E = kElemsPerBlock, SE = GD::SE;
+    constexpr int MT = GD::MT, KI = GD::KI, KE = GD::KE, UROWS = GD::UROWS;
+    const GradArgs &a = args.a;
+    if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) return;
+    extern __shared__ double smem[];
+    __shared__ __align__(8) unsigned long long fullBar[PD::kGroups][2], emptyBar[PD::kGroups][2];
+    double *sT = smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool producer = warp >= WD::kConsWarps;
+    const int group = producer ? (warp - WD::kConsWarps) >> 1 : warp >> 3;
+    double *sStage = sT + GD::kTableDoubles + (size_t)group * 2 * PD::kStageDoubles;
+    const size_t Kp = a.Kp;
+    const int nTiles = args.nTiles;
+    const int stride = gridDim.x * PD::kGroups;
+    const int tile0 = blockIdx.x * PD::kGroups + group;
+
+    for (int t = threadIdx.x; t < GD::kTableDoubles; t += WD::kThreads) sT[t] = args.table[t];
+    // padding rows of every stage are zeroed once; the copies only ever write the real rows
+    for (int t = threadIdx.x; t < PD::kGroups * 2 * 4 * UROWS * E; t += WD::kThreads) {
+        const int col = t % E, r = (t / E) % UROWS, rest = t / (E * UROWS);          // rest = (group, stage, variable)
+        const bool pad = (r < 4 * KI) ? (r >= NI) : (((r - 4 * KI) % (4 * KE)) >= NEd);
+        if (pad) sT[GD::kTableDoubles + (size_t)(rest >> 2) * PD::kStageDoubles + ((rest & 3) * UROWS + r) * SE + col] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+        for (int g = 0; g < PD::kGroups; g++)
+            for (int st = 0; st < 2; st++) {
+                mbar_init(&fullBar[g][st], WD::kFullCount);
+                mbar_init(&emptyBar[g][st], 8);
+            }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (producer) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WD::kProdRegs));
+        const int role = (warp - WD::kConsWarps) & 1;
+        if (role == 0) {
+            // ================================ dense rows: solution slabs and metric rows ==================================
+            int it = 0;
+            for (int tile = tile0; tile < nTiles; tile += stride, it++) {
+                const int st = it & 1;
+                if (it >= 2) mbar_wait(&emptyBar[group][st], (unsigned)(((it >> 1) + 1) & 1));
+                const int k0 = tile * E;
+                const unsigned uB = smem_u32(sStage + (size_t)st * PD::kStageDoubles);
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    slab_g2s<NI, SE>(uB + (unsigned)((v * UROWS) * SE * sizeof(double)), a.q + (size_t)v * NI * Kp + k0, Kp, lane);
+                slab_g2s<4, E>(uB + (unsigned)(PD::kUDoubles * sizeof(double)), a.Jinv + k0, Kp, lane);
+                slab_g2s<6, E>(uB + (unsigned)((PD::kUDoubles + 4 * E) * sizeof(double)), args.mxy + k0, Kp, lane);
+                cp_async_arrive_noinc(&fullBar[group][st]);
+                mbar_arrive(&fullBar[group][st]);
+            }
+        } else {
+            // ================================ index chain and gathers: lane = element =====================================
+            int sIdx[3], vIdx[3];            // etoe / etov of this lane's element in the NEXT tile (prefetched one tile ahead)
+            auto elem_of = [&](int tile) {
+                const int tc = tile < nTiles ? tile : nTiles - 1;
+                const int k = tc * E + lane;
+                return k < a.K ? k : a.K - 1;
+            };
+            auto load_idx = [&](int tile) {
+                const int kc = elem_of(tile);
+#pragma unroll
+                for (int le = 0; le < 3; le++) {
+                    sIdx[le] = a.etoe[(size_t)le * Kp + kc];
+                    vIdx[le] = a.etov[(size_t)le * Kp + kc];
+                }
+            };
+            load_idx(tile0);
+            int it = 0;
+            for (int tile = tile0; tile < nTiles; tile += stride, it++) {
+                const int st = it & 1;
+                if (it >= 2) mbar_wait(&emptyBar[group][st], (unsigned)(((it >> 1) + 1) & 1));
+                const int kc = elem_of(tile);
+                double *base = sStage + (size_t)st * PD::kStageDoubles;
+                const unsigned uB = smem_u32(base);
+                // edge-table entries of the edges this element does not own (second level of the index chain)
+                int eKL[3], eNum[3];
+#pragma unroll
+                for (int le = 0; le < 3; le++) {
+                    eKL[le] = -1; eNum[le] = 0;
+                    if (sIdx[le] < 0) { eKL[le] = a.ekL[-1 - sIdx[le]]; eNum[le] = a.emeta[-1 - sIdx[le]] & 3; }
+                }
+                // per local edge: vertex epsilon, owner normal of the slot, the etoe entry (as the bits of a 64-bit integer)
+#pragma unroll
+                for (int le = 0; le < 3; le++) {
+                    const int slot = sIdx[le] >= 0 ? sIdx[le] : -1 - sIdx[le];
+                    cp_async8_u32(uB + (unsigned)((PD::kUDoubles + (10 + le) * E + lane) * sizeof(double)), a.epsV + vIdx[le]);
+                    cp_async8_u32(uB + (unsigned)((PD::kUDoubles + (13 + le) * E + lane) * sizeof(double)), a.enx + slot);
+                    cp_async8_u32(uB + (unsigned)((PD::kUDoubles + (16 + le) * E + lane) * sizeof(double)), a.eny + slot);
+                    base[PD::kUDoubles + (19 + le) * E + lane] = __longlong_as_double((long long)sIdx[le]);
+                }
+                // edge values: own edge rows, or the owner's rows with the points reversed (euler.go:896-912)
+#pragma unroll
+                for (int le = 0; le < 3; le++) {
+                    const bool rev = eKL[le] >= 0;
+                    const double *src0 = a.qface + (rev ? (size_t)(eNum[le] * NEd) * Kp + eKL[le] : (size_t)(le * NEd) * Kp + kc);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const double *src = src0 + (size_t)(v * NF3) * Kp;
+#pragma unroll
+                        for (int i = 0; i < NEd; i++)
+                            cp_async8_u32(uB + (unsigned)(((v * UROWS + 4 * KI + le * 4 * KE + i) * SE + lane) * sizeof(double)),
+                                          src + (size_t)(rev ? NEd - 1 - i : i) * Kp);
+                    }
+                }
+                cp_async_arrive_noinc(&fullBar[group][st]);
+                mbar_arrive(&fullBar[group][st]);
+                load_idx(tile + stride);
+            }
+        }
+    } else {
+        // ================================ consumer warps: (variable n, 16-element half) ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WD::kConsRegs));
+        const int wg = warp & 7, n = wg & 3, half = wg >> 2;
+        const int fr = lane >> 2, fc = lane & 3;
+        const int nt0 = 2 * half;
+        const unsigned groupOff = (unsigned)(GD::kTableDoubles + group * 2 * PD::kStageDoubles);
+        const unsigned laneU = (unsigned)(n * UROWS * SE + fc * SE + fr + 8 * nt0);          // B fragments
+        const unsigned laneM = (unsigned)(PD::kUDoubles + 8 * nt0 + 2 * fc);                 // metric / vertex-eps pairs
+        const unsigned laneB = (unsigned)(GD::kFragDoubles + fr * 3);                        // Bary rows
+        int it = 0;
+        for (int tile = tile0; tile < nTiles; tile += stride, it++) {
+            const int st = it & 1;
+            mbar_wait(&fullBar[group][st], (unsigned)((it >> 1) & 1));
+            const int k0 = tile * E;
+            unsigned oU = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles + laneU;
+            unsigned oM = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles + laneM;
+            unsigned oA = (unsigned)lane, oB = laneB;
+            size_t KpL = Kp;
+            asm volatile("" : "+r"(oU), "+r"(oM), "+r"(oA), "+r"(oB), "+l"(KpL));
+            const double *pU = smem + oU, *pM = smem + oM, *pA = smem + oA, *pB = smem + oB;
+            grad_mgroup<N, MG, 0>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+            if (MG < MT) grad_mgroup<N, MG, MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+            if (2 * MG < MT) grad_mgroup<N, MG, 2 * MG>(a, pU, pA, pM, pB, n, fr, fc, nt0, k0, KpL);
+            if (GD::NTAIL > 0) {
+                unsigned oT = groupOff + (unsigned)st * (unsigned)PD::kStageDoubles;
+                asm volatile("" : "+r"(oT));
+                grad_tail<N>(a, smem + oT + n * UROWS * SE, smem + oT + PD::kUDoubles, n, half, lane, k0);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyBar[group][st]);
+        }
+    }
+}
+
 }  // namespace dfr2d

@@ -171,11 +171,11 @@ def _smeared_sod_state(c, width=0.004):
 
 @pytest.mark.parametrize("n", [1, 2, 3, 4])
 @pytest.mark.parametrize("rk", [0, 2])
-@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
+@pytest.mark.parametrize("grad_kernel", [1, 3, 4])
 def test_dissipation_rhs_parity(n, rk, grad_kernel, monkeypatch):
     """RHSQ with sensor, vertex merge, RT gradient, viscous edge flux, AddDissipation and the RHS
     limiter; rk=2 also exercises the in-place limiting of the stage input (euler.go:605-609).
-    grad_kernel: 1 = constant-operand DFMA k_grad, 2 = tensor-core k_grad_mma, 3 = pipelined k_grad_pipe (read at
+    grad_kernel: 1 = constant-operand DFMA k_grad, 3 = pipelined k_grad_pipe, 4 = warp-specialised k_grad_ws (read at
     dfr2d_create).  The tensor-core kernels sum the Div contraction block-wise; at N=1 that order differs from the dense
     one by the operator's own float64 noise floor (3e-11, tests/test_noise_floor.py), hence 2e-10 there."""
     monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
@@ -194,7 +194,7 @@ def test_dissipation_rhs_parity(n, rk, grad_kernel, monkeypatch):
 
 
 @pytest.mark.parametrize("n", [2, 4])
-@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
+@pytest.mark.parametrize("grad_kernel", [1, 3, 4])
 def test_sod_steps_with_dissipation(n, grad_kernel, monkeypatch):
     """Config C3: Sod tube, PerssonC0, global dt (incl. the viscous dt limit), 10 steps from a smeared front."""
     monkeypatch.setenv("DFR2D_GRAD_KERNEL", str(grad_kernel))
@@ -396,7 +396,7 @@ def test_multi_partition_naca_local_dt():
 
 
 @pytest.mark.parametrize("n_parts,n", [(2, 2), (3, 4), (4, 1)])
-@pytest.mark.parametrize("grad_kernel", [1, 2, 3])
+@pytest.mark.parametrize("grad_kernel", [1, 3, 4])
 def test_multi_partition_sod_with_dissipation(n_parts, n, grad_kernel, monkeypatch):
     """PerssonC0 across partitions -- shared-vertex max merge, Q_Face + ghost vertex epsilon,
     DissX/DissY edge rows.  Bitwise equal to the single-partition device run, 1e-11 against the oracle."""

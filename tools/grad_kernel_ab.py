@@ -34,7 +34,7 @@ def main():
     # label -> (DFR2D_GRAD_KERNEL, DFR2D_GRAD_MG, DFR2D_GRAD_SKEW_NS, DFR2D_DISS_ELEM_KERNEL)
     variants = {1: ("1", "3", "0", "1"), 2: ("2", "3", "0", "1"), 3: ("3", "3", "0", "1"), 4: ("3", "2", "0", "1"),
                 5: ("3", "3", "1500", "1"), 6: ("3", "3", "3000", "1"), 7: ("3", "3", "5000", "1"), 8: ("3", "2", "3000", "1"),
-                9: ("3", "3", "0", "3"), 10: ("3", "3", "0", "5"), 11: ("3", "2", "0", "5")}
+                9: ("3", "3", "0", "3"), 10: ("3", "3", "0", "5"), 11: ("3", "2", "0", "5"), 12: ("4", "3", "0", "5"), 13: ("4", "2", "0", "5")}
     variants = {k: v for k, v in variants.items() if str(k) in args.variants.split(",")}
     for gk in variants:
         (os.environ["DFR2D_GRAD_KERNEL"], os.environ["DFR2D_GRAD_MG"], os.environ["DFR2D_GRAD_SKEW_NS"],
