@@ -494,7 +494,7 @@ class Runner:
         # per-GPU spread: every rank times its own kernels
         fr = self.reduce_list([ach / peak, -ach / peak], self.dist.ReduceOp.MAX if world > 1 else None)
         r = {"bound": "hbm",
-             "kernel": ("k_elem_ws<%d,8> (warp-specialised async-copy pipeline, FP64 DMMA contractions)" if n >= 2 else "k_elem<%d,false>") % n,
+             "kernel": ("k_elem_ws<%d,8,false,SPLIT> (warp-specialised async-copy pipeline: 4 copy warps, 8 flux+DMMA warps, 4 edge-interpolation warps)" if n >= 2 else "k_elem<%d,false>") % n,
              "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
              "algorithmic_bytes_per_launch": b_elem * k_local, "avg_launch_ms": te * 1e3,
              "per_gpu_frac_min_max": [-fr[1], fr[0]],

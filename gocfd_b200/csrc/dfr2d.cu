@@ -94,6 +94,7 @@ struct dfr2d_handle {
     bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
+    int wsSplit = 1;                 // kernel 5 with four extra interpolation warps (k_elem_ws<N,8,false,true>, DFR2D_WS_SPLIT)
     int edgePPT = 0;
     // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
     // single IPC handle / peer pointer gives a partner everything it writes
@@ -696,6 +697,11 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     if (const char *ev = getenv("DFR2D_ELEM_KERNEL")) h->elemKernel = atoi(ev);
     if (const char *ev = getenv("DFR2D_WS_STAGES")) h->wsStages = atoi(ev);
     if (const char *ev = getenv("DFR2D_WS_CW")) h->wsCW = atoi(ev) == 12 ? 12 : 8;
+    // measured (profiles/r02x_bench_c5_split{0,1}.json, two alternating runs each at C5): 32.94 / 33.15 ms per step without,
+    // 32.01 / 31.74 ms with the interpolation warps; kernel 5 itself 4.99 -> 4.65-4.70 ms (74.5 % -> 79-80 % of the HBM roofline);
+    // N=2 (2M triangles) 0.629 -> 0.626 ms: neutral.  Default on.
+    h->wsSplit = 1;
+    if (const char *ev = getenv("DFR2D_WS_SPLIT")) h->wsSplit = atoi(ev) != 0;
     if (const char *ev = getenv("DFR2D_DISS_PREFETCH")) h->dissPrefetch = atoi(ev) > 0 ? 1 : 0;
     if (const char *ev = getenv("DFR2D_EDGE_VISC_FUSED")) h->edgeViscFused = atoi(ev) != 0 ? 1 : 0;
     {
@@ -719,6 +725,9 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // N=3, 2.72 -> 2.53 at N=2 (2M triangles); k_grad_pipe stays selectable as 3 (2 maps to it as well)
     h->gradKernel = (N >= 2) ? 4 : 1;
     if (const char *ev = getenv("DFR2D_GRAD_KERNEL")) h->gradKernel = atoi(ev) >= 4 ? 4 : (atoi(ev) >= 2 ? 3 : 1);
+    // accumulation groups of the m-tiles: k_grad_pipe is best with {3,1} (profiles/r02s), k_grad_ws with {2,2} -- N=4: stage
+    // 4.87 -> 4.79 ms, N=3 ({2,1}): 3.73 -> 3.62 ms (profiles/r02u_ab_N*.json)
+    h->gradMG = (h->gradKernel == 4 && N >= 3) ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_MG")) h->gradMG = atoi(ev) == 2 ? 2 : 3;
     if (const char *ev = getenv("DFR2D_GRAD_SKEW_NS")) h->gradSkewNs = std::max(0, std::min(atoi(ev), 100000));
     // measured (2M triangles, profiles/r02l_ab_N*.json): the warp-specialised ring with the PerssonC0 terms
@@ -1114,7 +1123,7 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
             ta.tmaps = h->tmaps;
             DISPATCH_N(h->N, {
                 using TD = WsDim<NN>;
-                const size_t maxSmem = 232448 - 256;      // 227 KB per CTA minus the static mbarrier words
+                const size_t maxSmem = 232448 - 512;      // 227 KB per CTA minus the static mbarrier words
                 int stages = (int)(maxSmem / TD::smem_bytes(ta.nExtra, 1));
                 stages = std::max(2, std::min(stages, kWsMaxStages));     // two consumer groups: a waiter may be at most one phase ahead
                 // measured (profiles/r01i_ring_depth.txt): a deeper ring is SLOWER -- the shared memory it takes comes out
@@ -1132,8 +1141,11 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
                 if (!h->smemAttrSet) {
                     cudaFuncSetAttribute(k_elem_ws<NN, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
                     cudaFuncSetAttribute(k_elem_ws<NN, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
+                    cudaFuncSetAttribute(k_elem_ws<NN, 8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxSmem);
                 }
-                if (cw12) k_elem_ws<NN, 12, false><<<std::min(blocks, h->sms), (12 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
+                if (h->wsSplit && !cw12)
+                    k_elem_ws<NN, 8, false, true><<<std::min(blocks, h->sms), (8 + 4 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
+                else if (cw12) k_elem_ws<NN, 12, false><<<std::min(blocks, h->sms), (12 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
                 else k_elem_ws<NN, 8, false><<<std::min(blocks, h->sms), (8 + kWsProdWarps) * 32, sm, h->stream>>>(ta);
             });
             h->smemAttrSet = true;

@@ -129,19 +129,41 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
     asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// DFR2D_WS_KNOCKOUT (timing experiments only, tools/elem_knockout.py -- results are WRONG when non-zero): bit 0 drops the fused
+// edge interpolation (C2 and the Q_Face stores), bit 1 the physical flux evaluation, bit 3 the DMMA of the first
+// contraction, bit 4 all consumer work (the producers then run against the ring alone: the copy / HBM floor of the kernel),
+// bit 2 the stores of the new stage register, bit 5 the Q_Face stores but not C2, bit 6 C2 but not its stores
+#ifndef DFR2D_WS_KNOCKOUT
+#define DFR2D_WS_KNOCKOUT 0
+#endif
+__device__ __forceinline__ void ko_keep(double &acc, double v) {      // keeps v alive without touching the FP64 pipe
+    acc = __longlong_as_double(__double_as_longlong(acc) ^ __double_as_longlong(v));
+}
+
 // CW = consumer warps (8: two groups of four, 224 registers each; 12: three groups, 152 registers each)
 // DISS = the element kernel of the PerssonC0 path (AddDissipation, dissipation.go:274-346, and LimitFilterSolution on
 // RHSQ, euler.go:496-501, dissipation.go:520-542) on the same ring: the interior dissipation DOFs join Fr / Fs before
 // the DivInt contraction (the edge DOFs already carry F - F_visc: k_visc_edge subtracts in place), the modal limiter is
 // two more DMMA products through the warp's own columns of the dead DissX / DissY slabs, the viscous dt limit joins the
 // dt logic (euler.go:945-1002), and there is no fused interpolation (k_diss_prepare needs the vertex-merged sigma first).
-template <int N, int CW, bool DISS>
-__global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsArgs args) {
-    constexpr int kWsConsWarps = CW, kWsThreads = (CW + kWsProdWarps) * 32, kGroups = CW / 4;
-    constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = (CW == 8) ? 224 : 152;
+// SPLIT (r2, inviscid kernel only): the fused edge interpolation (C2 + the Q_Face stores) moves to FOUR MORE WARPS.  The
+// knock-out timings of tools/elem_knockout.py (profiles/r02v_*, r02w_*: 2M triangles, N=4) showed the kernel bound by the
+// latency of its consumer warps, not by the FP64 pipe or by HBM: dropping the flux evaluation changes nothing (1.26 ->
+// 1.25 ms), dropping 3/4 of the DMMA buys 10 %, but dropping C2 and its stores buys 29 % (0.90 ms, 83-87 % of the HBM
+// peak) -- 150 instructions of a dependent chain at ~10 cycles each that nothing else in the warp can hide.  With SPLIT
+// a consumer warp hands its 8 columns of the fresh register over (mbarrier qnewBar[stage][wq]) and moves on to its next
+// tile; interpolation warp wq contracts them with FluxEdgeInterp, releases the stage and streams Q_Face out.
+template <int N, int CW, bool DISS, bool SPLIT = false>
+__global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsArgs args) {
+    static_assert(!SPLIT || (CW == 8 && !DISS), "SPLIT: inviscid kernel with two consumer groups");
+    constexpr int kWsConsWarps = CW, kWsInterpWarps = SPLIT ? 4 : 0, kGroups = CW / 4;
+    constexpr int kWsThreads = (CW + kWsInterpWarps + kWsProdWarps) * 32;
+    // register budget (65,536 per SM): 8 x 32 x 224 + 4 x 32 x 56 | SPLIT: 8 x 32 x 176 + 4 x 32 x 96 + 4 x 32 x 56
+    constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = SPLIT ? 176 : ((CW == 8) ? 224 : 152), kInterpRegs = 96;
     using TD = WsDim<N>;
     constexpr int NI = TD::NI, NEd = TD::NEd, NF3 = TD::NF3, SE = TD::SE, E = kElemsPerBlock;
     constexpr int M1 = TD::M1, KI = TD::KI, KE = TD::KE, K1 = TD::K1, M2 = TD::M2, K2 = TD::K2;
+    constexpr int KO = DFR2D_WS_KNOCKOUT;
     const ElemArgs &a = args.a;
     if (step_is_noop(a.sc, a.ph, a.par, a.stepIndex)) {
         if (a.rk == 4 && a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -153,6 +175,7 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     extern __shared__ __align__(128) double smem_ws[];
     double *smem = smem_ws;
     __shared__ __align__(8) unsigned long long fullBar[kWsMaxStages], emptyBar[kWsMaxStages];
+    __shared__ __align__(8) unsigned long long qnewBar[SPLIT ? kWsMaxStages : 1][4];   // consumer warp wq -> interpolation warp wq
     const int S = args.nStages, nExtra = args.nExtra;
     const int nExtraS = TD::extras_in_smem(nExtra, DISS);           // extra RK registers staged in the ring
     const bool useTma = !DISS && args.tmaps != nullptr;
@@ -165,7 +188,9 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; s++) {
             mbar_init(&fullBar[s], kWsFullCount);
-            mbar_init(&emptyBar[s], 4);              // the four consumer warps of the tile
+            mbar_init(&emptyBar[s], 4);              // the four consumer (SPLIT: interpolation) warps of the tile
+            if (SPLIT)
+                for (int w = 0; w < 4; w++) mbar_init(&qnewBar[s][w], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -199,12 +224,12 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
     }
     const int nLocal = (args.nTiles > (int)blockIdx.x) ? (args.nTiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    if (warp >= kWsConsWarps) {
+    if (warp >= kWsConsWarps + kWsInterpWarps) {
         // =================================== producer warps ==================================================
         // 168 registers per thread are allotted at launch (12 warps x 168 x 32 = 64,512); the producers keep 56 and
         // hand the rest to the consumers (setmaxnreg, 4 x 56 + 8 x 224 = the same total)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProdRegs));
-        const int pw = warp - kWsConsWarps;
+        const int pw = warp - kWsConsWarps - kWsInterpWarps;
         if (pw == 0) {
             // ---- row slabs by the TMA engine; dt per element (lane = element) -------------------------------------
             int c0 = 0, c1 = 0, c2 = 0;
@@ -337,6 +362,87 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
+    } else if (SPLIT && warp >= kWsConsWarps) {
+        // =================================== interpolation warps (SPLIT) ======================================
+        // warp wq owns columns 8 wq .. 8 wq + 7 of EVERY tile of this CTA (both consumer groups), in tile order
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kInterpRegs));
+        const int wq = warp - kWsConsWarps;
+        const int fr = lane >> 2, fc = lane & 3;
+        const int eB = 8 * wq + fr, eC = 8 * wq + 2 * fc;
+        constexpr int NFL = Dim<N>::NpFlux;
+        const double *opF = smem + NI * NFL;
+        double a2[M2][K2];
+#pragma unroll
+        for (int mt = 0; mt < M2; mt++) {
+            const int row = 8 * mt + fr;
+#pragma unroll
+            for (int ks = 0; ks < K2; ks++) {
+                const int j = 4 * ks + fc;
+                a2[mt][ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");
+        const bool doInterp = a.rhsOut == nullptr && a.qface != nullptr;
+        int s = 0;
+        unsigned ph = 0;
+        for (int n = 0; n < nLocal; n++) {
+            const size_t k0 = (size_t)(blockIdx.x + (size_t)n * gridDim.x) * E;
+            const double *sQ = smem + (size_t)s * stageDoubles + TD::qOff;
+            mbar_wait(&qnewBar[s][wq], ph);
+            double tail[TD::NTail > 0 ? TD::NTail : 1];
+            double b[K2][4];
+            if (doInterp) {
+                // ragged last rows of FluxEdgeInterp by DFMA: lane = (variable, column) of the warp's 8 columns
+                if (TD::NTail > 0) {
+                    const Ops<N> &op = ops<N>();
+                    const double *qv = sQ + ((lane >> 3) * NI) * SE + 8 * wq + (lane & 7);
+#pragma unroll
+                    for (int r = 0; r < TD::NTail; r++) tail[r] = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NI; j++) {
+                        const double q = qv[j * SE];
+#pragma unroll
+                        for (int r = 0; r < TD::NTail; r++) tail[r] = fma(op.FEI[8 * M2 + r][j], q, tail[r]);
+                    }
+                }
+                // every B fragment of C2 up front: the stage goes back to the producers before the tensor work starts
+#pragma unroll
+                for (int ks = 0; ks < K2; ks++) {
+                    const int j = 4 * ks + fc;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) b[ks][v] = (4 * ks + 3 < NI || j < NI) ? sQ[(v * NI + j) * SE + eB] : 0.0;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&emptyBar[s]);
+            if (doInterp) {
+                double c2[4][M2][2];
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) c2[v][mt][0] = c2[v][mt][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < K2; ks++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+#pragma unroll
+                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[mt][ks], b[ks][v]);
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) {
+                        const int m = 8 * mt + fr;
+                        if (m < NF3)
+                            *reinterpret_cast<double2 *>(a.qface + ((size_t)v * NF3 + m) * Kp + k0 + eC) =
+                                make_double2(c2[v][mt][0], c2[v][mt][1]);
+                    }
+#pragma unroll
+                for (int r = 0; r < TD::NTail; r++)
+                    a.qface[((size_t)(lane >> 3) * NF3 + 8 * M2 + r) * Kp + k0 + 8 * wq + (lane & 7)] = tail[r];
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
     } else {
         // =================================== consumer warps ==================================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsRegs));
@@ -354,7 +460,7 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
         const double *opD = smem, *opF = smem + NI * NFL;
         // operator fragments, A[row = fr][k = fc] of every (m-tile, k-step); k-steps 2m / 2m+1 carry Fr / Fs of points
         // 4m..4m+3, k-steps 2KI.. the edge rows
-        double a1[M1][K1], a2[DISS ? 1 : M2][DISS ? 1 : K2];
+        double a1[M1][K1], a2[(DISS || SPLIT) ? 1 : M2][(DISS || SPLIT) ? 1 : K2];
         // DISS: Vinv and V (LimitFilterSolution, dissipation.go:606-622) as A fragments, both with the permuted row order;
         // mfRow = ModeFilter of this lane's modes (mode 0 is never scaled)
         double aVi[DISS ? M1 : 1][DISS ? KI : 1], aV[DISS ? M1 : 1][DISS ? KI : 1], mfRow[DISS ? M1 : 1];
@@ -393,14 +499,14 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                 a1[mt][2 * KI + ke] = (row < NI && r < TD::NE3k) ? opD[row * NFL + 2 * NI + r] : 0.0;
             }
         }
-        if (!DISS) {
+        if (!DISS && !SPLIT) {
 #pragma unroll
             for (int mt = 0; mt < M2; mt++) {
                 const int row = 8 * mt + fr;
 #pragma unroll
                 for (int ks = 0; ks < K2; ks++) {
                     const int j = 4 * ks + fc;
-                    a2[DISS ? 0 : mt][DISS ? 0 : ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
+                    a2[(DISS || SPLIT) ? 0 : mt][(DISS || SPLIT) ? 0 : ks] = (row < NF3 && j < NI) ? opF[row * NI + j] : 0.0;
                 }
             }
         }
@@ -416,6 +522,15 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
             double *sQ = st + TD::qOff;
             const double *sE = st + TD::eOff, *g = st + TD::gOff;
             mbar_wait(&fullBar[s], ph);
+            if (KO & 16) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&emptyBar[s]);
+#pragma unroll
+                for (int t = 0; t < kGroups; t++)
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                continue;
+            }
 
             // ---- C1 = DivInt . F_RT_DOF with the flux evaluated in B-fragment layout ----------------------------
             const double jd = g[eB], j0 = g[32 + eB], j1 = g[64 + eB], j2 = g[96 + eB], j3 = g[128 + eB];
@@ -433,7 +548,12 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                     double Q[4], Fx[4], Fy[4];
 #pragma unroll
                     for (int v = 0; v < 4; v++) Q[v] = sQ[(v * NI + p) * SE + eB];
-                    flux_calc(a.ph.gamma, Q, Fx, Fy);
+                    if (KO & 2) {
+#pragma unroll
+                        for (int v = 0; v < 4; v++) { Fx[v] = Q[v]; Fy[v] = Q[(v + 1) & 3]; }
+                    } else {
+                        flux_calc(a.ph.gamma, Q, Fx, Fy);
+                    }
 #pragma unroll
                     for (int v = 0; v < 4; v++) {
                         Fr[v] = jd * (j0 * Fx[v] + j1 * Fy[v]);
@@ -465,6 +585,11 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                         for (int v = 0; v < 4; v++) Fs[v] = sE[(v * NF3 + r) * SE + eB] * scl;
                     }
                 }
+                if (KO & 8) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) { ko_keep(c1[v][0][0], Fr[v]); ko_keep(c1[v][M1 - 1][1], Fs[v]); }
+                    continue;
+                }
 #pragma unroll
                 for (int v = 0; v < 4; v++)
 #pragma unroll
@@ -483,6 +608,11 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                     const double scl = pick3(le, sc0, sc1, sc2);
 #pragma unroll
                     for (int v = 0; v < 4; v++) b[v] = sE[(v * NF3 + r) * SE + eB] * scl;
+                }
+                if (KO & 8) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) ko_keep(c1[v][0][0], b[v]);
+                    continue;
                 }
 #pragma unroll
                 for (int v = 0; v < 4; v++)
@@ -602,15 +732,33 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
                             *reinterpret_cast<double2 *>(a.R + o) = r;
                         }
                         bad |= (qn.x != qn.x) || (qn.y != qn.y);
-                        *reinterpret_cast<double2 *>(dst + o) = qn;
+                        if (!(KO & 4)) *reinterpret_cast<double2 *>(dst + o) = qn;
                         *reinterpret_cast<double2 *>(&sQ[so]) = qn;      // in place: B operand of the interpolation below
                     }
                 }
             }
-            const bool doInterp = !DISS && a.rhsOut == nullptr && a.qface != nullptr;
+            if (SPLIT) {
+                // the fresh register is in this warp's columns of the stage-input slab: over to interpolation warp wq
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&qnewBar[s][wq]);
+#pragma unroll
+                for (int t = 0; t < kGroups; t++)
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                continue;
+            }
+            const bool doInterp = !(KO & 1) && !DISS && a.rhsOut == nullptr && a.qface != nullptr;
             double c2[4][M2][2];
             double tail[TD::NTail > 0 ? TD::NTail : 1];
-            if (doInterp) {
+            if (KO & 64) {            // stores without the contraction
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) c2[v][mt][0] = c2[v][mt][1] = 0.0;
+#pragma unroll
+                for (int r = 0; r < TD::NTail; r++) tail[r] = 0.0;
+            }
+            if (doInterp && !(KO & 64)) {
                 __syncwarp();
                 // ---- C2 = FluxEdgeInterp . q_new: next stage's Q_Face ---------------------------------------------
 #pragma unroll
@@ -628,7 +776,7 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
 #pragma unroll
                     for (int v = 0; v < 4; v++)
 #pragma unroll
-                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[DISS ? 0 : mt][DISS ? 0 : ks], b[v]);
+                        for (int mt = 0; mt < M2; mt++) dmma884(c2[v][mt][0], c2[v][mt][1], a2[(DISS || SPLIT) ? 0 : mt][(DISS || SPLIT) ? 0 : ks], b[v]);
                 }
                 // ragged last rows of FluxEdgeInterp by DFMA: lane = (variable, column) of the warp's 8 columns
                 if (TD::NTail > 0) {
@@ -649,7 +797,16 @@ __global__ void __launch_bounds__((CW + kWsProdWarps) * 32, 1) k_elem_ws(ElemWsA
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&emptyBar[s]);
-            if (doInterp) {
+            if (doInterp && (KO & 32)) {          // the contraction without its stores
+                double sink = 0.0;
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+#pragma unroll
+                    for (int mt = 0; mt < M2; mt++) { ko_keep(sink, c2[v][mt][0]); ko_keep(sink, c2[v][mt][1]); }
+#pragma unroll
+                for (int r = 0; r < TD::NTail; r++) ko_keep(sink, tail[r]);
+                bad |= (__double_as_longlong(sink) == 0x123456789abcll);
+            } else if (doInterp) {
 #pragma unroll
                 for (int v = 0; v < 4; v++)
 #pragma unroll
