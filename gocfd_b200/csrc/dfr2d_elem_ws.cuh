@@ -160,6 +160,9 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
     constexpr int kWsThreads = (CW + kWsInterpWarps + kWsProdWarps) * 32;
     // register budget (65,536 per SM): 8 x 32 x 224 + 4 x 32 x 56 | SPLIT: 8 x 32 x 176 + 4 x 32 x 96 + 4 x 32 x 56
     constexpr int kProdRegs = (CW == 8) ? 56 : 40, kConsRegs = SPLIT ? 176 : ((CW == 8) ? 224 : 152), kInterpRegs = 96;
+    // setmaxnreg only redistributes the registers the CTA got at launch; asking for more never returns
+    static_assert(CW * 32 * kConsRegs + kWsInterpWarps * 32 * kInterpRegs + kWsProdWarps * 32 * kProdRegs <= ((65536 / kWsThreads) & ~7) * kWsThreads,
+                  "setmaxnreg budget");
     using TD = WsDim<N>;
     constexpr int NI = TD::NI, NEd = TD::NEd, NF3 = TD::NF3, SE = TD::SE, E = kElemsPerBlock;
     constexpr int M1 = TD::M1, KI = TD::KI, KE = TD::KE, K1 = TD::K1, M2 = TD::M2, K2 = TD::K2;

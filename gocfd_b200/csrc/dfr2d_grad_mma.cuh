@@ -150,6 +150,17 @@ __device__ __forceinline__ void grad_block(const double *pUb, const double *pAb,
     }
 }
 
+// unroll factors of the two block loops of grad_mgroup (1 = rolled).  Measured with k_grad_ws<N,2> on 2M triangles
+// (profiles/r02ab_*): the two interior blocks unrolled (their DMMA chains and metric FMAs overlap) 2.66 -> 2.59 ms at N=4,
+// 2.04 -> 1.98 ms at N=3 for gradient + fused interior edges; unrolling the three edge blocks instead is slower (2.73 /
+// 2.06 ms), both together spill (288 B of local memory at 104 registers).
+#ifndef DFR2D_GRAD_UNROLL_INT
+#define DFR2D_GRAD_UNROLL_INT 2
+#endif
+#ifndef DFR2D_GRAD_UNROLL_EDGE
+#define DFR2D_GRAD_UNROLL_EDGE 1
+#endif
+
 // Rows [M0, M0+MG) of one tile: all five blocks, Epsilon product, stores.
 template <int N, int MG, int M0>
 __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU, const double *pA, const double *pM,
@@ -161,10 +172,11 @@ __device__ __forceinline__ void grad_mgroup(const GradArgs &a, const double *pU,
     for (int mt = 0; mt < MG; mt++)
 #pragma unroll
         for (int nt = 0; nt < 2; nt++) gx[mt][nt][0] = gx[mt][nt][1] = gy[mt][nt][0] = gy[mt][nt][1] = 0.0;
-#pragma unroll 1
+    constexpr int kUnrollInt = DFR2D_GRAD_UNROLL_INT, kUnrollEdge = DFR2D_GRAD_UNROLL_EDGE;
+#pragma unroll kUnrollInt
     for (int r = 0; r < 2; r++)                 // the two interior blocks share the B rows
         grad_block<N, MG, M0, KI>(pU, pA + r * KI * 32, pM + 2 * r * E, gx, gy);
-#pragma unroll 1
+#pragma unroll kUnrollEdge
     for (int le = 0; le < 3; le++)              // points of edge le
         grad_block<N, MG, M0, KE>(pU + (4 * KI + le * 4 * KE) * SE, pA + (2 * KI + le * KE) * 32, pM + (4 + 2 * le) * E, gx, gy);
     // vertex epsilon of this lane's element pairs (rows 10..12 of the metric block)
@@ -442,7 +454,14 @@ template <int N> struct GradWsDim {
     static constexpr int kConsWarps = 16, kProdWarps = 2 * PD::kGroups, kThreads = (kConsWarps + kProdWarps) * 32;
     static constexpr int kFullCount = 128;         // per producer lane (2 warps): its cp.async completions + one plain arrive
     // 640 threads are allotted 96 registers each; the producers keep 40 and hand the rest to the consumers
-    static constexpr int kProdRegs = 40, kConsRegs = 104;
+#ifndef DFR2D_GRAD_CONS_REGS
+#define DFR2D_GRAD_CONS_REGS 104
+#endif
+    static constexpr int kProdRegs = 40, kConsRegs = DFR2D_GRAD_CONS_REGS;
+    // setmaxnreg only redistributes what the CTA was given at launch (65,536 / threads, rounded down to 8): a consumer request
+    // beyond that waits for registers nobody will ever release -- the kernel hangs (measured the hard way at 112)
+    static constexpr int kLaunchRegs = (65536 / kThreads) & ~7;
+    static_assert(kConsWarps * 32 * kConsRegs + kProdWarps * 32 * kProdRegs <= kLaunchRegs * kThreads, "setmaxnreg budget");
 };
 
 template <int N, int MG>

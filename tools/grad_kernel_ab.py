@@ -23,10 +23,13 @@ def main():
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--variants", default="1,3,9", help="subset of the variant labels to run (1 is the reference state)")
+    ap.add_argument("--lib", default="", help="alternative build of libdfr2d.so (compile-time variants)")
     args = ap.parse_args()
     import torch
     import bench
     from gocfd_b200 import lib
+    if args.lib:
+        lib.LIB_PATH = os.path.abspath(args.lib)
     c = bench.build_case(args.nx, args.ny, args.order, dissipation=True)
     p = c.problem
     out = {"K": int(p.K), "N": int(p.N), "steps": args.steps}

@@ -14,8 +14,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also > $o/${tag}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_elem_ws|k_edge_int' -s 30 -c 10 -f -o /tmp/${tag}_c5_full \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also > $o/${tag}_ncu_full.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_elem_ws|k_grad_pipe|k_edge_int|k_diss_prepare' \
-    -s 24 -c 4 -f -o /tmp/${tag}_diss_full python tools/grad_kernel_ab.py --nx 1000 --ny 250 --steps 1 --variants 10 > $o/${tag}_ncu_diss.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:'k_elem_ws|k_grad_ws|k_edge_int|k_diss_prepare' \
+    -s 24 -c 4 -f -o /tmp/${tag}_diss_full python tools/grad_kernel_ab.py --nx 1000 --ny 250 --steps 1 --variants 13 > $o/${tag}_ncu_diss.log 2>&1
 # the reports stay on the box (an 8M-element capture with source is > 64 MiB); only text summaries travel
 python tools/ncu_summary.py /tmp/${tag}_c5_full.ncu-rep > $o/${tag}_ncu_full_c5.txt 2>&1
 python tools/ncu_summary.py /tmp/${tag}_diss_full.ncu-rep > $o/${tag}_ncu_full_diss_500K.txt 2>&1
