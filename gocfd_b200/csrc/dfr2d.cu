@@ -94,6 +94,7 @@ struct dfr2d_handle {
     bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
+    bool resInScalars = false;       // the residual maxima of the last step are in DevScalars::resMax (kernel 5), not in R
     int wsSplit = 1;                 // kernel 5 with four extra interpolation warps (k_elem_ws<N,8,false,true>, DFR2D_WS_SPLIT)
     int edgePPT = 0;
     // peer exchange (dfr2d_peer.cuh): one allocation = the three receive buffers + arrival flags + wave inbox, so that a
@@ -1063,6 +1064,11 @@ static int run_elem(dfr2d_handle *h, int rk, double *rhsOut, bool fuseInterp) {
     a.stepIndex = h->stepIndex;
     a.ph = h->ph;
     const int blocks = (h->K + kElemsPerBlock - 1) / kElemsPerBlock;
+    if (rk == 4 && rhsOut == nullptr) {
+        // kernel 5 reduces the residual register to its four maxima inside the launch (DevScalars::resMax) instead of
+        // writing it out; every other element kernel stores it and dfr2d_residual reduces it afterwards
+        h->resInScalars = h->ph.dissipation ? (h->dissElemKernel == 5) : (h->elemKernel == 5);
+    }
     if (h->ph.dissipation && h->dissElemKernel == 5) {
         // the warp-specialised ring of kernel 5 with the PerssonC0 terms (k_elem_ws<N, 8, true>, dfr2d_elem_ws.cuh)
         ElemWsArgs ta{};
@@ -1796,6 +1802,13 @@ extern "C" int dfr2d_rhs(dfr2d_handle *h, int rk, double *RHS_out) {
 extern "C" int dfr2d_residual(dfr2d_handle *h, double maxR[4]) {
     if (!h || !maxR) return 1;
     CK(cudaSetDevice(h->device));
+    if (h->resInScalars) {
+        unsigned long long enc[4];
+        CK(cudaMemcpyAsync(enc, &h->sc->resMax[0], sizeof(enc), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int n = 0; n < 4; n++) maxR[n] = res_decode(enc[n]);
+        return 0;
+    }
     if (int rc = scratch_reserve(h, 4 * sizeof(double))) return rc;
     double *tmp = (double *)h->scratch;
     k_signed_max<<<4, 1024, 0, h->stream>>>(h->R, h->NpInt, h->K, h->Kp, tmp);

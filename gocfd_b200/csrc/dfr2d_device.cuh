@@ -57,7 +57,29 @@ struct DevScalars {
     long long steps;                 // rk.StepCount
     int finished;
     int nanFlag;
+    // (r2) Matrix.Max of the four Residual registers (PrintUpdate, euler.go:821-835), reduced inside the rk 4 launch of
+    // kernel 5 instead of writing the residual register out and reading it back: order-preserving unsigned encoding of
+    // the signed doubles (res_encode), zeroed by the host before that launch
+    unsigned long long resMax[4];
 };
+
+// signed double <-> unsigned integer with the same order (NaNs aside): atomicMax on the integer is max on the doubles
+__host__ __device__ __forceinline__ unsigned long long res_encode(double d) {
+#ifdef __CUDA_ARCH__
+    const long long b = __double_as_longlong(d);
+#else
+    long long b; memcpy(&b, &d, 8);
+#endif
+    return b >= 0 ? ((unsigned long long)b | 0x8000000000000000ull) : ~(unsigned long long)b;
+}
+__host__ __device__ __forceinline__ double res_decode(unsigned long long u) {
+    const unsigned long long b = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
 
 // ---- fast reciprocal / square root ----------------------------------------------------------------
 // IEEE double division and sqrt expand to ~15-25 instructions with a slow-path call each; the Riemann

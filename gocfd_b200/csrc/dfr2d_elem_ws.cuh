@@ -385,6 +385,8 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
             }
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");
+        // (measured and dropped, profiles/r02ac_*: storing the fresh register from here as well -- the B fragments of a warp
+        // are exactly its 8 columns of it -- makes these warps the bottleneck: kernel 4.70 -> 5.13 ms at C5)
         const bool doInterp = a.rhsOut == nullptr && a.qface != nullptr;
         int s = 0;
         unsigned ph = 0;
@@ -515,6 +517,7 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kWsThreads) : "memory");      // operator table consumed: the ring may be filled
         bool bad = false;
+        double resMax[4] = {-1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308, -1.7976931348623157e308};
         double *dst = (a.rk == 0) ? a.q1 : (a.rk == 1) ? a.q2 : (a.rk == 2) ? a.q3 : (a.rk == 3) ? a.q4 : a.q0;
 
         int s = group % S;
@@ -624,6 +627,7 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
             }
 
             // ---- epilogue in accumulator layout: rows 8 mt + fr, columns eC, eC + 1 ------------------------------
+            const bool fullTile = k0 + E <= (size_t)a.K;
             const double2 jdc = *reinterpret_cast<const double2 *>(&g[eC]);
             const double2 dt = *reinterpret_cast<const double2 *>(&g[8 * 32 + eC]);
             double mo0 = -(1.0 / jdc.x), mo1 = -(1.0 / jdc.y);
@@ -732,7 +736,10 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
                             r.y = -q0v.y + RK4_A * q2v.y + RK4_B * q3v.y + RK4_C * qs.y + RK4_D * (dt.y * rv.y) + RK4_E * (dt.y * rhs1);
                             qn.x = q0v.x + r.x;
                             qn.y = q0v.y + r.y;
-                            *reinterpret_cast<double2 *>(a.R + o) = r;
+                            // the residual register is only ever reduced to its per-variable maximum (PrintUpdate,
+                            // euler.go:821-835): reduce here instead of writing it out (pad columns excluded)
+                            if (fullTile || k0 + eC < (size_t)a.K) resMax[v] = fmax(resMax[v], r.x);
+                            if (fullTile || k0 + eC + 1 < (size_t)a.K) resMax[v] = fmax(resMax[v], r.y);
                         }
                         bad |= (qn.x != qn.x) || (qn.y != qn.y);
                         if (!(KO & 4)) *reinterpret_cast<double2 *>(dst + o) = qn;
@@ -828,11 +835,21 @@ __global__ void __launch_bounds__((CW + (SPLIT ? 4 : 0) + kWsProdWarps) * 32, 1)
                 if (++s == S) { s = 0; ph ^= 1u; }
         }
         if (bad) a.sc->nanFlag = 1;
+        if (a.rk == 4 && a.rhsOut == nullptr) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const double m = warp_max(resMax[v]);
+                if (lane == 0 && nLocal > group) atomicMax(&a.sc->resMax[v], res_encode(m));
+            }
+        }
     }
 
     if (a.rhsOut == nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         a.sc->wave[a.slot ^ 1][0] = 0ull;
         a.sc->wave[a.slot ^ 1][1] = 0ull;
+        // the residual maxima of this step are accumulated by the rk 4 launch: cleared here, inside a launch that only runs
+        // when the step does (a host-side memset would also clear them on the no-op steps after FinalTime)
+        if (a.rk == 3) a.sc->resMax[0] = a.sc->resMax[1] = a.sc->resMax[2] = a.sc->resMax[3] = 0ull;
         if (!a.ph.localDT) a.sc->globalDT = dtGlobal;
         if (a.rk == 4) {
             const double tnew = a.sc->time[a.par] + (a.ph.localDT ? a.sc->globalDT : dtGlobal);

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdfr2d.so")
+LIB_PATH = os.environ.get("DFR2D_LIB_PATH") or os.path.join(_HERE, "csrc", "libdfr2d.so")     # override: A/B of two builds
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
