@@ -94,6 +94,11 @@ struct dfr2d_handle {
     bool dissWsAttrSet = false;
     int dissPrefetch = 0;             // k_elem_mma_diss: L2 prefetch of the next tile (DFR2D_DISS_PREFETCH, measured slower)
     int wsCW = 8;                    // consumer warps of kernel 5: 8 (two groups) or 12 (three groups, DFR2D_WS_CW)
+    // single partition: the short boundary-edge list kernel (BC transcendentals, a few dozen CTAs, 14 us at C2) runs on a
+    // second stream beside the interior-edge kernel instead of after it (DFR2D_EDGE_OVERLAP=0 turns it off)
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    int edgeOverlap = 1;
     bool resInScalars = false;       // the residual maxima of the last step are in DevScalars::resMax (kernel 5), not in R
     int wsSplit = 1;                 // kernel 5 with four extra interpolation warps (k_elem_ws<N,8,false,true>, DFR2D_WS_SPLIT)
     int edgePPT = 0;
@@ -234,6 +239,9 @@ extern "C" void dfr2d_destroy(dfr2d_handle *h) {
     for (void *p : h->allocs) cudaFree(p);
     if (h->scratch) cudaFree(h->scratch);
     if (h->scHost) cudaFreeHost(h->scHost);
+    if (h->auxStream) cudaStreamDestroy(h->auxStream);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     delete h;
 }
 
@@ -703,6 +711,12 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     // N=2 (2M triangles) 0.629 -> 0.626 ms: neutral.  Default on.
     h->wsSplit = 1;
     if (const char *ev = getenv("DFR2D_WS_SPLIT")) h->wsSplit = atoi(ev) != 0;
+    if (const char *ev = getenv("DFR2D_EDGE_OVERLAP")) h->edgeOverlap = atoi(ev) != 0;
+    if (h->edgeOverlap && h->nParts == 1) {
+        CK(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming));
+    }
     if (const char *ev = getenv("DFR2D_DISS_PREFETCH")) h->dissPrefetch = atoi(ev) > 0 ? 1 : 0;
     if (const char *ev = getenv("DFR2D_EDGE_VISC_FUSED")) h->edgeViscFused = atoi(ev) != 0 ? 1 : 0;
     {
@@ -1010,6 +1024,14 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
     })
     if (h->edgeSplit) {
         const int ib = std::max(1, std::min(h->edgeBlocks * 2, (int)(((long long)h->NEp * ((h->N + 2) / ppt) + 255) / 256)));
+        // both kernels in one call on a single partition: the list kernel goes to the second stream, forked here (after
+        // everything both depend on) and joined below; they write disjoint edge slots and share only the atomicMax words
+        const bool overlap = part == 3 && h->auxStream != nullptr && h->nBnd > 0;
+        if (overlap) {
+            CK(cudaEventRecord(h->evFork, h->stream));
+            CK(cudaStreamWaitEvent(h->auxStream, h->evFork, 0));
+        }
+        cudaStream_t listStream = overlap ? h->auxStream : h->stream;
         if (part & 1) {
         switch (h->ph.fluxType) {
 #define KI_AVG(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_Average, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_Average, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
@@ -1028,8 +1050,12 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
         {
             const int ppt = pptList;       // (EDGE_LAUNCH dispatches on `ppt`)
             const int bb = std::max(1, std::min(h->edgeBlocks, (h->nBnd * ((h->N + 2) / ppt) + 255) / 256));
-#define KB(NN_, P_) do { if (visc) k_edge<NN_, P_, true><<<bb, 256, 0, h->stream>>>(a); else k_edge<NN_, P_, false><<<bb, 256, 0, h->stream>>>(a); } while (0)
+#define KB(NN_, P_) do { if (visc) k_edge<NN_, P_, true><<<bb, 256, 0, listStream>>>(a); else k_edge<NN_, P_, false><<<bb, 256, 0, listStream>>>(a); } while (0)
             EDGE_LAUNCH(KB);
+        }
+        if (overlap) {
+            CK(cudaEventRecord(h->evJoin, h->auxStream));
+            CK(cudaStreamWaitEvent(h->stream, h->evJoin, 0));
         }
         return launch_check(h, "k_edge(boundary)");
     }
