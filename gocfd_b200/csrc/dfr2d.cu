@@ -20,6 +20,7 @@
 #include "dfr2d_elem_ws.cuh"
 #include "dfr2d_grad_mma.cuh"
 #include "dfr2d_elem_mma_diss.cuh"
+#include "dfr2d_edge_ws.cuh"
 
 using namespace dfr2d;
 
@@ -99,6 +100,8 @@ struct dfr2d_handle {
     cudaStream_t auxStream = nullptr;
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     int edgeOverlap = 1;
+    int edgeWs = 0, edgeWsStages = 0; // interior edges by the warp-specialised k_edge_ws (DFR2D_EDGE_WS, DFR2D_EDGE_WS_STAGES)
+    bool edgeWsAttrSet = false;
     bool resInScalars = false;       // the residual maxima of the last step are in DevScalars::resMax (kernel 5), not in R
     int wsSplit = 1;                 // kernel 5 with four extra interpolation warps (k_elem_ws<N,8,false,true>, DFR2D_WS_SPLIT)
     int edgePPT = 0;
@@ -712,6 +715,8 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
     h->wsSplit = 1;
     if (const char *ev = getenv("DFR2D_WS_SPLIT")) h->wsSplit = atoi(ev) != 0;
     if (const char *ev = getenv("DFR2D_EDGE_OVERLAP")) h->edgeOverlap = atoi(ev) != 0;
+    if (const char *ev = getenv("DFR2D_EDGE_WS")) h->edgeWs = atoi(ev) != 0;
+    if (const char *ev = getenv("DFR2D_EDGE_WS_STAGES")) h->edgeWsStages = atoi(ev);
     if (h->edgeOverlap && h->nParts == 1) {
         CK(cudaStreamCreateWithFlags(&h->auxStream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming));
@@ -1008,6 +1013,9 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
     // edges through the BC transcendental functions one point after the other (measured at C5: 57 us for 8,000 edges)
     int pptList = (h->nBnd < 64 * h->sms * 256 && h->edgePPT <= 0) ? 1 : ppt;
     if ((h->N + 2) % pptList != 0) pptList = h->N + 2;
+    // interior edges by the producer / consumer pipeline (two points per thread): even NpEdge, inviscid form only
+    const bool useWs = h->edgeWs && h->edgeSplit && !visc && (h->N % 2 == 0);
+    if (useWs) ppt = 2;
     if ((ppt != h->N + 2 || (h->edgeSplit && pptList != h->N + 2)) && h->ph.localDT && (part & 1))
     {
         CK(cudaMemsetAsync(h->agg, 0, (size_t)h->NEp * sizeof(double), h->stream));
@@ -1032,7 +1040,24 @@ static int run_edges(dfr2d_handle *h, int rk, int part) {
             CK(cudaStreamWaitEvent(h->auxStream, h->evFork, 0));
         }
         cudaStream_t listStream = overlap ? h->auxStream : h->stream;
-        if (part & 1) {
+        if ((part & 1) && useWs) {
+            const int nTiles = (h->NEp + 127) / 128;
+#define KWS(NN_, FL_) do {                                                                                              \
+                using ED = EdgeWsDim<NN_>;                                                                              \
+                int st = h->edgeWsStages >= 2 ? std::min(h->edgeWsStages, (int)ED::kMaxStages) : ED::stages();          \
+                while (st > 2 && (size_t)st * ED::kStageDoubles * sizeof(double) > 232448 - 512) st--;                  \
+                cudaFuncSetAttribute(k_edge_ws<NN_, FL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 512);   \
+                k_edge_ws<NN_, FL_><<<std::min(nTiles, h->sms), ED::kThreads, (size_t)st * ED::kStageDoubles * sizeof(double), h->stream>>>(a, nTiles, st); \
+            } while (0)
+#define KWS_N(FL_) do { if (h->N == 4) KWS(4, FL_); else if (h->N == 2) KWS(2, FL_); else KWS(0, FL_); } while (0)
+            switch (h->ph.fluxType) {
+                case DFR2D_FLUX_Average: KWS_N(DFR2D_FLUX_Average); break;
+                case DFR2D_FLUX_LaxFriedrichs: KWS_N(DFR2D_FLUX_LaxFriedrichs); break;
+                case DFR2D_FLUX_Roe: KWS_N(DFR2D_FLUX_Roe); break;
+                default: KWS_N(DFR2D_FLUX_RoeER); break;
+            }
+            if (int rc = launch_check(h, "k_edge_ws")) return rc;
+        } else if (part & 1) {
         switch (h->ph.fluxType) {
 #define KI_AVG(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_Average, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_Average, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)
 #define KI_LAX(NN_, P_) do { if (visc) k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_, true><<<ib, 256, 0, h->stream>>>(a); else k_edge_int<NN_, DFR2D_FLUX_LaxFriedrichs, P_, false><<<ib, 256, 0, h->stream>>>(a); } while (0)

@@ -94,6 +94,28 @@ def test_elem_ws_interpolation_warps_bitwise(n, local_dt, monkeypatch):
     assert rel_l2(states[1], want_state) < TOL
 
 
+@pytest.mark.parametrize("n", [0, 2, 4])
+@pytest.mark.parametrize("flux,local_dt", [("roe", False), ("lax", True), ("roe-er", False)])
+def test_edge_ws_kernel_bitwise(n, flux, local_dt, monkeypatch):
+    """The warp-specialised interior-edge kernel (DFR2D_EDGE_WS=1, k_edge_ws: producer warps gather Q_Face into a shared
+    ring, consumer threads = edge x pair of points) calls the same flux functions on the same operands as k_edge_int:
+    states bitwise equal, incl. the per-edge aggregates of local time stepping (atomicMax of three threads per edge)."""
+    from gocfd_b200 import lib
+    c = make(dict(PolynomialOrder=n, InitType="IVortex", FluxType=flux, CFL=1.0, FinalTime=50.0, LocalTimeStepping=local_dt),
+             structured_tri_mesh(31, 17))
+    states, dts = [], []
+    for ws in ("0", "1"):
+        monkeypatch.setenv("DFR2D_EDGE_WS", ws)
+        dev = lib.Dfr2d(c.problem)
+        dev.set_state(c.Q)
+        dev.step(3)
+        states.append(dev.get_state())
+        dts.append(dev.get_field(0))
+        dev.close()
+    assert np.array_equal(states[0], states[1])
+    assert np.array_equal(dts[0], dts[1])
+
+
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 4])
 def test_vortex_steps_global_dt(n):
     """Isentropic vortex with analytic IVortex+Riemann boundaries, global dt, 5 steps."""
