@@ -148,7 +148,9 @@ int dfr2d_set_clock(dfr2d_handle *h, double time, int64_t steps);
  * info may be NULL (no host synchronisation at all). */
 int dfr2d_step(dfr2d_handle *h, int nsteps, dfr2d_step_info *info);
 
-/* Signed max of the Residual arrays per variable, as PrintUpdate reports it (euler.go:821-835). */
+/* Signed max of the Residual arrays per variable, as PrintUpdate reports it (euler.go:821-835), for the last step that
+ * ran.  With the default element kernel the four maxima are reduced inside the last stage's launch and this call only
+ * reads four scalars; the Residual register itself (euler.go:553-560) is then never materialised. */
 int dfr2d_residual(dfr2d_handle *h, double maxR[4]);
 
 /* Test hooks: RHSQ of stage rk evaluated on register `rk` ({c.Q,Q1..Q4}[rk], euler.go:422) without
