@@ -16,12 +16,16 @@
  *   28 x { int64 nbytes ; data }                 the pointer members in declaration order
  *   int64 nbytes ; data                          initial state Q  [4][NpInt][K]
  *
- * usage: solve_host <pack> <out> <nsteps> [n_parts [n_devices]]
+ * usage: solve_host <pack> <out> <nsteps> [n_parts [n_devices [migrate]]]
  *   n_parts = 1 : dfr2d_create / dfr2d_set_state / nsteps x dfr2d_step(1) / dfr2d_residual / dfr2d_get_state
  *   n_parts > 1 : the MultiSolver sequence (dfr2d_multi_set_state / dfr2d_multi_step / dfr2d_multi_get_state), partition g
  *                 on device g % n_devices
+ *   migrate = 1 : every step call is made from a freshly created OS thread -- a goroutine that is not locked to its
+ *                 thread (no runtime.LockOSThread) migrates between OS threads from one cgo call to the next, so the
+ *                 library must select its device inside every entry point (SURVEY.md 8b "Threading")
  * out: "DFR2DOUT" ; dfr2d_step_info ; double maxR[4] ; int64 n ; double Q[n]
  */
+#include <pthread.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -48,8 +52,47 @@ static void *read_block(FILE *f, int64_t *nbytes) {
     return p;
 }
 
+/* one step call, possibly on another OS thread */
+typedef struct step_call {
+    dfr2d_handle **hs;
+    int n_parts;
+    dfr2d_step_info *info;
+    double *maxR; /* single partition: dfr2d_residual after the step */
+    int rc;
+    const char *what;
+} step_call;
+
+static void *do_step(void *arg) {
+    step_call *c = (step_call *)arg;
+    if (c->n_parts == 1) {
+        c->what = "dfr2d_step";
+        c->rc = dfr2d_step(c->hs[0], 1, c->info);
+        if (!c->rc) {
+            c->what = "dfr2d_residual";
+            c->rc = dfr2d_residual(c->hs[0], c->maxR);
+        }
+    } else {
+        c->what = "dfr2d_multi_step";
+        c->rc = dfr2d_multi_step(c->hs, c->n_parts, 1, c->info);
+    }
+    return NULL;
+}
+
+static void step_once(step_call *c, int migrate) {
+    if (migrate) {
+        pthread_t t;
+        if (pthread_create(&t, NULL, do_step, c)) die("pthread_create", NULL);
+        pthread_join(t, NULL);
+    } else {
+        do_step(c);
+    }
+    if (c->rc) die(c->what, dfr2d_last_error(c->hs[0]));
+    if (c->info->nan_found) die("NAN found", NULL);
+}
+
 int main(int argc, char **argv) {
-    if (argc < 4) die("usage: solve_host <pack> <out> <nsteps> [n_parts [n_devices]]", NULL);
+    if (argc < 4) die("usage: solve_host <pack> <out> <nsteps> [n_parts [n_devices [migrate]]]", NULL);
+    int migrate = argc > 6 ? atoi(argv[6]) : 0;
     int nsteps = atoi(argv[3]);
     int n_parts = argc > 4 ? atoi(argv[4]) : 1;
     int n_devices = argc > 5 ? atoi(argv[5]) : 1;
@@ -84,22 +127,16 @@ int main(int argc, char **argv) {
     dfr2d_step_info info;
     memset(&info, 0, sizeof info);
     double maxR[4] = {0, 0, 0, 0};
+    step_call call = {hs, n_parts, &info, maxR, 0, ""};
     if (n_parts == 1) {
         if (dfr2d_set_state(hs[0], Q)) die("dfr2d_set_state", dfr2d_last_error(hs[0]));
         /* for !finished { c.RK.Step(c); steps++; ... PrintUpdate every n }  (euler.go:175-186) */
-        for (int s = 0; s < nsteps && !info.finished; s++) {
-            if (dfr2d_step(hs[0], 1, &info)) die("dfr2d_step", dfr2d_last_error(hs[0]));
-            if (info.nan_found) die("NAN found", NULL);
-            if (dfr2d_residual(hs[0], maxR)) die("dfr2d_residual", dfr2d_last_error(hs[0]));
-        }
+        for (int s = 0; s < nsteps && !info.finished; s++) step_once(&call, migrate);
         memset(Q, 0, (size_t)qbytes);
         if (dfr2d_get_state(hs[0], Q)) die("dfr2d_get_state", dfr2d_last_error(hs[0]));
     } else {
         if (dfr2d_multi_set_state(hs, n_parts, Q)) die("dfr2d_multi_set_state", dfr2d_last_error(hs[0]));
-        for (int s = 0; s < nsteps && !info.finished; s++) {
-            if (dfr2d_multi_step(hs, n_parts, 1, &info)) die("dfr2d_multi_step", dfr2d_last_error(hs[0]));
-            if (info.nan_found) die("NAN found", NULL);
-        }
+        for (int s = 0; s < nsteps && !info.finished; s++) step_once(&call, migrate);
         /* MultiSolver.Residual: signed max over the partitions' own maxima */
         for (int g = 0; g < n_parts; g++) {
             double r[4];

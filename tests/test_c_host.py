@@ -149,3 +149,18 @@ def test_c_host_multi_partition_is_bitwise_single(host, tmp_path, n_parts):
     assert info.steps == 5
     assert np.array_equal(q1, qn)
     assert np.array_equal(r1, rn)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_parts", [1, 3])
+def test_c_host_calls_migrate_between_os_threads(host, tmp_path, n_parts):
+    """A goroutine that is not locked to its OS thread makes successive cgo calls from different threads (SURVEY.md 8b
+    "Threading"): every step issued from a freshly created pthread gives bitwise the result of the single-threaded host --
+    the library selects its device (and, with several partitions, every partition's device) inside each entry point."""
+    from conftest import _cuda_device_count
+    c = case(PolynomialOrder=2, LocalTimeStepping=(n_parts == 1))
+    nd = min(n_parts, _cuda_device_count())
+    i0, r0, q0 = run(host, c, tmp_path, 6, n_parts, nd, 0)
+    i1, r1, q1 = run(host, c, tmp_path, 6, n_parts, nd, 1)
+    assert i0.steps == i1.steps == 6 and i0.time == i1.time
+    assert np.array_equal(q0, q1) and np.array_equal(r0, r1)
