@@ -226,6 +226,25 @@ func (s *Solver) PlotField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []float32 
 	return out
 }
 
+// CaptureEdgeValues keeps the EdgeQValues store (the owner side's Q_Face of every step's last stage, edges.go:344-350)
+// on the device from the next step on; GradientField needs it.  Turn it on before the step whose fields are plotted.
+func (s *Solver) CaptureEdgeValues(c *Euler2D.Euler, on bool) {
+	if !on {
+		s.check(C.dfr2d_capture_edge_values(s.h, 0, nil, nil), "dfr2d_capture_edge_values")
+		return
+	}
+	fn := c.DFR.FaceNorm
+	s.check(C.dfr2d_capture_edge_values(s.h, 1, d(fn[0].DataP), d(fn[1].DataP)), "dfr2d_capture_edge_values")
+}
+
+// GradientField replaces GetPlotField for XGradientDensity..YGradientEnergy (plot.go:54-77): [NpFlux x K] doubles, not
+// interpolated, as GetSolutionGradientUsingRTElement(-1, n, c.Q, ...) leaves GradX / GradY.
+func (s *Solver) GradientField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []float64 {
+	out := make([]float64, c.DFR.FluxElement.Np*s.k)
+	s.check(C.dfr2d_gradient_field(s.h, C.int(ff), d(out)), "dfr2d_gradient_field")
+	return out
+}
+
 func (s *Solver) Close() { C.dfr2d_destroy(s.h); s.h = nil }
 
 // MultiSolver drives one handle per GPU from a single Go process -- the shape of the reference's controller goroutine

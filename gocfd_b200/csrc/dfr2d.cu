@@ -71,6 +71,11 @@ struct dfr2d_handle {
     DevScalars *scHost = nullptr;     // pinned
     long long stageCounter = 0, stepIndex = 0, launches = 0;
     bool qfaceValid = false;          // Q_Face holds the interpolation of the next stage's input register
+    // gradient plot fields (plot.go:54-77): the EdgeQValues store = Q_Face of the last stage 5, captured on request
+    bool captureEdgeQ = false;
+    double *qfaceSaved = nullptr;     // [4][3NpEdge][Kp], zero until the first captured step (the reference's store starts at 0)
+    double *nxkPlot = nullptr, *nykPlot = nullptr;   // [3][Kp] element face normals (the limiter's copies when it is on)
+    bool haveDiv = false;             // dfr2d_problem.Div was given
     bool interiorDone = false;        // the interior-edge kernel of the stage in flight has been launched (overlap with the halo)
     int edgeBlocks = 0;
     bool smemAttrSet = false;
@@ -535,6 +540,7 @@ static int create_impl(dfr2d_handle *h, const dfr2d_problem *p) {
         default: pack_ops<4>(p, h->opsHost); break;
     }
     h->opsFp = ops_fingerprint(h->opsHost);
+    h->haveDiv = p->Div != nullptr;
     // physics block
     Phys &ph = h->ph;
     ph.gamma = p->FSFar.Gamma;
@@ -1446,6 +1452,14 @@ static int stage_update(dfr2d_handle *h, int rk, double *rhsOut) {
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     const bool fuse = (rhsOut == nullptr) && !h->ph.dissipation;
+    if (rk == 4 && rhsOut == nullptr && h->captureEdgeQ) {
+        // EdgeQValues of the stage that is about to complete (edges.go:344-350), before kernel 5 reuses Q_Face
+        const size_t n2 = (size_t)4 * 3 * h->NpEdge * h->Kp / 2;       // Kp is even (padded to the element-block size)
+        const int blocks = (int)std::min<size_t>((n2 + 255) / 256, (size_t)h->sms * 8);
+        k_capture_qface<<<std::max(blocks, 1), 256, 0, h->stream>>>(n2, (const double2 *)h->qface, (double2 *)h->qfaceSaved, h->sc, h->ph,
+                                                                  (int)(h->stepIndex & 1), h->stepIndex);
+        if (int rc = launch_check(h, "k_capture_qface")) return rc;
+    }
     if (int rc = run_elem(h, rk, rhsOut, fuse)) return rc;
     if (rhsOut == nullptr) {
         h->qfaceValid = fuse;
@@ -1954,6 +1968,70 @@ extern "C" int dfr2d_epsilon_field(dfr2d_handle *h, int c0, double *out) {
     DISPATCH_N(h->N, (k_epsilon_field<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(h->K, h->Kp, c0, h->ds.epsk, h->ds.epsV, h->ds.etov, tmp)));
     if (int rc = launch_check(h, "k_epsilon_field")) return rc;
     CK(cudaMemcpy2DAsync(out + h->hostOff, (size_t)h->hostPitch * sizeof(double), tmp, (size_t)h->K * sizeof(double),
+                         (size_t)h->K * sizeof(double), (size_t)h->NpFlux, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---- gradient plot fields --------------------------------------------------------------------------------------------
+extern "C" int dfr2d_capture_edge_values(dfr2d_handle *h, int on, const double *FaceNormX, const double *FaceNormY) {
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    if (!on) { h->captureEdgeQ = false; return 0; }
+    if (!h->qfaceSaved) {
+        const size_t n = (size_t)4 * 3 * h->NpEdge * h->Kp;
+        if (h->Kp % 2) { h->err = "internal: odd column padding"; return 1; }
+        if (int rc = dev_alloc(h, &h->qfaceSaved, n)) return rc;
+        CK(cudaMemsetAsync(h->qfaceSaved, 0, n * sizeof(double), h->stream));
+    }
+    if (!h->nxkPlot) {
+        if (h->ph.dissipation) {
+            h->nxkPlot = h->ds.nxk; h->nykPlot = h->ds.nyk;
+        } else {
+            if (!FaceNormX || !FaceNormY) {
+                h->err = "dfr2d_capture_edge_values: DFR.FaceNorm[0|1] are needed once (the handle keeps element normals only "
+                         "with the limiter)";
+                return 1;
+            }
+            std::vector<double> nxk((size_t)3 * h->Kp, 0.0), nyk((size_t)3 * h->Kp, 0.0);
+            for (int le = 0; le < 3; le++)
+                for (int k = 0; k < h->K; k++) {
+                    nxk[(size_t)le * h->Kp + k] = FaceNormX[(size_t)le * h->hostPitch + h->hostOff + k];
+                    nyk[(size_t)le * h->Kp + k] = FaceNormY[(size_t)le * h->hostPitch + h->hostOff + k];
+                }
+            if (int rc = dev_upload(h, &h->nxkPlot, nxk)) return rc;
+            if (int rc = dev_upload(h, &h->nykPlot, nyk)) return rc;
+        }
+    }
+    h->captureEdgeQ = true;
+    return 0;
+}
+
+extern "C" int dfr2d_gradient_field(dfr2d_handle *h, int flow_function, double *out) {
+    if (!h || !out) return 1;
+    const bool isX = flow_function >= 200 && flow_function <= 203, isY = flow_function >= 300 && flow_function <= 303;
+    if (!isX && !isY) { h->err = "dfr2d_gradient_field: flow_function must be 200..203 (XGradient*) or 300..303 (YGradient*)"; return 1; }
+    if (!h->qfaceSaved || !h->nxkPlot) {
+        h->err = "dfr2d_gradient_field: the edge values of the last stage are not kept by default; call "
+                 "dfr2d_capture_edge_values(h, 1, ...) before the step whose fields are plotted";
+        return 1;
+    }
+    if (!h->haveDiv) { h->err = "dfr2d_gradient_field: dfr2d_problem.Div (DFR.FluxElement.Div) was not given at create"; return 1; }
+    CK(cudaSetDevice(h->device));
+    if (int rc = ensure_ops(h)) return rc;
+    const size_t n = (size_t)h->NpFlux * std::max(h->K, 1);
+    if (int rc = scratch_reserve(h, 2 * n * sizeof(double))) return rc;
+    GradPlotArgs a{};
+    a.K = h->K; a.Kp = h->Kp; a.var = flow_function % 100;
+    a.q = h->q[0]; a.qfaceSaved = h->qfaceSaved;
+    a.etoe = h->etoe; a.ekL = h->ekL; a.emeta = h->emeta;
+    a.Jdet = h->Jdet; a.Jinv = h->Jinv; a.IInII = h->IInII; a.nxk = h->nxkPlot; a.nyk = h->nykPlot;
+    a.gradX = (double *)h->scratch; a.gradY = a.gradX + n;
+    if (h->K > 0) {
+        DISPATCH_N(h->N, (k_grad_plot<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(a)));
+        if (int rc = launch_check(h, "k_grad_plot")) return rc;
+    }
+    CK(cudaMemcpy2DAsync(out + h->hostOff, (size_t)h->hostPitch * sizeof(double), isX ? a.gradX : a.gradY, (size_t)h->K * sizeof(double),
                          (size_t)h->K * sizeof(double), (size_t)h->NpFlux, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;

@@ -572,6 +572,81 @@ __global__ void k_epsilon_field(int K, int Kp, int c0, const double *epsk, const
     }
 }
 
+// ---- gradient plot fields (plot.go:54-77): XGradient* / YGradient* = GetSolutionGradientUsingRTElement(-1, n, c.Q, ...) ----
+// The reference evaluates them from the CURRENT c.Q at the interior RT points and from the EdgeQValues store at the edge
+// points -- the owner side's Q_Face of the last CalculateEdgeEulerFlux, i.e. of the input of stage 5 of the last step.
+// Kernel 5 of that stage overwrites Q_Face with the next stage's interpolation, so a host that wants these fields turns
+// the capture on (dfr2d_capture_edge_values) and this copy runs between the edge phase and the update of every stage 5.
+// It honours the step predicate: a step issued after the run has finished must leave the store alone.
+__global__ void __launch_bounds__(256) k_capture_qface(size_t n2, const double2 *src, double2 *dst, const DevScalars *sc, Phys ph, int par,
+                                                       long long stepIndex) {
+    if (step_is_noop(sc, ph, par, stepIndex)) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+struct GradPlotArgs {
+    int K, Kp, var;
+    const double *q;                   // c.Q
+    const double *qfaceSaved;          // [4][3NpEdge][Kp] captured Q_Face (own + ghost columns)
+    const int *etoe, *ekL, *emeta;
+    const double *Jdet, *Jinv, *IInII, *nxk, *nyk;
+    double *gradX, *gradY;             // [NpFlux][K]
+};
+
+// One thread per element and all NpFlux rows: DOF_j = metric_j U_j (CalculateRTBasedDerivativeMetrics,
+// DG2D/dfr_startup.go:213-254), Grad = Div . DOF (raviart_thomas_element.go:249-297).  A read-back utility that runs once
+// per plotted field, not a stage kernel: the operator comes straight from constant memory (warp-uniform index).
+template <int N>
+__global__ void __launch_bounds__(128) k_grad_plot(GradPlotArgs a) {
+    constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.K) return;
+    const Ops<N> &op = ops<N>();
+    const size_t Kp = a.Kp;
+    const int n = a.var;
+    double dx[NF], dy[NF];
+    const double j0 = a.Jinv[0 * Kp + k], j1 = a.Jinv[1 * Kp + k], j2 = a.Jinv[2 * Kp + k], j3 = a.Jinv[3 * Kp + k];
+#pragma unroll
+    for (int i = 0; i < NI; i++) {
+        const double u = a.q[((size_t)n * NI + i) * Kp + k];
+        dx[i] = j0 * u; dy[i] = j1 * u;
+        dx[NI + i] = j2 * u; dy[NI + i] = j3 * u;
+    }
+    const double oojd = 1.0 / a.Jdet[k];
+    const size_t qplane = (size_t)NF3 * Kp;
+#pragma unroll
+    for (int le = 0; le < 3; le++) {
+        const double iin = a.IInII[(size_t)le * Kp + k];
+        const double mx = oojd * a.nxk[(size_t)le * Kp + k] * iin, my = oojd * a.nyk[(size_t)le * Kp + k] * iin;
+        const int s = a.etoe[(size_t)le * Kp + k];
+        int col = k, row0 = le * NEd, dir = 1;
+        if (s < 0) {                    // neighbour: the owner's values in reversed order (euler.go:896-912)
+            const int slot = -1 - s;
+            col = a.ekL[slot];
+            row0 = (a.emeta[slot] & 3) * NEd + NEd - 1;
+            dir = -1;
+        }
+#pragma unroll
+        for (int i = 0; i < NEd; i++) {
+            const double u = a.qfaceSaved[n * qplane + (size_t)(row0 + dir * i) * Kp + col];
+            dx[2 * NI + le * NEd + i] = mx * u;
+            dy[2 * NI + le * NEd + i] = my * u;
+        }
+    }
+#pragma unroll 1
+    for (int r = 0; r < NF; r++) {
+        double gx = 0.0, gy = 0.0;
+#pragma unroll
+        for (int j = 0; j < NF; j++) {
+            const double d = op.Div[r][j];
+            gx = fma(d, dx[j], gx);
+            gy = fma(d, dy[j], gy);
+        }
+        a.gradX[(size_t)r * a.K + k] = gx;
+        a.gradY[(size_t)r * a.K + k] = gy;
+    }
+}
+
 template <int N> static size_t elem_smem_diss() { return (size_t)12 * Dim<N>::NpInt * kElemsPerBlock * sizeof(double); }
 
 }  // namespace dfr2d

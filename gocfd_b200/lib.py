@@ -54,6 +54,7 @@ EXPORTS = [
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
     "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_create_window", "dfr2d_plan_create_window", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
+    "dfr2d_capture_edge_values", "dfr2d_gradient_field",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -120,6 +121,8 @@ def load():
     lib.dfr2d_multi_get_state.argtypes = [C.POINTER(H), C.c_int, _dp]
     lib.dfr2d_set_clock.argtypes = [H, C.c_double, C.c_int64]
     lib.dfr2d_epsilon_field.argtypes = [H, C.c_int, _dp]
+    lib.dfr2d_capture_edge_values.argtypes = [H, C.c_int, _dp, _dp]
+    lib.dfr2d_gradient_field.argtypes = [H, C.c_int, _dp]
     lib.dfr2d_multi_step_profile.argtypes = [C.POINTER(H), C.c_int, C.POINTER(C.c_float)]
     lib.dfr2d_grad_mma_table.argtypes = [C.c_int, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_grad_mma_table.restype = C.c_int64
@@ -361,6 +364,22 @@ class Dfr2d:
         if out is None:
             out = np.zeros((self.p.NpFlux, self.p.K))
         self._ck(self.lib.dfr2d_epsilon_field(self.h, int(bool(c0)), _d(out)))
+        return out
+
+    def capture_edge_values(self, on=True):
+        """Keep the EdgeQValues store (Q_Face of every step's last stage) for the gradient plot fields."""
+        if on and not self.p.Dissipation:
+            nx = np.ascontiguousarray(self.p.FaceNormX, dtype=np.float64)
+            ny = np.ascontiguousarray(self.p.FaceNormY, dtype=np.float64)
+            self._ck(self.lib.dfr2d_capture_edge_values(self.h, 1, _d(nx), _d(ny)))
+        else:
+            self._ck(self.lib.dfr2d_capture_edge_values(self.h, int(bool(on)), None, None))
+
+    def gradient_field(self, flow_function, out=None):
+        """XGradient* (200..203) / YGradient* (300..303) plot fields (plot.go:54-77): [NpFlux, K] float64."""
+        if out is None:
+            out = np.zeros((self.p.NpFlux, self.p.K))
+        self._ck(self.lib.dfr2d_gradient_field(self.h, int(flow_function), _d(out)))
         return out
 
     # ---- multi-partition plumbing -------------------------------------------------------

@@ -183,6 +183,20 @@ int dfr2d_plot_field(dfr2d_handle *h, int flow_function, const double *graph_int
  * (dissipation.go:377-390); c0 = 1: EpsilonDissipationC0 = Bary . vertex epsilon as the last stage left it (:392-395). */
 int dfr2d_epsilon_field(dfr2d_handle *h, int c0, double *out);
 
+/* The remaining GetPlotField cases (plot.go:54-77; fluids.go:227-234): flow_function 200..203 = XGradientDensity ..
+ * XGradientEnergy, 300..303 = YGradient*: GetSolutionGradientUsingRTElement(-1, n, c.Q, ...) (euler.go:864-918) -- the RT
+ * gradient of conserved variable n = flow_function % 100 of the CURRENT c.Q at the interior RT points and of the
+ * EdgeQValues store at the edge points, Div . (DXMetric|DYMetric (.) U), not interpolated: out = [NpFlux x K] doubles,
+ * global column index, own columns written.  The store holds the owner side's Q_Face of the last stage that ran
+ * (edges.go:344-350: the input of stage 5 of the last step; zeros before the first step).  The device reuses Q_Face for
+ * the next stage, so these values are kept only on request: dfr2d_capture_edge_values(h, 1, ...) makes every following
+ * step copy Q_Face (own and ghost columns) aside before its last update, at the cost of one device copy per step; turn it
+ * on before the step whose fields are plotted and off again afterwards (on = 0 keeps what was captured).  FaceNormX/Y =
+ * DFR.FaceNorm[0|1] exactly as the problem struct given at create carried them; they are read once, and may be
+ * NULL on a handle with the limiter (which keeps them already).  Needs dfr2d_problem.Div. */
+int dfr2d_capture_edge_values(dfr2d_handle *h, int on, const double *FaceNormX, const double *FaceNormY);
+int dfr2d_gradient_field(dfr2d_handle *h, int flow_function, double *out);
+
 /* ---- plumbing for one-process-per-GPU hosts (torch.distributed / NCCL) ---------------------
  * The library never calls a collective itself: per stage the host moves the halo bytes and
  * max-reduces two doubles, between the three phases below.  Single-partition users only need

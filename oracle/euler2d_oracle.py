@@ -371,6 +371,18 @@ class OracleSolver:
         self.nyL = p.FaceNormY[p.edge_numL, p.edge_kL]
         self.bp_of_edge = np.full(self.NE, -1, dtype=np.int64)
         self.bp_of_edge[p.bp_edge] = np.arange(p.NBP)
+        # DXMetric / DYMetric (CalculateRTBasedDerivativeMetrics, DG2D/dfr_startup.go:213-254): built by NewDFR2D for every
+        # run -- the PerssonC0 limiter and the gradient plot fields (plot.go:54-77) both use them
+        ne = self.NpEdge
+        self.DXMetric = np.empty((self.NpFlux, k))
+        self.DYMetric = np.empty((self.NpFlux, k))
+        self.DXMetric[:ni], self.DXMetric[ni:2 * ni] = p.Jinv[:, 0], p.Jinv[:, 2]
+        self.DYMetric[:ni], self.DYMetric[ni:2 * ni] = p.Jinv[:, 1], p.Jinv[:, 3]
+        oojd = 1.0 / p.Jdet
+        for fn in range(3):
+            rows = slice(2 * ni + fn * ne, 2 * ni + (fn + 1) * ne)
+            self.DXMetric[rows] = oojd * p.FaceNormX[fn] * p.IInII[fn]
+            self.DYMetric[rows] = oojd * p.FaceNormY[fn] * p.IInII[fn]
         if p.Dissipation:
             self.sd_kappa = p.Kappa if p.Kappa != 0.0 else 5.0      # dissipation.go:140-147
             self.Eps0 = 5.0 / 1.5
@@ -383,17 +395,6 @@ class OracleSolver:
             self.Se = np.zeros(k)
             self.DissX = np.zeros((4, self.NpFlux, k))
             self.DissY = np.zeros((4, self.NpFlux, k))
-            # DXMetric / DYMetric (DG2D/dfr_startup.go:213-254)
-            ne = self.NpEdge
-            self.DXMetric = np.empty((self.NpFlux, k))
-            self.DYMetric = np.empty((self.NpFlux, k))
-            self.DXMetric[:ni], self.DXMetric[ni:2 * ni] = p.Jinv[:, 0], p.Jinv[:, 2]
-            self.DYMetric[:ni], self.DYMetric[ni:2 * ni] = p.Jinv[:, 1], p.Jinv[:, 3]
-            oojd = 1.0 / p.Jdet
-            for fn in range(3):
-                rows = slice(2 * ni + fn * ne, 2 * ni + (fn + 1) * ne)
-                self.DXMetric[rows] = oojd * p.FaceNormX[fn] * p.IInII[fn]
-                self.DYMetric[rows] = oojd * p.FaceNormY[fn] * p.IInII[fn]
 
     # ---- state I/O -----------------------------------------------------------------
     def set_state(self, q):
@@ -530,23 +531,38 @@ class OracleSolver:
             self.Aggregates[:, 1] = (oohk * oohk * eps).max(axis=1)
 
     def calculate_epsilon_gradient(self, q):
+        for n in range(4):
+            gx, gy = self.solution_gradient_rt(n, q)
+            self.DissX[n] = gx * self.Epsilon
+            self.DissY[n] = gy * self.Epsilon
+
+    def solution_gradient_rt(self, n, q):
+        """GetSolutionGradientUsingRTElement (euler.go:864-918) for conserved variable n: interior rows from q, edge rows
+        from the EdgeQValues store (owner side of the last CalculateEdgeEulerFlux, reversed for the neighbour), times
+        DXMetric / DYMetric, then the RT divergence.  Returns GradX, GradY [NpFlux, K]."""
         p = self.p
         ni, ne = self.NpInt, self.NpEdge
         eq = self.EdgeFlux[1]
-        for n in range(4):
-            un = np.empty((self.NpFlux, self.K))
-            un[:ni] = q[n]
-            un[ni:2 * ni] = q[n]
-            for e in range(3):
-                ei = p.EtoEdge[:, e]
-                owner = p.edge_kL[ei] == np.arange(self.K)
-                vals = eq[n][ei]                                   # [K, NpEdge] in owner order
-                vals = np.where(owner[:, None], vals, vals[:, ::-1])
-                un[2 * ni + e * ne:2 * ni + (e + 1) * ne] = vals.T
-            gx = p.Div @ (self.DXMetric * un)
-            gy = p.Div @ (self.DYMetric * un)
-            self.DissX[n] = gx * self.Epsilon
-            self.DissY[n] = gy * self.Epsilon
+        un = np.empty((self.NpFlux, self.K))
+        un[:ni] = q[n]
+        un[ni:2 * ni] = q[n]
+        for e in range(3):
+            ei = p.EtoEdge[:, e]
+            owner = p.edge_kL[ei] == np.arange(self.K)
+            vals = eq[n][ei]                                   # [K, NpEdge] in owner order
+            vals = np.where(owner[:, None], vals, vals[:, ::-1])
+            un[2 * ni + e * ne:2 * ni + (e + 1) * ne] = vals.T
+        return p.Div @ (self.DXMetric * un), p.Div @ (self.DYMetric * un)
+
+    def gradient_plot_field(self, pf):
+        """GetPlotField for XGradientDensity..YGradientEnergy (plot.go:54-77; fluids.go:227-234: 200+n = R direction,
+        300+n = S direction): the RT gradient of variable n of the CURRENT c.Q with the edge values the store holds from
+        the last stage that ran (the input of stage 5 of the last step; zeros before the first step) -- not interpolated,
+        [NpFlux, K] doubles."""
+        if not (200 <= pf <= 203 or 300 <= pf <= 303):
+            raise ValueError("not a gradient plot field: %d" % pf)
+        gx, gy = self.solution_gradient_rt(pf % 100, self.Q[0])
+        return gx if pf < 300 else gy
 
     def store_edge_viscous_flux(self):
         p = self.p
