@@ -94,13 +94,16 @@ def test_windowed_partitions_run_bitwise_like_the_global_problem(diss):
         c.Q[0] *= 1.0 + 0.1 * np.sign(np.sin(7.0 * c.DFR.solution_xy()[0]))      # jumps inside elements: the sensor fires
     one = lib.Dfr2d(c.problem)
     one.set_state(c.Q)
+    one.capture_edge_values(True)
     a = one.step(4)
     want = one.get_state()
+    want_grad = {pf: one.gradient_field(pf) for pf in (201, 303)}
     devs, wins = [], []
     for part in range(3):
         pw, win = window_problem(c.problem, 3, part)
         d = lib.Dfr2d(pw, n_parts=3, part=part, window=win)
         d.set_state(np.ascontiguousarray(c.Q[:, :, win[1]:win[1] + pw.K]))
+        d.capture_edge_values(True)                       # FaceNorm in window columns, like every other problem array
         devs.append(d)
         wins.append((win[1], pw.K))
     b = lib.multi_step(devs, 4)
@@ -112,6 +115,8 @@ def test_windowed_partitions_run_bitwise_like_the_global_problem(diss):
         got[:, :, k0:k1] = q[:, :, k0 - off:k1 - off]
         dt_w = d.get_field(0)
         np.testing.assert_array_equal(dt_w[k0 - off:k1 - off], one.get_field(0)[k0:k1])
+        for pf, g in want_grad.items():                   # gradient plot fields: the neighbour side reads captured ghost columns
+            np.testing.assert_array_equal(d.gradient_field(pf)[:, k0 - off:k1 - off], g[:, k0:k1])
     assert np.array_equal(got, want)
     for d in devs + [one]:
         d.close()
