@@ -249,3 +249,13 @@ def test_multi_step_rejects_bad_requests_without_touching_cuda():
     assert L.dfr2d_multi_step(arr, 0, 1, None) == 1
     assert L.dfr2d_multi_step(arr, 33, 1, None) == 1
     assert L.dfr2d_multi_step(arr, 2, 1, None) == 1      # null handles
+
+
+def test_makefile_builds_with_the_flags_of_the_build_entry():
+    """gocfd_b200/csrc/Makefile (the Python-free build a Go tree uses) carries exactly the nvcc flags of
+    __graft_entry__.build(): sm_100a only, -lineinfo."""
+    import __graft_entry__ as g
+    mk = open(os.path.join(ROOT, "gocfd_b200", "csrc", "Makefile")).read()
+    flags = re.search(r"^NVCCFLAGS := (.*)$", mk, re.M).group(1).split()
+    assert flags == g.NVCC_FLAGS
+    assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags
