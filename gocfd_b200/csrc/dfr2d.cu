@@ -2020,18 +2020,18 @@ extern "C" int dfr2d_gradient_field(dfr2d_handle *h, int flow_function, double *
     CK(cudaSetDevice(h->device));
     if (int rc = ensure_ops(h)) return rc;
     const size_t n = (size_t)h->NpFlux * std::max(h->K, 1);
-    if (int rc = scratch_reserve(h, 2 * n * sizeof(double))) return rc;
+    if (int rc = scratch_reserve(h, n * sizeof(double))) return rc;
     GradPlotArgs a{};
-    a.K = h->K; a.Kp = h->Kp; a.var = flow_function % 100;
+    a.K = h->K; a.Kp = h->Kp; a.var = flow_function % 100; a.dirY = isY ? 1 : 0;
     a.q = h->q[0]; a.qfaceSaved = h->qfaceSaved;
     a.etoe = h->etoe; a.ekL = h->ekL; a.emeta = h->emeta;
-    a.Jdet = h->Jdet; a.Jinv = h->Jinv; a.IInII = h->IInII; a.nxk = h->nxkPlot; a.nyk = h->nykPlot;
-    a.gradX = (double *)h->scratch; a.gradY = a.gradX + n;
+    a.Jdet = h->Jdet; a.Jinv = h->Jinv; a.IInII = h->IInII; a.nk = isY ? h->nykPlot : h->nxkPlot;
+    a.grad = (double *)h->scratch;
     if (h->K > 0) {
         DISPATCH_N(h->N, (k_grad_plot<NN><<<(h->K + 127) / 128, 128, 0, h->stream>>>(a)));
         if (int rc = launch_check(h, "k_grad_plot")) return rc;
     }
-    CK(cudaMemcpy2DAsync(out + h->hostOff, (size_t)h->hostPitch * sizeof(double), isX ? a.gradX : a.gradY, (size_t)h->K * sizeof(double),
+    CK(cudaMemcpy2DAsync(out + h->hostOff, (size_t)h->hostPitch * sizeof(double), a.grad, (size_t)h->K * sizeof(double),
                          (size_t)h->K * sizeof(double), (size_t)h->NpFlux, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;

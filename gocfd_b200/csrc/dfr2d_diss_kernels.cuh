@@ -585,17 +585,18 @@ __global__ void __launch_bounds__(256) k_capture_qface(size_t n2, const double2 
 }
 
 struct GradPlotArgs {
-    int K, Kp, var;
+    int K, Kp, var, dirY;              // dirY = 0: GradX (DXMetric), 1: GradY (DYMetric)
     const double *q;                   // c.Q
     const double *qfaceSaved;          // [4][3NpEdge][Kp] captured Q_Face (own + ghost columns)
     const int *etoe, *ekL, *emeta;
-    const double *Jdet, *Jinv, *IInII, *nxk, *nyk;
-    double *gradX, *gradY;             // [NpFlux][K]
+    const double *Jdet, *Jinv, *IInII, *nk;   // nk = the element normals' x (dirY = 0) or y (dirY = 1) component, [3][Kp]
+    double *grad;                      // [NpFlux][K]
 };
 
-// One thread per element and all NpFlux rows: DOF_j = metric_j U_j (CalculateRTBasedDerivativeMetrics,
-// DG2D/dfr_startup.go:213-254), Grad = Div . DOF (raviart_thomas_element.go:249-297).  A read-back utility that runs once
-// per plotted field, not a stage kernel: the operator comes straight from constant memory (warp-uniform index).
+// One thread per element and all NpFlux rows of the requested direction: DOF_j = metric_j U_j
+// (CalculateRTBasedDerivativeMetrics, DG2D/dfr_startup.go:213-254), Grad = Div . DOF (raviart_thomas_element.go:249-297).
+// A read-back utility that runs once per plotted field, not a stage kernel: the operator comes straight from constant
+// memory (warp-uniform index).
 template <int N>
 __global__ void __launch_bounds__(128) k_grad_plot(GradPlotArgs a) {
     constexpr int NI = Dim<N>::NpInt, NEd = Dim<N>::NpEdge, NF = Dim<N>::NpFlux, NF3 = Dim<N>::NF3;
@@ -604,20 +605,20 @@ __global__ void __launch_bounds__(128) k_grad_plot(GradPlotArgs a) {
     const Ops<N> &op = ops<N>();
     const size_t Kp = a.Kp;
     const int n = a.var;
-    double dx[NF], dy[NF];
-    const double j0 = a.Jinv[0 * Kp + k], j1 = a.Jinv[1 * Kp + k], j2 = a.Jinv[2 * Kp + k], j3 = a.Jinv[3 * Kp + k];
+    double dof[NF];
+    // DXMetric rows: {rx, sx} = Jinv[0], Jinv[2]; DYMetric rows: {ry, sy} = Jinv[1], Jinv[3]
+    const double ja = a.Jinv[(size_t)(a.dirY ? 1 : 0) * Kp + k], jb = a.Jinv[(size_t)(a.dirY ? 3 : 2) * Kp + k];
 #pragma unroll
     for (int i = 0; i < NI; i++) {
         const double u = a.q[((size_t)n * NI + i) * Kp + k];
-        dx[i] = j0 * u; dy[i] = j1 * u;
-        dx[NI + i] = j2 * u; dy[NI + i] = j3 * u;
+        dof[i] = ja * u;
+        dof[NI + i] = jb * u;
     }
     const double oojd = 1.0 / a.Jdet[k];
     const size_t qplane = (size_t)NF3 * Kp;
 #pragma unroll
     for (int le = 0; le < 3; le++) {
-        const double iin = a.IInII[(size_t)le * Kp + k];
-        const double mx = oojd * a.nxk[(size_t)le * Kp + k] * iin, my = oojd * a.nyk[(size_t)le * Kp + k] * iin;
+        const double m = oojd * a.nk[(size_t)le * Kp + k] * a.IInII[(size_t)le * Kp + k];
         const int s = a.etoe[(size_t)le * Kp + k];
         int col = k, row0 = le * NEd, dir = 1;
         if (s < 0) {                    // neighbour: the owner's values in reversed order (euler.go:896-912)
@@ -627,23 +628,15 @@ __global__ void __launch_bounds__(128) k_grad_plot(GradPlotArgs a) {
             dir = -1;
         }
 #pragma unroll
-        for (int i = 0; i < NEd; i++) {
-            const double u = a.qfaceSaved[n * qplane + (size_t)(row0 + dir * i) * Kp + col];
-            dx[2 * NI + le * NEd + i] = mx * u;
-            dy[2 * NI + le * NEd + i] = my * u;
-        }
+        for (int i = 0; i < NEd; i++)
+            dof[2 * NI + le * NEd + i] = m * a.qfaceSaved[n * qplane + (size_t)(row0 + dir * i) * Kp + col];
     }
 #pragma unroll 1
     for (int r = 0; r < NF; r++) {
-        double gx = 0.0, gy = 0.0;
+        double g = 0.0;
 #pragma unroll
-        for (int j = 0; j < NF; j++) {
-            const double d = op.Div[r][j];
-            gx = fma(d, dx[j], gx);
-            gy = fma(d, dy[j], gy);
-        }
-        a.gradX[(size_t)r * a.K + k] = gx;
-        a.gradY[(size_t)r * a.K + k] = gy;
+        for (int j = 0; j < NF; j++) g = fma(op.Div[r][j], dof[j], g);
+        a.grad[(size_t)r * a.K + k] = g;
     }
 }
 
