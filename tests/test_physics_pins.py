@@ -11,6 +11,8 @@ by what they must equal mathematically or physically -- independent of the Go so
     high order (error ratio between two meshes), for N = 1..4;
   * the five-stage combination of rkAdvance (euler.go:511-563) is fourth-order accurate on a nonlinear ODE and has the
     stability polynomial of the Spiteri-Ruuth SSPRK(5,4) scheme;
+  * the time step is the CFL condition: CFL x hK / (|V| + c) globally and per element on a uniform stream;
+  * the modal sensor: exactly Persson & Peraire's energy ratio at N = 1; blind to everything below the top modes at any N;
   * WallBC (bcs.go:11-23): a gas at rest inside solid walls stays at rest, and a centred pressure pulse in a walled box
     stays mirror symmetric;
   * the PerssonC0 path carries a Sod shock to t = 0.1 and lands on the exact Riemann solution (centre-line samples of
@@ -293,3 +295,74 @@ def test_wall_reflects_a_normal_pressure_pulse_symmetrically():
     assert abs(mass_l - mass_r) < 2e-3 * abs(mass_l)
     assert abs(mom_l + mom_r) < 2e-2 * max(abs(mom_l), abs(mom_r)) and abs(mom_l) > 1e-4
     assert mom_l < 0 < mom_r                                   # the pulse pushes gas outwards on both sides
+
+
+# ---- the time step is a CFL number (euler.go:945-1002, edges.go:246-289) ---------------------------------------------
+def test_global_and_local_dt_are_the_cfl_condition_on_a_uniform_stream():
+    """With a uniform stream the wave speed |V| + c is the same number everywhere, so the time step must be
+    CFL x (length scale) / (|V| + c) with the length scale hK = EdgeLenMax / (N+1)^2 (the reference's choice,
+    DG2D/dfr_startup.go:125-147): globally the smallest hK of the mesh, locally the smallest hK among an element and the
+    owners of its three edges."""
+    from oracle.euler2d_oracle import OracleSolver
+    for local, cfl, n in ((False, 0.7, 2), (True, 1.3, 1)):
+        c = Euler(InputParameters2D(CFL=cfl, FluxType="Roe", InitType="Freestream", PolynomialOrder=n, FinalTime=100.0,
+                                    MaxIterations=10, Gamma=1.4, Minf=0.5, Alpha=3.0, LocalTimeStepping=local),
+                  mesh_path("mesh_NACA0012_inv.su2"))
+        p = c.problem
+        o = OracleSolver(p)
+        o.set_state(c.Q)
+        rho, ru, rv, e = (c.Q[v][0, 0] for v in range(4))
+        pr = (G - 1) * (e - 0.5 * (ru * ru + rv * rv) / rho)
+        wave = np.hypot(ru, rv) / rho + np.sqrt(G * pr / rho)
+        hk = p.EdgeLenMax / float((n + 1) ** 2)
+        o.stage(0)                                          # stage 1 computes dt from the (uniform) input state
+        if not local:
+            assert o.GlobalDT == pytest.approx(cfl * hk.min() / wave, rel=1e-12)
+        else:
+            h_adj = np.minimum.reduce([hk[p.edge_kL[p.EtoEdge[:, e]]] for e in range(3)])
+            np.testing.assert_allclose(o.DT, cfl * h_adj / wave, rtol=1e-12)
+            assert o.DT.max() / o.DT.min() > 50             # a real spread of cell sizes (airfoil surface vs far field)
+
+
+# ---- the modal sensor (UpdateSeMoment, dissipation.go:455-488; ModeAliasShockFinder, DG2D/dfr_shock_capturing.go:70-105) --
+def _sensor_case(n):
+    from oracle.euler2d_oracle import OracleSolver
+    c = Euler(InputParameters2D(CFL=1.0, FluxType="Roe", InitType="shocktube", PolynomialOrder=n, FinalTime=0.2, MaxIterations=10,
+                                Gamma=1.4, Limiter="persson c0", Kappa=5.0), mesh_path("sod-aligned-100pts.su2"))
+    return c, OracleSolver(c.problem)
+
+
+def test_sensor_is_the_persson_peraire_energy_ratio_at_n1():
+    """At N = 1 the WSJ cubature integrates the products of basis functions exactly, the reference's `MassMatrix` is the
+    identity in modal space, and Se is exactly log10(energy in the linear modes / total modal energy) -- the definition of
+    Persson & Peraire's indicator, evaluated here from the modal coefficients alone."""
+    c, o = _sensor_case(1)
+    p = c.problem
+    rho = 1.0 + 0.3 * np.random.default_rng(1).random((p.NpInt, p.K))
+    o.update_se_moment(rho)
+    uh = p.Vinv @ rho
+    top = np.array(c.DFR.SolutionElement.JB2D.OrderAtJ) == 1
+    np.testing.assert_allclose(o.Se, np.log10((uh[top] ** 2).sum(axis=0) / (uh ** 2).sum(axis=0)), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_sensor_sees_only_the_top_modes(n):
+    """For any order: a density that is a polynomial of degree N-1 inside every element has no top-mode content, so the
+    numerator vanishes (Se at round-off level, far below the ramp: sigma = 0); adding a top-order mode of relative size
+    0.1 lifts Se to about log10(0.01) = -2, inside the ramp [S0 - Kappa, S0 + Kappa] of the limiter."""
+    c, o = _sensor_case(n)
+    p = c.problem
+    orders = np.array(c.DFR.SolutionElement.JB2D.OrderAtJ)
+    rng = np.random.default_rng(n)
+    uh = np.zeros((p.NpInt, p.K))
+    uh[0] = 3.0
+    uh[(orders > 0) & (orders < n)] = 0.2 * rng.standard_normal(((orders > 0) & (orders < n)).sum())[:, None]
+    with np.errstate(all="ignore"):
+        o.update_se_moment(p.V @ uh)
+        o.update_shock_finder_sigma()
+    assert np.nan_to_num(o.Se, nan=-99.0, neginf=-99.0).max() < -20 and o.SigmaScalar.max() == 0.0
+    uh[orders == n] = 0.3 / np.sqrt((orders == n).sum())
+    o.update_se_moment(p.V @ uh)
+    o.update_shock_finder_sigma()
+    assert np.all((o.Se > -2.6) & (o.Se < -1.4))
+    assert np.all((o.SigmaScalar > 0.0) & (o.SigmaScalar < 1.0))
