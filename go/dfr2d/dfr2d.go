@@ -312,14 +312,8 @@ func (m *MultiSolver) GetState(c *Euler2D.Euler) {
 
 // Residual is the per-variable signed max over all partitions (PrintUpdate's loop over np, euler.go:823-829).
 func (m *MultiSolver) Residual() (r [4]float64) {
-	for g, s := range m.Parts {
-		rg := s.Residual()
-		for n := 0; n < 4; n++ {
-			if g == 0 || rg[n] > r[n] {
-				r[n] = rg[n]
-			}
-		}
-	}
+	hs := m.handles()
+	m.Parts[0].check(C.dfr2d_multi_residual(&hs[0], C.int(len(hs)), (*C.double)(unsafe.Pointer(&r[0]))), "dfr2d_multi_residual")
 	return
 }
 

@@ -1769,6 +1769,46 @@ static int multi_step_impl(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info
     return rc;
 }
 
+// SURVEY.md 8(b)'s shape of the boundary -- one create for the whole run, the fan-out over GPUs inside the library:
+// hs_out[g] = partition g of n_parts on devices[g] (NULL: g modulo the number of visible devices).
+extern "C" int dfr2d_multi_create(const dfr2d_problem *p, int n_parts, const int *devices, dfr2d_handle **hs_out) {
+    if (!p || !hs_out || n_parts < 1 || n_parts > kMaxParts) { g_create_error = "dfr2d_multi_create: bad arguments"; return 1; }
+    int ndev = 0;
+    if (!devices) {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev < 1) {
+            g_create_error = std::string("dfr2d_multi_create: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "no CUDA device");
+            return 2;
+        }
+    }
+    for (int g = 0; g < n_parts; g++) hs_out[g] = nullptr;
+    for (int g = 0; g < n_parts; g++) {
+        int rc = dfr2d_create(p, n_parts, g, devices ? devices[g] : g % ndev, &hs_out[g]);
+        if (rc) {
+            for (int j = 0; j < g; j++) { dfr2d_destroy(hs_out[j]); hs_out[j] = nullptr; }
+            return rc;
+        }
+    }
+    return 0;
+}
+
+extern "C" void dfr2d_multi_destroy(dfr2d_handle **hs, int n) {
+    if (!hs) return;
+    for (int g = 0; g < n; g++) { dfr2d_destroy(hs[g]); hs[g] = nullptr; }
+}
+
+// PrintUpdate's loop over the partitions (euler.go:823-829) without its clamp at zero: the signed maximum per variable
+extern "C" int dfr2d_multi_residual(dfr2d_handle **hs, int n, double maxR[4]) {
+    if (!hs || n < 1 || !maxR) return 1;
+    for (int g = 0; g < n; g++) {
+        double r[4];
+        if (int rc = dfr2d_residual(hs[g], r)) return rc;
+        for (int v = 0; v < 4; v++)
+            if (g == 0 || r[v] > maxR[v]) maxR[v] = r[v];
+    }
+    return 0;
+}
+
 extern "C" int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info) {
     return multi_step_impl(hs, n, nsteps, info, nullptr);
 }

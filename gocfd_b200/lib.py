@@ -54,7 +54,7 @@ EXPORTS = [
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
     "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_create_window", "dfr2d_plan_create_window", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
-    "dfr2d_capture_edge_values", "dfr2d_gradient_field",
+    "dfr2d_capture_edge_values", "dfr2d_gradient_field", "dfr2d_multi_create", "dfr2d_multi_destroy", "dfr2d_multi_residual",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -118,6 +118,10 @@ def load():
     lib.dfr2d_stage_wave.argtypes = [H, C.c_int]
     lib.dfr2d_peer_enable.argtypes = [H, C.c_int]
     lib.dfr2d_multi_set_state.argtypes = [C.POINTER(H), C.c_int, _dp]
+    lib.dfr2d_multi_create.argtypes = [C.POINTER(ProblemStruct), C.c_int, _ip, C.POINTER(H)]
+    lib.dfr2d_multi_destroy.argtypes = [C.POINTER(H), C.c_int]
+    lib.dfr2d_multi_destroy.restype = None
+    lib.dfr2d_multi_residual.argtypes = [C.POINTER(H), C.c_int, _dp]
     lib.dfr2d_multi_get_state.argtypes = [C.POINTER(H), C.c_int, _dp]
     lib.dfr2d_set_clock.argtypes = [H, C.c_double, C.c_int64]
     lib.dfr2d_epsilon_field.argtypes = [H, C.c_int, _dp]

@@ -18,8 +18,8 @@
  *
  * usage: solve_host <pack> <out> <nsteps> [n_parts [n_devices [migrate]]]
  *   n_parts = 1 : dfr2d_create / dfr2d_set_state / nsteps x dfr2d_step(1) / dfr2d_residual / dfr2d_get_state
- *   n_parts > 1 : the MultiSolver sequence (dfr2d_multi_set_state / dfr2d_multi_step / dfr2d_multi_get_state), partition g
- *                 on device g % n_devices
+ *   n_parts > 1 : the MultiSolver sequence (dfr2d_multi_create / dfr2d_multi_set_state / dfr2d_multi_step /
+ *                 dfr2d_multi_residual / dfr2d_multi_get_state / dfr2d_multi_destroy), partition g on device g % n_devices
  *   migrate = 1 : every step call is made from a freshly created OS thread -- a goroutine that is not locked to its
  *                 thread (no runtime.LockOSThread) migrates between OS threads from one cgo call to the next, so the
  *                 library must select its device inside every entry point (SURVEY.md 8b "Threading")
@@ -121,8 +121,14 @@ int main(int argc, char **argv) {
     if (qbytes != 4 * NpInt * p.K * (int64_t)sizeof(double)) die("state block has the wrong size", NULL);
 
     dfr2d_handle **hs = (dfr2d_handle **)calloc((size_t)n_parts, sizeof *hs);
-    for (int g = 0; g < n_parts; g++)
-        if (dfr2d_create(&p, n_parts, g, g % n_devices, &hs[g])) die("dfr2d_create", dfr2d_last_error(NULL));
+    if (n_parts == 1) {
+        if (dfr2d_create(&p, 1, 0, 0, &hs[0])) die("dfr2d_create", dfr2d_last_error(NULL));
+    } else {
+        int *devices = (int *)malloc((size_t)n_parts * sizeof *devices);
+        for (int g = 0; g < n_parts; g++) devices[g] = g % n_devices;
+        if (dfr2d_multi_create(&p, n_parts, devices, hs)) die("dfr2d_multi_create", dfr2d_last_error(NULL));
+        free(devices);
+    }
 
     dfr2d_step_info info;
     memset(&info, 0, sizeof info);
@@ -138,20 +144,13 @@ int main(int argc, char **argv) {
         if (dfr2d_multi_set_state(hs, n_parts, Q)) die("dfr2d_multi_set_state", dfr2d_last_error(hs[0]));
         for (int s = 0; s < nsteps && !info.finished; s++) step_once(&call, migrate);
         /* MultiSolver.Residual: signed max over the partitions' own maxima */
-        for (int g = 0; g < n_parts; g++) {
-            double r[4];
-            if (dfr2d_residual(hs[g], r)) die("dfr2d_residual", dfr2d_last_error(hs[g]));
-            for (int v = 0; v < 4; v++)
-                if (g == 0 || r[v] > maxR[v]) maxR[v] = r[v];
-        }
+        if (dfr2d_multi_residual(hs, n_parts, maxR)) die("dfr2d_multi_residual", dfr2d_last_error(hs[0]));
         memset(Q, 0, (size_t)qbytes);
         if (dfr2d_multi_get_state(hs, n_parts, Q)) die("dfr2d_multi_get_state", dfr2d_last_error(hs[0]));
     }
     int64_t launches = 0;
-    for (int g = 0; g < n_parts; g++) {
-        launches += dfr2d_launch_count(hs[g]);
-        dfr2d_destroy(hs[g]);
-    }
+    for (int g = 0; g < n_parts; g++) launches += dfr2d_launch_count(hs[g]);
+    dfr2d_multi_destroy(hs, n_parts);
 
     f = fopen(argv[2], "wb");
     if (!f) die("cannot open output", argv[2]);

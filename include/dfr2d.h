@@ -258,6 +258,14 @@ int dfr2d_stage_wave(dfr2d_handle *h, int rk);   /* connected hosts: put + gathe
  * the edges that touch no ghost column runs while the halo is in flight.  No host synchronisation inside the call;
  * `info` (may be NULL) is read back from partition 0 at the end.  Results are bitwise those of a single partition. */
 int dfr2d_multi_step(dfr2d_handle **hs, int n, int nsteps, dfr2d_step_info *info);
+/* The same through one call each (the shape SURVEY.md 8(b) gives the boundary: one create for the run, the fan-out over the
+ * GPUs inside the library): hs_out[g] = partition g of n_parts on devices[g]; devices = NULL spreads them round-robin over
+ * the visible devices.  On failure nothing is left allocated and dfr2d_last_error(NULL) has the message.
+ * dfr2d_multi_residual = the signed maximum over the partitions of dfr2d_residual (PrintUpdate's loop, euler.go:823-829). */
+int dfr2d_multi_create(const dfr2d_problem *p, int n_parts, const int *devices, dfr2d_handle **hs_out);
+void dfr2d_multi_destroy(dfr2d_handle **hs, int n);
+int dfr2d_multi_residual(dfr2d_handle **hs, int n, double maxR[4]);
+
 /* c.Q <-> all partitions of this process; the copies of the n devices cross PCIe concurrently */
 int dfr2d_multi_set_state(dfr2d_handle **hs, int n, const double *Q);
 int dfr2d_multi_get_state(dfr2d_handle **hs, int n, double *Q);

@@ -259,3 +259,28 @@ def test_makefile_builds_with_the_flags_of_the_build_entry():
     flags = re.search(r"^NVCCFLAGS := (.*)$", mk, re.M).group(1).split()
     assert flags == g.NVCC_FLAGS
     assert "arch=compute_100a,code=sm_100a" in flags and "-lineinfo" in flags
+
+
+def test_multi_create_argument_validation_and_loud_failure_without_a_device():
+    """dfr2d_multi_create (one create for the run): bad arguments are refused, and on a machine without a
+    GPU the call fails with the CUDA error and leaves every handle slot NULL -- there is no CPU path behind it."""
+    import ctypes as C
+    from conftest import _cuda_device_count
+    from gocfd_b200 import lib
+    l = lib.load()
+    c = _case(1, structured_tri_mesh(4, 3))
+    s, keep = lib.problem_struct(c.problem)
+    hs = (C.c_void_p * 3)()
+    assert l.dfr2d_multi_create(C.byref(s), 0, None, hs) == 1
+    assert b"bad arguments" in l.dfr2d_last_error(None)
+    assert l.dfr2d_multi_create(None, 2, None, hs) == 1
+    if _cuda_device_count() == 0:
+        for devices in (None, (C.c_int32 * 3)(0, 0, 0)):
+            hs = (C.c_void_p * 3)(1, 1, 1)
+            assert l.dfr2d_multi_create(C.byref(s), 3, devices, hs) != 0
+            assert l.dfr2d_last_error(None)
+            if devices is not None:
+                assert all(h is None for h in hs)
+    l.dfr2d_multi_destroy(None, 0)          # tolerated
+    assert l.dfr2d_multi_residual(None, 2, None) == 1
+    del keep
