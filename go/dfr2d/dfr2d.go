@@ -245,6 +245,16 @@ func (s *Solver) GradientField(c *Euler2D.Euler, ff Euler2D.FlowFunction) []floa
 	return out
 }
 
+// HilbertOrder returns order[new] = old element along a Hilbert curve through the rank-normalised element centroids: apply
+// it to EToV right after the mesh is read (before NewDFR2D) so that the contiguous PartitionMap ranges are spatially compact.
+func HilbertOrder(EToV []int32, VX, VY []float64) []int32 {
+	order := make([]int32, len(EToV)/3)
+	if rc := C.dfr2d_hilbert_order(C.int64_t(len(order)), C.int64_t(len(VX)), i32(EToV), d(VX), d(VY), i32(order)); rc != 0 {
+		panic(fmt.Errorf("dfr2d_hilbert_order: %s", C.GoString(C.dfr2d_last_error(nil))))
+	}
+	return order
+}
+
 func (s *Solver) Close() { C.dfr2d_destroy(s.h); s.h = nil }
 
 // MultiSolver drives one handle per GPU from a single Go process -- the shape of the reference's controller goroutine

@@ -2283,6 +2283,51 @@ extern "C" int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, co
     return 0;
 }
 
+// Host-only: elements ordered along a Hilbert curve through their centroids.  The coordinates are replaced by their RANKS
+// first (position in the sorted list, scaled to 16 bits), so the curve resolves the thin cells at an airfoil surface as
+// well as the far field; ties are broken by the element index, which makes the order a pure function of the mesh.
+extern "C" int dfr2d_hilbert_order(int64_t K, int64_t NV, const int32_t *EToV, const double *VX, const double *VY, int32_t *order) {
+    if (K <= 0 || NV <= 0 || !EToV || !VX || !VY || !order) { g_create_error = "bad hilbert request"; return 1; }
+    std::vector<double> cx((size_t)K), cy((size_t)K);
+    for (int64_t k = 0; k < K; k++) {
+        double sx = 0.0, sy = 0.0;
+        for (int v = 0; v < 3; v++) {
+            const int32_t id = EToV[3 * k + v];
+            if (id < 0 || id >= NV) { g_create_error = "hilbert request: vertex id out of range"; return 1; }
+            sx += VX[id]; sy += VY[id];
+        }
+        cx[(size_t)k] = sx; cy[(size_t)k] = sy;      // 3 x centroid: the ranks are the same
+    }
+    constexpr int64_t kSide = 65536;
+    auto ranks = [&](const std::vector<double> &c, std::vector<int64_t> &r) {
+        std::vector<int32_t> idx((size_t)K);
+        for (int64_t k = 0; k < K; k++) idx[(size_t)k] = (int32_t)k;
+        std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return c[a] != c[b] ? c[a] < c[b] : a < b; });
+        r.resize((size_t)K);
+        for (int64_t pos = 0; pos < K; pos++) r[(size_t)idx[(size_t)pos]] = pos * (kSide - 1) / std::max<int64_t>(K - 1, 1);
+    };
+    std::vector<int64_t> rx, ry, d((size_t)K);
+    ranks(cx, rx);
+    ranks(cy, ry);
+    for (int64_t k = 0; k < K; k++) {
+        int64_t x = rx[(size_t)k], y = ry[(size_t)k], dd = 0;
+        for (int64_t sft = kSide / 2; sft > 0; sft /= 2) {
+            const int64_t bx = (x & sft) ? 1 : 0, by = (y & sft) ? 1 : 0;
+            dd += sft * sft * ((3 * bx) ^ by);
+            if (by == 0) {                       // rotate the quadrant
+                if (bx == 1) { x = kSide - 1 - x; y = kSide - 1 - y; }
+                std::swap(x, y);
+            }
+        }
+        d[(size_t)k] = dd;
+    }
+    std::vector<int32_t> idx((size_t)K);
+    for (int64_t k = 0; k < K; k++) idx[(size_t)k] = (int32_t)k;
+    std::sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return d[a] != d[b] ? d[a] < d[b] : a < b; });
+    for (int64_t k = 0; k < K; k++) order[k] = idx[(size_t)k];
+    return 0;
+}
+
 #ifdef DFR2D_PIPE_TIMING
 extern "C" int dfr2d_debug_pipe_clocks(unsigned long long out[8], int reset) {
     cudaMemcpyFromSymbol(out, g_pipe_clk, 8 * sizeof(unsigned long long));

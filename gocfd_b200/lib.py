@@ -54,7 +54,7 @@ EXPORTS = [
     "dfr2d_exchange_counts", "dfr2d_exchange_buffers", "dfr2d_plan_vertices", "dfr2d_plot_field", "dfr2d_init_state", "dfr2d_rcm_order", "dfr2d_grad_mma_table", "dfr2d_multi_step", "dfr2d_mma_diss_table",
     "dfr2d_peer_export", "dfr2d_peer_connect", "dfr2d_peer_enable", "dfr2d_multi_set_state", "dfr2d_multi_get_state",
     "dfr2d_set_clock", "dfr2d_epsilon_field", "dfr2d_create_window", "dfr2d_plan_create_window", "dfr2d_stage_wave", "dfr2d_multi_step_profile",
-    "dfr2d_capture_edge_values", "dfr2d_gradient_field", "dfr2d_multi_create", "dfr2d_multi_destroy", "dfr2d_multi_residual",
+    "dfr2d_capture_edge_values", "dfr2d_gradient_field", "dfr2d_multi_create", "dfr2d_multi_destroy", "dfr2d_multi_residual", "dfr2d_hilbert_order",
     "dfr2d_plan_create", "dfr2d_plan_destroy", "dfr2d_plan_sizes", "dfr2d_plan_edges", "dfr2d_plan_halo",
 ]
 
@@ -110,6 +110,7 @@ def load():
     lib.dfr2d_plan_edges.argtypes = [H, _ip, _ip, _ip, lp, _ip]
     lib.dfr2d_plan_halo.argtypes = [H, lp, lp, lp, _ip, _ip, _ip, _ip]
     lib.dfr2d_rcm_order.argtypes = [C.c_int64, C.c_int64, _ip, _ip, _ip, _ip]
+    lib.dfr2d_hilbert_order.argtypes = [C.c_int64, C.c_int64, _ip, _dp, _dp, _ip]
     lib.dfr2d_mma_diss_table.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_int64]
     lib.dfr2d_mma_diss_table.restype = C.c_int64
     lib.dfr2d_multi_step.argtypes = [C.POINTER(H), C.c_int, C.c_int, C.POINTER(StepInfo)]
@@ -260,6 +261,19 @@ def rcm_order(problem):
     rc = lib.dfr2d_rcm_order(problem.K, problem.NE, _i(kl), _i(kr), _i(nc), _i(order))
     if rc != 0:
         raise Dfr2dError("dfr2d_rcm_order failed (%d): %s" % (rc, lib.dfr2d_last_error(None).decode()))
+    return order
+
+
+def hilbert_order(etov, vx, vy):
+    """order[new] = old element along a Hilbert curve through the rank-normalised element centroids (host only)."""
+    lib = load()
+    ev = np.ascontiguousarray(etov, dtype=np.int32).reshape(-1, 3)
+    x = np.ascontiguousarray(vx, dtype=np.float64)
+    y = np.ascontiguousarray(vy, dtype=np.float64)
+    order = np.zeros(ev.shape[0], dtype=np.int32)
+    rc = lib.dfr2d_hilbert_order(ev.shape[0], x.shape[0], _i(ev), _d(x), _d(y), _i(order))
+    if rc != 0:
+        raise Dfr2dError("dfr2d_hilbert_order failed (%d): %s" % (rc, lib.dfr2d_last_error(None).decode()))
     return order
 
 

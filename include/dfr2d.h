@@ -300,6 +300,13 @@ int dfr2d_plan_vertices(const dfr2d_plan *pl, int64_t *counts, int32_t *vertex_i
 int dfr2d_rcm_order(int64_t K, int64_t NE, const int32_t *edge_kL, const int32_t *edge_kR, const int32_t *edge_nconn,
                     int32_t *order);
 
+/* Host-only (no CUDA), the stronger of the two orderings on the reference's airfoil meshes: order[new index] = old element
+ * along a Hilbert curve through the element centroids, with each coordinate replaced by its rank so that the curve
+ * resolves surface cells and far field alike.  Takes what the host holds right after the mesh is read (EToV = [K x 3],
+ * VX, VY = [NV]).  Cut edges of the contiguous Split1D ranges at 8 partitions: nacaAirfoil-base 10,983 as numbered by the
+ * mesh generator, 1,020 after dfr2d_rcm_order, 606 after this; mesh_NACA0012_inv 2,973 / 1,104 / 582. */
+int dfr2d_hilbert_order(int64_t K, int64_t NV, const int32_t *EToV, const double *VX, const double *VY, int32_t *order);
+
 /* Host-only (no CUDA): the operator table the tensor-core gradient kernel (k_grad_mma, DFR2D_GRAD_KERNEL=2) stages in
  * shared memory -- DFR.FluxElement.Div (raviart_thomas_element.go:249-297) cut to the rows and metric blocks that
  * GetSolutionGradientUsingRTElement (euler.go:864-918) consumes, in DMMA.8x8x4 A-fragment lane order, followed by the

@@ -284,3 +284,75 @@ def test_multi_create_argument_validation_and_loud_failure_without_a_device():
     l.dfr2d_multi_destroy(None, 0)          # tolerated
     assert l.dfr2d_multi_residual(None, 2, None) == 1
     del keep
+
+
+def _hilbert_reference(etov, vx, vy):
+    """numpy restatement of dfr2d_hilbert_order: rank-normalised centroids, canonical xy -> d of a 65536^2 Hilbert curve."""
+    ev = np.asarray(etov).reshape(-1, 3)
+    k = ev.shape[0]
+    side = 65536
+
+    def rank(c):
+        idx = np.lexsort((np.arange(k), c))
+        r = np.empty(k, dtype=np.int64)
+        r[idx] = np.arange(k, dtype=np.int64) * (side - 1) // max(k - 1, 1)
+        return r
+
+    cx = (vx[ev[:, 0]] + vx[ev[:, 1]]) + vx[ev[:, 2]]
+    cy = (vy[ev[:, 0]] + vy[ev[:, 1]]) + vy[ev[:, 2]]
+    x, y = rank(cx), rank(cy)
+    d = np.zeros(k, dtype=np.int64)
+    s = side // 2
+    while s > 0:
+        bx, by = ((x & s) > 0).astype(np.int64), ((y & s) > 0).astype(np.int64)
+        d += s * s * ((3 * bx) ^ by)
+        flip = (by == 0) & (bx == 1)
+        x, y = np.where(flip, side - 1 - x, x), np.where(flip, side - 1 - y, y)
+        x, y = np.where(by == 0, y, x), np.where(by == 0, x, y)
+        s //= 2
+    return np.lexsort((np.arange(k), d)).astype(np.int32)
+
+
+@pytest.mark.parametrize("name", ["mesh_NACA0012_inv.su2", "nacaAirfoil-base.su2"])
+def test_hilbert_order_beats_rcm_on_the_airfoil_meshes(name):
+    """dfr2d_hilbert_order (host only): bit-exact against its numpy restatement, a permutation, and -- on both airfoil
+    meshes the reference ships -- fewer cut edges of the Split1D ranges than RCM at 4 and 8 partitions; the plans of the
+    renumbered mesh carry exactly those cuts."""
+    from gocfd_b200 import lib
+    from gocfd_b200.host import readfiles as rf
+    mesh = rf.read_mesh(mesh_path(name))
+    c = _case(1, mesh, InitType="Freestream")
+    p = c.problem
+    vx, vy = np.asarray(c.DFR.VX, dtype=np.float64), np.asarray(c.DFR.VY, dtype=np.float64)
+    order = lib.hilbert_order(p.EToV, vx, vy)
+    assert sorted(order.tolist()) == list(range(p.K))
+    np.testing.assert_array_equal(order, _hilbert_reference(p.EToV, vx, vy))
+
+    def cut_edges(prob, n_parts):
+        pm = PartitionMap(n_parts, prob.K)
+        sh = prob.edge_nconn == 2
+        bounds = np.array([pm.get_bucket_range(b)[1] for b in range(n_parts)])
+        bl, br = np.searchsorted(bounds, prob.edge_kL[sh], side="right"), np.searchsorted(bounds, prob.edge_kR[sh], side="right")
+        return int((bl != br).sum())
+
+    p_h = _case(1, rf.renumber_elements(mesh, order), InitType="Freestream").problem
+    p_r = _case(1, rf.renumber_elements(mesh, lib.rcm_order(p)), InitType="Freestream").problem
+    for n_parts in (4, 8):
+        orig, rcm, hil = cut_edges(p, n_parts), cut_edges(p_r, n_parts), cut_edges(p_h, n_parts)
+        assert hil < 0.75 * rcm < 0.75 * orig, (n_parts, orig, rcm, hil)
+    plans = [lib.Plan(p_h, 8, r) for r in range(8)]
+    assert sum(pl.n_cut for pl in plans) == 2 * cut_edges(p_h, 8)
+    print("%s: cut edges at 8 partitions  original %d  rcm %d  hilbert %d" % (name, cut_edges(p, 8), cut_edges(p_r, 8), cut_edges(p_h, 8)))
+
+
+def test_hilbert_order_rejects_bad_requests():
+    import ctypes as C
+    from gocfd_b200 import lib
+    l = lib.load()
+    ev = np.array([0, 1, 7], dtype=np.int32)
+    v = np.zeros(3)
+    o = np.zeros(1, dtype=np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    assert l.dfr2d_hilbert_order(1, 3, ev.ctypes.data_as(ip), v.ctypes.data_as(dp), v.ctypes.data_as(dp), o.ctypes.data_as(ip)) == 1
+    assert b"out of range" in l.dfr2d_last_error(None)
+    assert l.dfr2d_hilbert_order(0, 3, None, None, None, None) == 1
